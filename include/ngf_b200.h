@@ -1,0 +1,217 @@
+/*
+ * ngf_b200.h — C ABI of libngf_b200.so: the B200 (sm_100a) implementation of the volumetric-rendering hot
+ * path of fnzhan/Neural-Gauge-Fields (TriPlane / InfoInv sub-projects).
+ *
+ * The reference is pure Python/PyTorch and has no FFI; its "plugin" seam is the model class that
+ * `eval(args.model_name)(**kwargs)` instantiates (TriPlane/main.py:37,226,230) and whose forward() the
+ * `renderer` chunk loop calls (TriPlane/main.py:60-71).  Each entry point below states the reference
+ * interface it replaces (paths relative to /root/reference).  INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - every function returns 0 (NGF_OK) or a negative NgfStatus; ngf_last_error() gives the thread-local text.
+ *   - "dev" pointers are CUDA device pointers on the handle's device; "host" pointers are CPU memory
+ *     (pinned memory makes the copies asynchronous and fast; pageable memory also works).
+ *   - the caller owns every buffer it passes; the library copies what it needs during ngf_field_pack and never
+ *     retains caller pointers after a call returns.  The handle owns its packed shadows and workspaces.
+ *   - all device work is enqueued on the `stream` argument (a cudaStream_t passed as void*; NULL = default
+ *     stream) and is asynchronous with respect to the host unless stated otherwise.  No host synchronisation
+ *     happens inside ngf_field_render (the reference forward() has ~15 per 4096-ray chunk).
+ *   - one handle per device; a handle may be used from one stream at a time.
+ */
+#ifndef NGF_B200_H_
+#define NGF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGF_ABI_VERSION 1
+
+typedef enum NgfStatus {
+  NGF_OK = 0,
+  NGF_EINVAL = -1,       /* bad shape / stride / null pointer / alignment */
+  NGF_ECUDA = -2,        /* CUDA runtime error; text in ngf_last_error()   */
+  NGF_EUNSUPPORTED = -3, /* configuration outside what the kernels are built for */
+  NGF_ENOMEM = -4
+} NgfStatus;
+
+typedef enum NgfVariant {
+  NGF_TRIPLANE = 0, /* TriPlane/models/Field.py: 64-ch planes (16 density + 48 appearance), learned gauge planes */
+  NGF_INFOINV = 1   /* InfoInv/models/Field.py: 96-ch planes (24 + 72), sinusoidal phase product, density MLP   */
+} NgfVariant;
+
+typedef enum NgfMlpImpl {
+  NGF_MLP_TCGEN05 = 0, /* colour MLP on 5th-gen tensor cores (fp16 operands, fp32 accumulate in TMEM) */
+  NGF_MLP_SIMT = 1     /* same packed weights on CUDA cores; debugging / cross-check only            */
+} NgfMlpImpl;
+
+/* A dense linear layer y = W x + b in PyTorch nn.Linear layout: w is [out][in] row-major fp32, b is [out]
+ * (b may be NULL for a bias-free layer). */
+typedef struct NgfLinear {
+  const float* w;
+  const float* b;
+  int32_t in_dim;
+  int32_t out_dim;
+} NgfLinear;
+
+/*
+ * Field description: the parameters and attributes Base.forward() reads
+ * (TriPlane/models/FieldBase.py:251-312, InfoInv/models/FieldBase.py:228-282).  Parameter pointers may be host
+ * or device memory (they are copied with cudaMemcpyDefault while packing).  All arrays are fp32 in the
+ * reference's own NCHW layouts, so a state_dict tensor's data_ptr can be passed as is.
+ */
+typedef struct NgfFieldDesc {
+  int32_t variant; /* NgfVariant */
+
+  /* plane_xy [1,C,Hy,Wx], plane_yz [1,C,Hz,Wy], plane_xz [1,C,Hz,Wx] (Field.py:19-21; non-square after
+   * up_sampling/shrink, Field.py:108-132) */
+  const float* plane[3];
+  int32_t plane_h[3];
+  int32_t plane_w[3];
+  int32_t plane_c;   /* 64 (TriPlane) | 96 (InfoInv) */
+  int32_t density_c; /* 16 | 24: channels [0,density_c) feed density, the rest feed colour */
+
+  /* gauge_xy / gauge_yz / gauge_xz [1,2,Hg,Wg] (TriPlane/models/Field.py:23-26); uploaded when all three are
+   * non-NULL.  gauge_on = (iteration >= gauge_start), TriPlane/models/Field.py:58: initial value of the switch
+   * ngf_field_set_gauge() flips. */
+  const float* gauge[3];
+  int32_t gauge_h[3];
+  int32_t gauge_w[3];
+  int32_t gauge_on;
+
+  /* rgb_decoder (networks.py:12-32): basis (bias-free F x F), mlp.0 (F+3+12 -> 64), mlp.2 (64 -> 64),
+   * mlp.4 (64 -> 3); view_pe = 2. */
+  NgfLinear rgb_basis;
+  NgfLinear rgb_l1, rgb_l2, rgb_l3;
+  int32_t view_pe;
+
+  /* density head: TriPlane: density_decoder Linear(48,1) in dens_l1 (dens_l2/l3 unused, Field.py:29);
+   * InfoInv: density_decoder.mlp.{0,2,4} = 72->32->32->1 (InfoInv/models/networks.py:34-54). */
+  NgfLinear dens_l1, dens_l2, dens_l3;
+  float density_shift; /* feature2density default -10 (Field.py:48) */
+  int32_t infoinv;     /* forward(..., infoinv=True): multiply plane features by the phase code */
+
+  /* Base attributes (FieldBase.py:45-74).  inv_aabb_size / step_size must be the fp32 values torch computed
+   * (Base.invaabbSize, Base.stepSize) so every mask decision rounds exactly like the reference. */
+  float aabb[6];          /* aabb[0] = min xyz, aabb[1] = max xyz */
+  float inv_aabb_size[3]; /* 2 / (aabb[1]-aabb[0]) */
+  float step_size;
+  int32_t n_samples; /* Base.nSamples: used when N_samples <= 0 */
+  float near_t, far_t;
+  float distance_scale;
+  float weight_thres; /* rayMarch_weight_thres */
+
+  /* AlphaGridMask (FieldBase.py:22-40) or NULL: alpha_volume is the [D][H][W] fp32 {0,1} volume,
+   * alpha_dims = {W, H, D}, alpha_aabb its own box, alpha_inv = AlphaGridMask.invgridSize (fp32 from torch). */
+  const float* alpha_volume;
+  int32_t alpha_dims[3];
+  float alpha_aabb[6];
+  float alpha_inv[3];
+} NgfFieldDesc;
+
+/* Counters of the last render (device-side sums copied on request; forces a stream sync). */
+typedef struct NgfStats {
+  uint64_t rays;
+  uint64_t samples_in_box;  /* samples inside the box after the conservative range clip   */
+  uint64_t samples_density; /* density evaluations: valid samples (bbox and alpha mask)    */
+  uint64_t samples_colour;  /* colour-MLP evaluations: weight > weight_thres               */
+  uint64_t mlp_tiles;       /* 128-sample tensor-core tiles issued                         */
+} NgfStats;
+
+typedef struct NgfField_* NgfField;
+
+int ngf_abi_version(void);
+const char* ngf_last_error(void);
+/* Number of kernels this library has launched in the calling process so far (bench.py's gpu_launches). */
+uint64_t ngf_launch_count(void);
+
+/*
+ * Build the device-side shadows of a field on `device`: channels-last fp32 density texels, channels-last fp16
+ * appearance texels, float2 gauge texels, bit-packed occupancy grid, folded (basis . mlp.0) fp16 weights in
+ * tcgen05 shared-memory layout.
+ * Replaces: TriPlane.__init__/init_model + Base.load (Field.py:14-32, FieldBase.py:111-116) as far as the
+ * render path is concerned.  Synchronous.
+ */
+int ngf_field_pack(const NgfFieldDesc* desc, int device, NgfField* out);
+/* Re-read parameters after an optimizer step / load_state_dict: same shapes required. Synchronous. */
+int ngf_field_repack(NgfField f, const NgfFieldDesc* desc);
+void ngf_field_free(NgfField f);
+
+/*
+ * Render rays.  Replaces Base.forward(rays_chunk, white_bg, is_train=False, N_samples, ...) for a whole
+ * frame at once (FieldBase.py:251-312) and therefore also the chunk loop `renderer` (main.py:60-71).
+ *   rays_dev   [R][ray_stride] fp32, columns 0-2 origin, 3-5 direction (ray_stride >= 6; the LAST column feeds
+ *              the depth background term exactly as FieldBase.py:306 does)
+ *   n_samples  N_samples argument (<= 0: use desc.n_samples)
+ *   rgb_dev    [R][3] fp32 out (rgb_map), depth_dev [R] fp32 out (depth_map); acc_dev [R] fp32 out or NULL
+ *   tile_w     0, or the image width when rays are the row-major pixels of an image: lets the kernel map
+ *              warps to 8x4 pixel blocks for texel locality (results do not depend on it)
+ */
+int ngf_field_render(NgfField f, const float* rays_dev, int64_t n_rays, int32_t ray_stride, int32_t n_samples,
+                     int32_t white_bg, int32_t tile_w, float* rgb_dev, float* depth_dev, float* acc_dev,
+                     int32_t mlp_impl, void* stream);
+
+/*
+ * Same through HOST buffers: H2D of the rays, render, D2H of rgb/depth, chunked and overlapped on internal
+ * streams; returns after the results are in rgb_host/depth_host.  This is the call the reference-facing
+ * `renderer(rays_cpu, field, ...)` maps to when rays live on the CPU (main.py:64-65 does the H2D per chunk).
+ */
+int ngf_field_render_host(NgfField f, const float* rays_host, int64_t n_rays, int32_t ray_stride,
+                          int32_t n_samples, int32_t white_bg, int32_t tile_w, float* rgb_host,
+                          float* depth_host, int32_t mlp_impl);
+
+/* Per-call switches of forward(): TriPlane `iteration >= gauge_start` (TriPlane/models/Field.py:58) and InfoInv
+ * `infoinv=` (InfoInv/models/FieldBase.py:228).  They only flip a flag in the handle; no repack. */
+int ngf_field_set_gauge(NgfField f, int32_t on);
+int ngf_field_set_infoinv(NgfField f, int32_t on);
+
+/* Copy the counters of the last render on `stream` (synchronises that stream). */
+int ngf_field_stats(NgfField f, NgfStats* out, void* stream);
+
+/*
+ * Point-wise queries (API parity with the reference's public methods).
+ *  ngf_field_sample_ray : Base.sample_ray, eval branch (FieldBase.py:118-137): pts [R][S][3], t [R][S],
+ *                         inside [R][S] (uint8 0/1).
+ *  ngf_field_alpha_keep : AlphaGridMask.sample_alpha(...) > 0 (FieldBase.py:33-37): world pts [N][3] -> uint8.
+ *  ngf_field_gauge      : Base.normalize_coord is NOT applied: in = normalised xyz [N][3];
+ *                         out xy/yz/xz [N][2] each = TriPlane.compute_gauge (Field.py:53-75) or
+ *                         InfoInv transform (InfoInv/models/Field.py:43-50).
+ *  ngf_field_density    : compute_density(xy, yz, xz) (Field.py:77-91 / InfoInv Field.py:52-70) -> sigma [N].
+ *  ngf_field_rgb        : compute_rgb(xy, yz, xz, viewdirs) (Field.py:93-105 / InfoInv Field.py:72-89) -> [N][3].
+ *  ngf_field_sigma_world: compute_alpha's inner part (FieldBase.py:140-156): world pts -> sigma with the alpha
+ *                         mask applied and gauge optional (the reference passes iteration=-1, i.e. off).
+ */
+int ngf_field_sample_ray(NgfField f, const float* rays_dev, int64_t n_rays, int32_t ray_stride, int32_t n_samples,
+                         float* pts_dev, float* t_dev, uint8_t* inside_dev, void* stream);
+int ngf_field_alpha_keep(NgfField f, const float* pts_dev, int64_t n, uint8_t* keep_dev, void* stream);
+int ngf_field_gauge(NgfField f, const float* xyz_norm_dev, int64_t n, int32_t gauge_on, float* xy_dev,
+                    float* yz_dev, float* xz_dev, void* stream);
+int ngf_field_density(NgfField f, const float* xy_dev, const float* yz_dev, const float* xz_dev, int64_t n,
+                      float* sigma_dev, void* stream);
+int ngf_field_rgb(NgfField f, const float* xy_dev, const float* yz_dev, const float* xz_dev,
+                  const float* viewdirs_dev, int64_t n, float* rgb_dev, int32_t mlp_impl, void* stream);
+int ngf_field_sigma_world(NgfField f, const float* pts_dev, int64_t n, int32_t use_gauge, float* sigma_dev,
+                          void* stream);
+
+/*
+ * Multi-GPU helpers (the reference has no distributed code).  Rays of a frame are dealt to
+ * ranks in interleaved blocks of `block` rays: global ray g belongs to rank (g / block) % world.
+ *  ngf_shard_count   : number of rays rank owns.
+ *  ngf_shard_gather  : dst[i] = src[global index of the i-th ray of rank] for a [n][width] fp32 device array
+ *  ngf_shard_scatter : inverse of the all-gather: src is [world][max_shard][width] (rank-major, as
+ *                      ncclAllGather leaves it), dst [n][width] in frame order.
+ */
+int64_t ngf_shard_count(int64_t n_rays, int32_t block, int32_t rank, int32_t world);
+int ngf_shard_gather(const float* src_dev, int64_t n_rays, int32_t width, int32_t block, int32_t rank,
+                     int32_t world, float* dst_dev, void* stream);
+int ngf_shard_scatter(const float* src_dev, int64_t n_rays, int32_t width, int32_t block, int32_t world,
+                      int64_t max_shard, float* dst_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGF_B200_H_ */

@@ -1,0 +1,599 @@
+// ngf_abi.cu — the C ABI of libngf_b200.so (include/ngf_b200.h): handle management, parameter packing, render
+// entry points.  Host code only; kernels live in ngf_kernels.cu.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/ngf_b200.h"
+#include "ngf_internal.h"
+
+using namespace ngf;
+
+// ---------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(expr)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess) return fail(NGF_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                                       __LINE__);                                                         \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------------------
+struct HostChunk {            // one in-flight chunk of the host-buffer render path
+  cudaStream_t stream = nullptr;
+  float* rays = nullptr;
+  float* rgb = nullptr;
+  float* depth = nullptr;
+  float* acc = nullptr;
+  unsigned int* counters = nullptr;
+};
+
+struct NgfField_ {
+  int device = 0;
+  int num_sms = 0;
+  int lbo_swap = 0;
+  int has_gauge = 0;
+  FieldDev dev{};
+  int n_samples_default = 0;
+  int plane_c = 0;
+  // owned device memory
+  float* dens[3] = {nullptr, nullptr, nullptr};
+  __half* app[3] = {nullptr, nullptr, nullptr};
+  float2* gauge[3] = {nullptr, nullptr, nullptr};
+  uint32_t* occ = nullptr;
+  float* dmlp = nullptr;
+  __half* w1p = nullptr;
+  __half* w2p = nullptr;
+  float* tail = nullptr;
+  // render workspace
+  float* acc_ws = nullptr;
+  long long acc_cap = 0;
+  unsigned int* counters = nullptr;   // [0] tile counter, [2..9] = 4 x u64 stats
+  // host path
+  HostChunk chunk[2];
+  long long chunk_cap = 0;
+  int chunk_stride = 0;
+};
+
+static const int kCounterBytes = 64;
+
+static void free_chunks(NgfField_* h) {
+  for (auto& c : h->chunk) {
+    if (c.stream) cudaStreamDestroy(c.stream);
+    cudaFree(c.rays); cudaFree(c.rgb); cudaFree(c.depth); cudaFree(c.acc); cudaFree(c.counters);
+    c = HostChunk{};
+  }
+  h->chunk_cap = 0;
+}
+
+static void free_all(NgfField_* h) {
+  for (int i = 0; i < 3; ++i) { cudaFree(h->dens[i]); cudaFree(h->app[i]); cudaFree(h->gauge[i]); }
+  cudaFree(h->occ); cudaFree(h->dmlp); cudaFree(h->w1p); cudaFree(h->w2p); cudaFree(h->tail);
+  cudaFree(h->acc_ws); cudaFree(h->counters);
+  free_chunks(h);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// validation
+// ---------------------------------------------------------------------------------------------------------
+static int check_linear(const NgfLinear& l, int in_dim, int out_dim, bool need_bias, const char* name) {
+  if (!l.w) return fail(NGF_EINVAL, "%s.w is NULL", name);
+  if (need_bias && !l.b) return fail(NGF_EINVAL, "%s.b is NULL", name);
+  if (l.in_dim != in_dim || l.out_dim != out_dim)
+    return fail(NGF_EUNSUPPORTED, "%s is %dx%d, kernels are built for %dx%d", name, l.out_dim, l.in_dim, out_dim, in_dim);
+  return NGF_OK;
+}
+
+static int validate(const NgfFieldDesc* d) {
+  if (!d) return fail(NGF_EINVAL, "desc is NULL");
+  if (d->variant != NGF_TRIPLANE && d->variant != NGF_INFOINV) return fail(NGF_EINVAL, "unknown variant %d", d->variant);
+  const int C = d->variant == NGF_TRIPLANE ? 64 : 96, DC = d->variant == NGF_TRIPLANE ? 16 : 24;
+  if (d->plane_c != C || d->density_c != DC)
+    return fail(NGF_EUNSUPPORTED, "plane_c=%d density_c=%d; variant %d is built for %d/%d", d->plane_c, d->density_c,
+                d->variant, C, DC);
+  for (int i = 0; i < 3; ++i) {
+    if (!d->plane[i]) return fail(NGF_EINVAL, "plane[%d] is NULL", i);
+    if (d->plane_h[i] < 1 || d->plane_w[i] < 1 || d->plane_h[i] > 32768 || d->plane_w[i] > 32768)
+      return fail(NGF_EINVAL, "plane[%d] has shape %dx%d", i, d->plane_h[i], d->plane_w[i]);
+    if (d->variant == NGF_TRIPLANE && d->gauge_on && !d->gauge[i])
+      return fail(NGF_EINVAL, "gauge_on but gauge[%d] is NULL", i);
+    if (d->variant == NGF_TRIPLANE && d->gauge[i] && (d->gauge_h[i] < 1 || d->gauge_w[i] < 1))
+      return fail(NGF_EINVAL, "gauge[%d] has shape %dx%d", i, d->gauge_h[i], d->gauge_w[i]);
+  }
+  const int F = 3 * (C - DC);
+  if (d->view_pe != 2) return fail(NGF_EUNSUPPORTED, "view_pe=%d (built for 2)", d->view_pe);
+  int rc;
+  if ((rc = check_linear(d->rgb_basis, F, F, false, "rgb_basis"))) return rc;
+  if ((rc = check_linear(d->rgb_l1, F + 15, 64, true, "rgb_l1"))) return rc;
+  if ((rc = check_linear(d->rgb_l2, 64, 64, true, "rgb_l2"))) return rc;
+  if ((rc = check_linear(d->rgb_l3, 64, 3, true, "rgb_l3"))) return rc;
+  if (d->variant == NGF_TRIPLANE) {
+    if ((rc = check_linear(d->dens_l1, 48, 1, true, "dens_l1"))) return rc;
+  } else {
+    if ((rc = check_linear(d->dens_l1, 72, 32, true, "dens_l1"))) return rc;
+    if ((rc = check_linear(d->dens_l2, 32, 32, true, "dens_l2"))) return rc;
+    if ((rc = check_linear(d->dens_l3, 32, 1, true, "dens_l3"))) return rc;
+  }
+  if (!(d->step_size > 0.f)) return fail(NGF_EINVAL, "step_size must be > 0");
+  for (int k = 0; k < 3; ++k)
+    if (!(d->aabb[3 + k] > d->aabb[k])) return fail(NGF_EINVAL, "aabb is empty along axis %d", k);
+  if (d->alpha_volume) {
+    long long n = 1;
+    for (int k = 0; k < 3; ++k) {
+      if (d->alpha_dims[k] < 1 || d->alpha_dims[k] > 2048) return fail(NGF_EINVAL, "alpha_dims[%d]=%d", k, d->alpha_dims[k]);
+      n *= d->alpha_dims[k];
+    }
+    if (n > (1ll << 31)) return fail(NGF_EUNSUPPORTED, "alpha volume larger than 2^31 voxels");
+  }
+  return NGF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// packing
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t dev_alloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)); }
+
+static cudaError_t fetch(std::vector<float>& dst, const float* src, size_t n) {
+  dst.resize(n);
+  return cudaMemcpy(dst.data(), src, n * sizeof(float), cudaMemcpyDefault);
+}
+
+// K-major core-matrix order used by the tcgen05 descriptors: element (row r, col k) of an [rows][K] operand at
+// (k/8)*rows*8 + r*8 + (k%8)   (in halves)
+static void put_kmajor(std::vector<__half>& dst, int rows, int r, int k, float v) {
+  dst[(size_t)(k / 8) * rows * 8 + (size_t)r * 8 + (k % 8)] = __float2half_rn(v);
+}
+
+static int pack_params(NgfField_* h, const NgfFieldDesc* d, bool allocate) {
+  const int V = d->variant;
+  const int C = d->plane_c, DC = d->density_c, AC = C - DC, F = 3 * AC;
+  const int K1 = V == 0 ? Cfg<0>::K1 : Cfg<1>::K1;
+  FieldDev& f = h->dev;
+  f.variant = V;
+  f.infoinv = d->infoinv ? 1 : 0;
+  const bool has_gauge = V == 0 && d->gauge[0] && d->gauge[1] && d->gauge[2];
+  h->has_gauge = has_gauge ? 1 : 0;
+  f.gauge_on = (has_gauge && d->gauge_on) ? 1 : 0;
+  for (int k = 0; k < 3; ++k) {
+    f.lo[k] = d->aabb[k];
+    f.hi[k] = d->aabb[3 + k];
+    f.inv[k] = d->inv_aabb_size[k];
+  }
+  f.step = d->step_size; f.near_t = d->near_t; f.far_t = d->far_t;
+  f.dscale = d->distance_scale; f.wthres = d->weight_thres; f.dshift = d->density_shift;
+  h->n_samples_default = d->n_samples;
+  h->plane_c = C;
+
+  // ---- planes
+  for (int i = 0; i < 3; ++i) {
+    const int H = d->plane_h[i], W = d->plane_w[i];
+    const size_t hw = (size_t)H * W;
+    if (allocate) {
+      CU(dev_alloc(&h->dens[i], hw * DC));
+      CU(dev_alloc(&h->app[i], hw * AC));
+    } else if (H != f.plane[i].H || W != f.plane[i].W) {
+      return fail(NGF_EINVAL, "repack: plane[%d] changed shape (%dx%d -> %dx%d); pack a new handle", i, f.plane[i].H,
+                  f.plane[i].W, H, W);
+    }
+    float* tmp = nullptr;
+    CU(dev_alloc(&tmp, hw * C));
+    cudaError_t e = cudaMemcpy(tmp, d->plane[i], hw * C * sizeof(float), cudaMemcpyDefault);
+    if (e == cudaSuccess) e = launch_pack_plane(tmp, C, H, W, DC, h->dens[i], h->app[i], 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(tmp);
+    CU(e);
+    f.plane[i] = PlaneDev{h->dens[i], h->app[i], H, W, (float)(W - 1), (float)(H - 1)};
+  }
+  // ---- gauge planes
+  for (int i = 0; i < 3; ++i) {
+    if (!has_gauge) { if (allocate) f.gauge[i] = GaugeDev{nullptr, 1, 1, 0.f, 0.f}; continue; }
+    const int H = d->gauge_h[i], W = d->gauge_w[i];
+    const size_t hw = (size_t)H * W;
+    if (allocate || !h->gauge[i]) {
+      if (h->gauge[i]) { cudaFree(h->gauge[i]); h->gauge[i] = nullptr; }
+      CU(dev_alloc(&h->gauge[i], hw));
+    } else if (H != f.gauge[i].H || W != f.gauge[i].W) {
+      return fail(NGF_EINVAL, "repack: gauge[%d] changed shape", i);
+    }
+    float* tmp = nullptr;
+    CU(dev_alloc(&tmp, hw * 2));
+    cudaError_t e = cudaMemcpy(tmp, d->gauge[i], hw * 2 * sizeof(float), cudaMemcpyDefault);
+    if (e == cudaSuccess) e = launch_pack_gauge(tmp, H, W, h->gauge[i], 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(tmp);
+    CU(e);
+    f.gauge[i] = GaugeDev{h->gauge[i], H, W, (float)(W - 1), (float)(H - 1)};
+  }
+  // ---- occupancy grid
+  if (d->alpha_volume) {
+    const long long n = (long long)d->alpha_dims[0] * d->alpha_dims[1] * d->alpha_dims[2];
+    if (h->occ) { cudaFree(h->occ); h->occ = nullptr; }
+    CU(dev_alloc(&h->occ, (size_t)((n + 31) / 32)));
+    float* tmp = nullptr;
+    CU(dev_alloc(&tmp, (size_t)n));
+    cudaError_t e = cudaMemcpy(tmp, d->alpha_volume, (size_t)n * sizeof(float), cudaMemcpyDefault);
+    if (e == cudaSuccess) e = launch_pack_occ(tmp, n, h->occ, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(tmp);
+    CU(e);
+    f.occ = h->occ;
+    f.occ_w = d->alpha_dims[0]; f.occ_h = d->alpha_dims[1]; f.occ_d = d->alpha_dims[2];
+    f.has_occ = 1;
+    for (int k = 0; k < 3; ++k) { f.occ_lo[k] = d->alpha_aabb[k]; f.occ_inv[k] = d->alpha_inv[k]; }
+  } else {
+    if (h->occ) { cudaFree(h->occ); h->occ = nullptr; }
+    f.occ = nullptr; f.has_occ = 0; f.occ_w = f.occ_h = f.occ_d = 1;
+    for (int k = 0; k < 3; ++k) { f.occ_lo[k] = 0.f; f.occ_inv[k] = 0.f; }
+  }
+  // ---- density head
+  std::vector<float> w, b;
+  if (V == 0) {
+    CU(fetch(w, d->dens_l1.w, 48));
+    CU(fetch(b, d->dens_l1.b, 1));
+    memcpy(f.dw, w.data(), 48 * sizeof(float));
+    f.db = b[0];
+    f.dmlp = nullptr;
+  } else {
+    std::vector<float> m(kDmlpFloats, 0.f), w2, b2, w3, b3;
+    CU(fetch(w, d->dens_l1.w, 32 * 72)); CU(fetch(b, d->dens_l1.b, 32));
+    CU(fetch(w2, d->dens_l2.w, 32 * 32)); CU(fetch(b2, d->dens_l2.b, 32));
+    CU(fetch(w3, d->dens_l3.w, 32)); CU(fetch(b3, d->dens_l3.b, 1));
+    for (int j = 0; j < 32; ++j)
+      for (int k = 0; k < 72; ++k) m[(size_t)k * 32 + j] = w[(size_t)j * 72 + k];        // input-major
+    float* p = m.data() + 32 * 72;
+    memcpy(p, b.data(), 32 * 4); p += 32;
+    memcpy(p, w2.data(), 32 * 32 * 4); p += 32 * 32;
+    memcpy(p, b2.data(), 32 * 4); p += 32;
+    memcpy(p, w3.data(), 32 * 4); p += 32;
+    p[0] = b3[0];
+    if (allocate) CU(dev_alloc(&h->dmlp, (size_t)kDmlpFloats));
+    CU(cudaMemcpy(h->dmlp, m.data(), kDmlpFloats * sizeof(float), cudaMemcpyHostToDevice));
+    f.dmlp = h->dmlp;
+    memset(f.dw, 0, sizeof(f.dw));
+    f.db = 0.f;
+  }
+  // ---- colour MLP: fold the bias-free basis into layer 1 (W1' = W1[:, :F] . B), append view columns and b1
+  {
+    std::vector<float> B, W1, b1, W2, b2, W3, b3;
+    CU(fetch(B, d->rgb_basis.w, (size_t)F * F));
+    CU(fetch(W1, d->rgb_l1.w, (size_t)64 * (F + 15))); CU(fetch(b1, d->rgb_l1.b, 64));
+    CU(fetch(W2, d->rgb_l2.w, 64 * 64)); CU(fetch(b2, d->rgb_l2.b, 64));
+    CU(fetch(W3, d->rgb_l3.w, 3 * 64)); CU(fetch(b3, d->rgb_l3.b, 3));
+    std::vector<__half> w1p((size_t)K1 * 64, __float2half_rn(0.f)), w2p((size_t)64 * 64);
+    std::vector<double> row(F);
+    for (int j = 0; j < 64; ++j) {
+      std::fill(row.begin(), row.end(), 0.0);
+      for (int m = 0; m < F; ++m) {
+        const double wjm = W1[(size_t)j * (F + 15) + m];
+        const float* brow = &B[(size_t)m * F];
+        for (int k = 0; k < F; ++k) row[k] += wjm * (double)brow[k];
+      }
+      for (int k = 0; k < F; ++k) put_kmajor(w1p, 64, j, k, (float)row[k]);
+      for (int k = 0; k < 15; ++k) put_kmajor(w1p, 64, j, F + k, W1[(size_t)j * (F + 15) + F + k]);
+      put_kmajor(w1p, 64, j, F + 15, b1[j]);
+      for (int k = 0; k < 64; ++k) put_kmajor(w2p, 64, j, k, W2[(size_t)j * 64 + k]);
+    }
+    std::vector<float> tail(kTailFloats, 0.f);
+    memcpy(tail.data(), W3.data(), 192 * 4);
+    memcpy(tail.data() + 192, b2.data(), 64 * 4);
+    memcpy(tail.data() + 256, b3.data(), 3 * 4);
+    if (allocate) {
+      CU(dev_alloc(&h->w1p, w1p.size()));
+      CU(dev_alloc(&h->w2p, w2p.size()));
+      CU(dev_alloc(&h->tail, tail.size()));
+    }
+    CU(cudaMemcpy(h->w1p, w1p.data(), w1p.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->w2p, w2p.data(), w2p.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->tail, tail.data(), tail.size() * sizeof(float), cudaMemcpyHostToDevice));
+    f.w1p = h->w1p; f.w2p = h->w2p; f.tail = h->tail;
+  }
+  if (allocate) {
+    CU(cudaMalloc(reinterpret_cast<void**>(&h->counters), kCounterBytes));
+    CU(cudaMemset(h->counters, 0, kCounterBytes));
+  }
+  CU(cudaDeviceSynchronize());
+  return NGF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int ngf_abi_version(void) { return NGF_ABI_VERSION; }
+const char* ngf_last_error(void) { return g_err; }
+uint64_t ngf_launch_count(void) { return launch_count(); }
+
+int ngf_field_pack(const NgfFieldDesc* desc, int device, NgfField* out) {
+  if (!out) return fail(NGF_EINVAL, "out is NULL");
+  *out = nullptr;
+  int rc = validate(desc);
+  if (rc) return rc;
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(NGF_EINVAL, "device %d out of range (%d visible)", device, ndev);
+  DeviceGuard g(device);
+  if (!g.ok) return fail(NGF_ECUDA, "cannot select device %d", device);
+  int major = 0;
+  CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) return fail(NGF_EUNSUPPORTED, "device %d has compute capability %d.x; this library is sm_100a only", device, major);
+  NgfField_* h = new NgfField_();
+  h->device = device;
+  CU(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
+  const char* sw = getenv("NGF_UMMA_SWAP");
+  h->lbo_swap = (sw && sw[0] == '1') ? 1 : 0;
+  rc = pack_params(h, desc, true);
+  if (rc) { free_all(h); delete h; return rc; }
+  *out = h;
+  return NGF_OK;
+}
+
+int ngf_field_repack(NgfField h, const NgfFieldDesc* desc) {
+  if (!h) return fail(NGF_EINVAL, "field is NULL");
+  int rc = validate(desc);
+  if (rc) return rc;
+  if (desc->variant != h->dev.variant) return fail(NGF_EINVAL, "repack: variant changed");
+  DeviceGuard g(h->device);
+  if (!g.ok) return fail(NGF_ECUDA, "cannot select device %d", h->device);
+  return pack_params(h, desc, false);
+}
+
+void ngf_field_free(NgfField h) {
+  if (!h) return;
+  DeviceGuard g(h->device);
+  cudaDeviceSynchronize();
+  free_all(h);
+  delete h;
+}
+
+static int render_dev(NgfField h, const float* rays, long long n_rays, int ray_stride, int n_samples, int white_bg,
+                      int tile_w, float* rgb, float* depth, float* acc, unsigned int* counters, bool reset_stats,
+                      int mlp_impl, cudaStream_t st) {
+  if (n_rays == 0) return NGF_OK;
+  RenderArgs a{};
+  a.rays = rays; a.n_rays = n_rays; a.ray_stride = ray_stride;
+  a.S = n_samples > 0 ? n_samples : h->n_samples_default;
+  if (a.S < 1) return fail(NGF_EINVAL, "n_samples resolves to %d", a.S);
+  a.white_bg = white_bg ? 1 : 0;
+  if (tile_w > 0 && n_rays % tile_w == 0) {
+    a.img_w = tile_w; a.img_h = (int)(n_rays / tile_w);
+    a.n_tiles = ((a.img_w + 7) / 8) * ((a.img_h + 3) / 4);
+  } else {
+    a.img_w = 0; a.img_h = 0;
+    a.n_tiles = (int)((n_rays + 31) / 32);
+  }
+  a.rgb = rgb; a.depth = depth; a.acc = acc;
+  a.tile_counter = counters;
+  a.stats = reinterpret_cast<unsigned long long*>(counters + 2);
+  a.lbo_swap = h->lbo_swap;
+  CU(cudaMemsetAsync(counters, 0, reset_stats ? kCounterBytes : 8, st));
+  CU(cudaMemsetAsync(rgb, 0, (size_t)n_rays * 3 * sizeof(float), st));
+  CU(launch_render(h->dev, a, mlp_impl, h->num_sms, st));
+  CU(launch_finalize(rgb, acc, n_rays, a.white_bg, st));
+  return NGF_OK;
+}
+
+int ngf_field_render(NgfField h, const float* rays_dev, int64_t n_rays, int32_t ray_stride, int32_t n_samples,
+                     int32_t white_bg, int32_t tile_w, float* rgb_dev, float* depth_dev, float* acc_dev,
+                     int32_t mlp_impl, void* stream) {
+  if (!h) return fail(NGF_EINVAL, "field is NULL");
+  if (n_rays < 0 || n_rays > 0x7fffffffll) return fail(NGF_EINVAL, "n_rays=%lld", (long long)n_rays);
+  if (n_rays == 0) return NGF_OK;
+  if (!rays_dev || !rgb_dev || !depth_dev) return fail(NGF_EINVAL, "NULL ray/output pointer");
+  if (ray_stride < 6) return fail(NGF_EINVAL, "ray_stride=%d (< 6)", ray_stride);
+  if (mlp_impl != NGF_MLP_TCGEN05 && mlp_impl != NGF_MLP_SIMT) return fail(NGF_EINVAL, "mlp_impl=%d", mlp_impl);
+  DeviceGuard g(h->device);
+  if (!g.ok) return fail(NGF_ECUDA, "cannot select device %d", h->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* acc = acc_dev;
+  if (!acc) {
+    if (h->acc_cap < n_rays) {
+      CU(cudaStreamSynchronize(st));
+      cudaFree(h->acc_ws);
+      h->acc_ws = nullptr; h->acc_cap = 0;
+      CU(dev_alloc(&h->acc_ws, (size_t)n_rays));
+      h->acc_cap = n_rays;
+    }
+    acc = h->acc_ws;
+  }
+  return render_dev(h, rays_dev, n_rays, ray_stride, n_samples, white_bg, tile_w, rgb_dev, depth_dev, acc,
+                    h->counters, true, mlp_impl, st);
+}
+
+int ngf_field_render_host(NgfField h, const float* rays_host, int64_t n_rays, int32_t ray_stride,
+                          int32_t n_samples, int32_t white_bg, int32_t tile_w, float* rgb_host,
+                          float* depth_host, int32_t mlp_impl) {
+  if (!h) return fail(NGF_EINVAL, "field is NULL");
+  if (n_rays < 0 || n_rays > 0x7fffffffll) return fail(NGF_EINVAL, "n_rays=%lld", (long long)n_rays);
+  if (n_rays == 0) return NGF_OK;
+  if (!rays_host || !rgb_host || !depth_host) return fail(NGF_EINVAL, "NULL ray/output pointer");
+  if (ray_stride < 6) return fail(NGF_EINVAL, "ray_stride=%d (< 6)", ray_stride);
+  if (mlp_impl != NGF_MLP_TCGEN05 && mlp_impl != NGF_MLP_SIMT) return fail(NGF_EINVAL, "mlp_impl=%d", mlp_impl);
+  DeviceGuard g(h->device);
+  if (!g.ok) return fail(NGF_ECUDA, "cannot select device %d", h->device);
+
+  // chunking: ~128 Ki rays per chunk, whole groups of 4 image rows when the image width is known
+  const bool img = tile_w > 0 && n_rays % tile_w == 0;
+  long long chunk = 128 * 1024;
+  if (img) {
+    long long rows = chunk / tile_w;
+    rows = rows < 4 ? 4 : rows - rows % 4;
+    chunk = rows * tile_w;
+  }
+  if (chunk > n_rays) chunk = n_rays;
+  if (h->chunk_cap < chunk || h->chunk_stride != ray_stride) {
+    free_chunks(h);
+    for (auto& c : h->chunk) {
+      CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+      CU(dev_alloc(&c.rays, (size_t)chunk * ray_stride));
+      CU(dev_alloc(&c.rgb, (size_t)chunk * 3));
+      CU(dev_alloc(&c.depth, (size_t)chunk));
+      CU(dev_alloc(&c.acc, (size_t)chunk));
+      CU(cudaMalloc(reinterpret_cast<void**>(&c.counters), kCounterBytes));
+    }
+    h->chunk_cap = chunk;
+    h->chunk_stride = ray_stride;
+  }
+  int ci = 0;
+  for (long long s = 0; s < n_rays; s += chunk, ci ^= 1) {
+    const long long n = (n_rays - s) < chunk ? (n_rays - s) : chunk;
+    HostChunk& c = h->chunk[ci];
+    CU(cudaMemcpyAsync(c.rays, rays_host + s * ray_stride, (size_t)n * ray_stride * sizeof(float),
+                       cudaMemcpyHostToDevice, c.stream));
+    int rc = render_dev(h, c.rays, n, ray_stride, n_samples, white_bg, img ? tile_w : 0, c.rgb, c.depth, c.acc,
+                        c.counters, true, mlp_impl, c.stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(rgb_host + s * 3, c.rgb, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaMemcpyAsync(depth_host + s, c.depth, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+  }
+  CU(cudaStreamSynchronize(h->chunk[0].stream));
+  CU(cudaStreamSynchronize(h->chunk[1].stream));
+  return NGF_OK;
+}
+
+int ngf_field_set_gauge(NgfField h, int32_t on) {
+  if (!h) return fail(NGF_EINVAL, "field is NULL");
+  if (on && !h->has_gauge) return fail(NGF_EINVAL, "field was packed without gauge planes");
+  h->dev.gauge_on = on ? 1 : 0;
+  return NGF_OK;
+}
+
+int ngf_field_set_infoinv(NgfField h, int32_t on) {
+  if (!h) return fail(NGF_EINVAL, "field is NULL");
+  h->dev.infoinv = on ? 1 : 0;
+  return NGF_OK;
+}
+
+int ngf_field_stats(NgfField h, NgfStats* out, void* stream) {
+  if (!h || !out) return fail(NGF_EINVAL, "NULL argument");
+  DeviceGuard g(h->device);
+  unsigned long long s[4];
+  CU(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+  CU(cudaMemcpy(s, h->counters + 2, sizeof(s), cudaMemcpyDeviceToHost));
+  out->rays = 0;
+  out->samples_in_box = s[0]; out->samples_density = s[1]; out->samples_colour = s[2]; out->mlp_tiles = s[3];
+  return NGF_OK;
+}
+
+#define NGF_POINTWISE_PROLOGUE()                                              \
+  if (!h) return fail(NGF_EINVAL, "field is NULL");                           \
+  if (n < 0) return fail(NGF_EINVAL, "negative count");                       \
+  if (n == 0) return NGF_OK;                                                  \
+  DeviceGuard g(h->device);                                                   \
+  if (!g.ok) return fail(NGF_ECUDA, "cannot select device %d", h->device);    \
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream)
+
+int ngf_field_sample_ray(NgfField h, const float* rays_dev, int64_t n, int32_t ray_stride, int32_t n_samples,
+                         float* pts_dev, float* t_dev, uint8_t* inside_dev, void* stream) {
+  NGF_POINTWISE_PROLOGUE();
+  if (!rays_dev || !pts_dev || !t_dev || !inside_dev) return fail(NGF_EINVAL, "NULL pointer");
+  if (ray_stride < 6) return fail(NGF_EINVAL, "ray_stride=%d (< 6)", ray_stride);
+  const int S = n_samples > 0 ? n_samples : h->n_samples_default;
+  CU(launch_sample_ray(h->dev, rays_dev, n, ray_stride, S, pts_dev, t_dev, inside_dev, st));
+  return NGF_OK;
+}
+
+int ngf_field_alpha_keep(NgfField h, const float* pts_dev, int64_t n, uint8_t* keep_dev, void* stream) {
+  NGF_POINTWISE_PROLOGUE();
+  if (!pts_dev || !keep_dev) return fail(NGF_EINVAL, "NULL pointer");
+  CU(launch_alpha_keep(h->dev, pts_dev, n, keep_dev, st));
+  return NGF_OK;
+}
+
+int ngf_field_gauge(NgfField h, const float* xyz_norm_dev, int64_t n, int32_t gauge_on, float* xy_dev,
+                    float* yz_dev, float* xz_dev, void* stream) {
+  NGF_POINTWISE_PROLOGUE();
+  if (!xyz_norm_dev || !xy_dev || !yz_dev || !xz_dev) return fail(NGF_EINVAL, "NULL pointer");
+  if (gauge_on && h->dev.variant == 0 && !h->has_gauge)
+    return fail(NGF_EINVAL, "gauge requested but the field was packed without gauge planes");
+  CU(launch_gauge(h->dev, xyz_norm_dev, n, gauge_on, xy_dev, yz_dev, xz_dev, st));
+  return NGF_OK;
+}
+
+int ngf_field_density(NgfField h, const float* xy_dev, const float* yz_dev, const float* xz_dev, int64_t n,
+                      float* sigma_dev, void* stream) {
+  NGF_POINTWISE_PROLOGUE();
+  if (!xy_dev || !yz_dev || !xz_dev || !sigma_dev) return fail(NGF_EINVAL, "NULL pointer");
+  CU(launch_density(h->dev, xy_dev, yz_dev, xz_dev, n, sigma_dev, st));
+  return NGF_OK;
+}
+
+int ngf_field_rgb(NgfField h, const float* xy_dev, const float* yz_dev, const float* xz_dev,
+                  const float* viewdirs_dev, int64_t n, float* rgb_dev, int32_t mlp_impl, void* stream) {
+  NGF_POINTWISE_PROLOGUE();
+  if (!xy_dev || !yz_dev || !xz_dev || !viewdirs_dev || !rgb_dev) return fail(NGF_EINVAL, "NULL pointer");
+  if (n > 0x7fffffffll) return fail(NGF_EINVAL, "n too large");
+  if (mlp_impl != NGF_MLP_TCGEN05 && mlp_impl != NGF_MLP_SIMT) return fail(NGF_EINVAL, "mlp_impl=%d", mlp_impl);
+  CU(launch_rgb(h->dev, xy_dev, yz_dev, xz_dev, viewdirs_dev, n, rgb_dev, mlp_impl, h->lbo_swap, h->num_sms, st));
+  return NGF_OK;
+}
+
+int ngf_field_sigma_world(NgfField h, const float* pts_dev, int64_t n, int32_t use_gauge, float* sigma_dev,
+                          void* stream) {
+  NGF_POINTWISE_PROLOGUE();
+  if (!pts_dev || !sigma_dev) return fail(NGF_EINVAL, "NULL pointer");
+  CU(launch_sigma_world(h->dev, pts_dev, n, use_gauge, sigma_dev, st));
+  return NGF_OK;
+}
+
+int64_t ngf_shard_count(int64_t n_rays, int32_t block, int32_t rank, int32_t world) {
+  if (n_rays < 0 || block < 1 || world < 1 || rank < 0 || rank >= world) return -1;
+  const long long per_cycle = (long long)block * world;
+  const long long full = n_rays / per_cycle, rem = n_rays - full * per_cycle;
+  long long extra = rem - (long long)rank * block;
+  if (extra < 0) extra = 0;
+  if (extra > block) extra = block;
+  return full * block + extra;
+}
+
+int ngf_shard_gather(const float* src_dev, int64_t n_rays, int32_t width, int32_t block, int32_t rank,
+                     int32_t world, float* dst_dev, void* stream) {
+  if (!src_dev || !dst_dev) return fail(NGF_EINVAL, "NULL pointer");
+  if (ngf_shard_count(n_rays, block, rank, world) < 0 || width < 1) return fail(NGF_EINVAL, "bad shard arguments");
+  CU(launch_shard_gather(src_dev, n_rays, width, block, rank, world, dst_dev, reinterpret_cast<cudaStream_t>(stream)));
+  return NGF_OK;
+}
+
+int ngf_shard_scatter(const float* src_dev, int64_t n_rays, int32_t width, int32_t block, int32_t world,
+                      int64_t max_shard, float* dst_dev, void* stream) {
+  if (!src_dev || !dst_dev) return fail(NGF_EINVAL, "NULL pointer");
+  if (n_rays < 0 || block < 1 || world < 1 || width < 1 || max_shard < ngf_shard_count(n_rays, block, 0, world))
+    return fail(NGF_EINVAL, "bad shard arguments");
+  CU(launch_shard_scatter(src_dev, n_rays, width, block, world, max_shard, dst_dev,
+                          reinterpret_cast<cudaStream_t>(stream)));
+  return NGF_OK;
+}
+
+}  // extern "C"

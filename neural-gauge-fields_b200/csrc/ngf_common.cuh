@@ -1,0 +1,316 @@
+// ngf_common.cuh — device-side field description and the point-wise building blocks of the render path.
+//
+// Every function names the reference code it implements (paths relative to /root/reference).  The
+// decision-critical chain (sample position, bbox test, occupancy test) uses __f*_rn intrinsics so nvcc cannot
+// contract mul+add into FMA: eager PyTorch rounds after every op, and a 1-ulp position change flips mask
+// decisions (SURVEY.md §7 "bit-level decision parity").  Never build this with --use_fast_math.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ngf {
+
+constexpr int kMid = 64;          // rgb_decoder middle_dim as instantiated (Field.py:28)
+constexpr int kDensMid = 32;      // InfoInv density_decoder middle_dim (InfoInv/models/Field.py:23)
+
+template <int V> struct Cfg;
+template <> struct Cfg<0> {       // TriPlane
+  static constexpr int DC = 16, AC = 48, F = 144, K1 = 160;
+};
+template <> struct Cfg<1> {       // InfoInv
+  static constexpr int DC = 24, AC = 72, F = 216, K1 = 240;
+};
+
+struct PlaneDev {
+  const float* dens;              // [H][W][DC] fp32, channels-last
+  const __half* app;              // [H][W][AC] fp16, channels-last
+  int H, W;
+  float wm1, hm1;                 // float(W-1), float(H-1)
+};
+
+struct GaugeDev {
+  const float2* g;                // [H][W] (du, dv)
+  int H, W;
+  float wm1, hm1;
+};
+
+struct FieldDev {
+  int variant;
+  PlaneDev plane[3];              // xy (u=x,v=y), yz (u=y,v=z), xz (u=x,v=z)
+  GaugeDev gauge[3];
+  int gauge_on;
+  int infoinv;
+  float lo[3], hi[3], inv[3];
+  float step, near_t, far_t, dscale, wthres, dshift;
+  // occupancy ("alpha mask") bit grid
+  const uint32_t* occ;            // bit (z*H + y)*W + x
+  int occ_w, occ_h, occ_d;
+  int has_occ;
+  float occ_lo[3], occ_inv[3];
+  // TriPlane density head Linear(48,1)
+  float dw[48];
+  float db;
+  // InfoInv density MLP 72->32->32->1, fp32: [w1t 72x32 (input-major)][b1 32][w2 32x32][b2 32][w3 32][b3 1]
+  const float* dmlp;
+  // colour MLP, packed: w1p/w2p fp16 in tcgen05 K-major core-matrix order, tail fp32 [w3 3x64][b2 64][b3 3][pad]
+  const __half* w1p;
+  const __half* w2p;
+  const float* tail;
+};
+
+constexpr int kDmlpFloats = 32 * 72 + 32 + 32 * 32 + 32 + 32 + 1;   // 3457
+constexpr int kTailFloats = 3 * 64 + 64 + 4;                        // 260
+
+// ---------------------------------------------------------------------------------------------------------
+// Base.sample_ray prologue (FieldBase.py:121-125): first sample distance t0.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ray_t0(const FieldDev& f, const float o[3], const float d[3]) {
+  float best = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float vec = (d[k] == 0.f) ? 1e-6f : d[k];
+    float ra = __fdiv_rn(__fsub_rn(f.hi[k], o[k]), vec);
+    float rb = __fdiv_rn(__fsub_rn(f.lo[k], o[k]), vec);
+    best = fmaxf(best, fminf(ra, rb));
+  }
+  return fminf(fmaxf(best, f.near_t), f.far_t);
+}
+
+// Conservative superset [i_lo, i_hi] of the sample indices whose position can be inside the box; the exact
+// per-sample test still runs inside it, so results do not depend on this clip.  The slab distances are widened
+// by the rounding error of p = o + d*t mapped back to t (huge for near-zero direction components, which then
+// leave the axis unconstrained) plus two whole steps.
+__device__ __forceinline__ void ray_index_range(const FieldDev& f, const float o[3], const float d[3], float t0,
+                                                int S, int& i_lo, int& i_hi) {
+  float t_in = -INFINITY, t_out = INFINITY;
+  bool empty = false;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (d[k] == 0.f) {                       // p_k == o_k exactly for every sample
+      if (f.lo[k] > o[k] || o[k] > f.hi[k]) empty = true;
+      continue;
+    }
+    float inv_d = 1.f / d[k];
+    float a = (f.hi[k] - o[k]) * inv_d, b = (f.lo[k] - o[k]) * inv_d;
+    float m = 4e-6f * (fabsf(o[k]) + fabsf(d[k]) * f.far_t + fmaxf(fabsf(f.lo[k]), fabsf(f.hi[k]))) * fabsf(inv_d);
+    t_in = fmaxf(t_in, fminf(a, b) - m);     // NaN operands are ignored by fminf/fmaxf: axis left unconstrained
+    t_out = fminf(t_out, fmaxf(a, b) + m);
+  }
+  if (empty || t_out < t_in) { i_lo = 0; i_hi = -1; return; }
+  float a = floorf((t_in - t0) / f.step) - 2.f;
+  float b = ceilf((t_out - t0) / f.step) + 2.f;
+  a = fminf(fmaxf(a, 0.f), (float)S);
+  b = fminf(fmaxf(b, -1.f), (float)(S - 1));
+  i_lo = (int)a;
+  i_hi = (int)b;
+}
+
+// t_i = t0 + stepSize * i  (FieldBase.py:131-132: mul, then add)
+__device__ __forceinline__ float sample_t(const FieldDev& f, float t0, int i) {
+  return __fadd_rn(t0, __fmul_rn(f.step, (float)i));
+}
+
+// p = o + d * t (FieldBase.py:134) and the bbox test (FieldBase.py:135)
+__device__ __forceinline__ bool sample_pos(const FieldDev& f, const float o[3], const float d[3], float t,
+                                           float p[3]) {
+  bool in = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    p[k] = __fadd_rn(o[k], __fmul_rn(d[k], t));
+    in = in && !(f.lo[k] > p[k] || p[k] > f.hi[k]);
+  }
+  return in;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// AlphaGridMask.sample_alpha(p) > 0 (FieldBase.py:33-40, used at :261-267) on the bit-packed volume.
+// ATen grid_sampler_3d, align_corners=True, zeros padding: i = ((q+1)/2)*(size-1); corner weights are products of
+// (floor(i)+1-i) (always > 0) and (i-floor(i)) (> 0 iff i is not an integer); the {0,1} volume sample is > 0 iff
+// an in-range corner with non-zero weight is set.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool occ_bit(const FieldDev& f, int x, int y, int z) {
+  if ((unsigned)x >= (unsigned)f.occ_w || (unsigned)y >= (unsigned)f.occ_h || (unsigned)z >= (unsigned)f.occ_d)
+    return false;
+  uint32_t idx = ((uint32_t)z * (uint32_t)f.occ_h + (uint32_t)y) * (uint32_t)f.occ_w + (uint32_t)x;
+  return (__ldg(f.occ + (idx >> 5)) >> (idx & 31)) & 1u;
+}
+
+__device__ __forceinline__ bool occ_keep(const FieldDev& f, const float p[3]) {
+  float fi[3];
+  int i0[3];
+  bool frac[3];
+  const int dims[3] = {f.occ_w, f.occ_h, f.occ_d};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float q = __fsub_rn(__fmul_rn(__fsub_rn(p[k], f.occ_lo[k]), f.occ_inv[k]), 1.f);
+    fi[k] = __fmul_rn(__fmul_rn(__fadd_rn(q, 1.f), 0.5f), (float)(dims[k] - 1));
+    float fl = floorf(fi[k]);
+    frac[k] = fi[k] != fl;
+    fl = fminf(fmaxf(fl, -2.f), (float)dims[k] + 1.f);
+    i0[k] = (int)fl;
+  }
+  bool keep = false;
+#pragma unroll
+  for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        bool w = (!dx || frac[0]) && (!dy || frac[1]) && (!dz || frac[2]);
+        if (w) keep = keep || occ_bit(f, i0[0] + dx, i0[1] + dy, i0[2] + dz);
+      }
+  return keep;
+}
+
+// Base.normalize_coord (FieldBase.py:88-89): (p - aabb0) * invaabbSize - 1
+__device__ __forceinline__ void unit_coords(const FieldDev& f, const float p[3], float n[3]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) n[k] = __fsub_rn(__fmul_rn(__fsub_rn(p[k], f.lo[k]), f.inv[k]), 1.f);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// grid_sample(bilinear, align_corners=True, zeros) tap set for one lookup (ATen GridSampler: ix=((u+1)/2)*(W-1)).
+// Taps outside the plane get weight 0 and a clamped (in-bounds) address.
+// ---------------------------------------------------------------------------------------------------------
+struct Taps {
+  int off[4];     // texel index y*W+x
+  float w[4];
+};
+
+__device__ __forceinline__ Taps make_taps(float u, float v, int W, int H, float wm1, float hm1) {
+  float ix = ((u + 1.f) * 0.5f) * wm1;
+  float iy = ((v + 1.f) * 0.5f) * hm1;
+  ix = fminf(fmaxf(ix, -2.f), (float)W + 1.f);      // also maps NaN to a bound: never an OOB address
+  iy = fminf(fmaxf(iy, -2.f), (float)H + 1.f);
+  float x0f = floorf(ix), y0f = floorf(iy);
+  float fx = ix - x0f, fy = iy - y0f;
+  int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
+  bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)x1 < (unsigned)W;
+  bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)y1 < (unsigned)H;
+  int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x1, 0), W - 1);
+  int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y1, 0), H - 1);
+  Taps t;
+  t.off[0] = cy0 * W + cx0; t.w[0] = (vx0 && vy0) ? (1.f - fx) * (1.f - fy) : 0.f;
+  t.off[1] = cy0 * W + cx1; t.w[1] = (vx1 && vy0) ? fx * (1.f - fy) : 0.f;
+  t.off[2] = cy1 * W + cx0; t.w[2] = (vx0 && vy1) ? (1.f - fx) * fy : 0.f;
+  t.off[3] = cy1 * W + cx1; t.w[3] = (vx1 && vy1) ? fx * fy : 0.f;
+  return t;
+}
+
+__device__ __forceinline__ float2 gauge_lookup(const GaugeDev& g, float u, float v) {
+  Taps t = make_taps(u, v, g.W, g.H, g.wm1, g.hm1);
+  float2 r = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 s = __ldg(g.g + t.off[k]);
+    r.x += t.w[k] * s.x;
+    r.y += t.w[k] * s.y;
+  }
+  return r;
+}
+
+// TriPlane.compute_gauge (TriPlane/models/Field.py:53-75) / InfoInv transform (InfoInv/models/Field.py:43-50).
+// c = {u_xy, v_xy, u_yz, v_yz, u_xz, v_xz}.  Association order of the adds follows the reference.
+__device__ __forceinline__ void gauge_coords(const FieldDev& f, const float n[3], bool gauge_on, float c[6]) {
+  const float x = n[0], y = n[1], z = n[2];
+  if (!gauge_on) {
+    c[0] = x; c[1] = y; c[2] = y; c[3] = z; c[4] = x; c[5] = z;
+    return;
+  }
+  float2 gxy = gauge_lookup(f.gauge[0], x, y);
+  float2 gyz = gauge_lookup(f.gauge[1], y, z);
+  float2 gxz = gauge_lookup(f.gauge[2], x, z);
+  c[0] = __fadd_rn(__fadd_rn(x, gxy.x), gxz.x);
+  c[1] = __fadd_rn(__fadd_rn(y, gxy.y), gyz.x);
+  c[2] = __fadd_rn(__fadd_rn(y, gyz.x), gxy.y);
+  c[3] = __fadd_rn(__fadd_rn(z, gyz.y), gxz.y);
+  c[4] = __fadd_rn(__fadd_rn(x, gxz.x), gxy.x);
+  c[5] = __fadd_rn(__fadd_rn(z, gxz.y), gyz.y);
+}
+
+// F.softplus(x) with torch defaults (beta=1, threshold=20)
+__device__ __forceinline__ float softplus_torch(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+// ---------------------------------------------------------------------------------------------------------
+// compute_density, TriPlane (Field.py:77-91): 3 x bilinear over channels [0,16), Linear(48,1), softplus(.-10).
+// The blend and the dot product are fused: sum_taps w_tap * <texel, dw_plane>.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigma_triplane(const FieldDev& f, const float c[6]) {
+  float acc = f.db;
+#pragma unroll
+  for (int pl = 0; pl < 3; ++pl) {
+    const PlaneDev& P = f.plane[pl];
+    Taps t = make_taps(c[2 * pl], c[2 * pl + 1], P.W, P.H, P.wm1, P.hm1);
+    const float* w = f.dw + 16 * pl;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4* tex = reinterpret_cast<const float4*>(P.dens) + (size_t)t.off[k] * 4;
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 a = __ldg(tex + q);
+        s += a.x * w[4 * q] + a.y * w[4 * q + 1] + a.z * w[4 * q + 2] + a.w * w[4 * q + 3];
+      }
+      acc += t.w[k] * s;
+    }
+  }
+  return softplus_torch(acc + f.dshift);
+}
+
+// positional_encoding value for channel ch of PE(xyz, NF) (InfoInv/models/networks.py:227-237): layout
+// [sin(x*2^0..2^(NF-1)), sin(y*..), sin(z*..), cos(same)].  x*2^j is exact in fp32, as in torch.
+template <int NF>
+__device__ __forceinline__ float phase_value(const float xyz[3], int ch) {
+  bool is_cos = ch >= 3 * NF;
+  int r = is_cos ? ch - 3 * NF : ch;
+  float a = xyz[r / NF] * (float)(1 << (r % NF));
+  return is_cos ? cosf(a) : sinf(a);
+}
+
+// compute_density, InfoInv (InfoInv/models/Field.py:52-70 + networks.py:34-54): 3 x bilinear over channels
+// [0,24) (x phase code of xyz with 4 bands when infoinv), MLP 72->32->32->1 (ReLU), softplus(.-10).
+// `w` points at the fp32 density MLP (shared memory in the render kernel, global in the point-wise kernel).
+__device__ __forceinline__ float sigma_infoinv(const FieldDev& f, const float c[6], const float* __restrict__ w) {
+  const float xyz[3] = {c[0], c[1], c[3]};
+  float h1[kDensMid];
+#pragma unroll
+  for (int j = 0; j < kDensMid; ++j) h1[j] = w[32 * 72 + j];
+  const float* w1t = w;                              // [72][32] input-major
+  for (int pl = 0; pl < 3; ++pl) {
+    const PlaneDev& P = f.plane[pl];
+    Taps t = make_taps(c[2 * pl], c[2 * pl + 1], P.W, P.H, P.wm1, P.hm1);
+    for (int q = 0; q < 6; ++q) {                    // 6 x float4 = 24 channels
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(P.dens) + (size_t)t.off[k] * 6 + q);
+        v.x += t.w[k] * a.x; v.y += t.w[k] * a.y; v.z += t.w[k] * a.z; v.w += t.w[k] * a.w;
+      }
+      float fe[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        int ch = 4 * q + e;
+        float x = fe[e];
+        if (f.infoinv) x *= phase_value<4>(xyz, ch);
+        const int col = pl * 24 + ch;
+#pragma unroll
+        for (int j = 0; j < kDensMid; ++j) h1[j] += w1t[col * 32 + j] * x;
+      }
+    }
+  }
+  const float* b2 = w + 32 * 72 + 32 + 32 * 32;
+  const float* w2 = w + 32 * 72 + 32;
+  const float* w3 = b2 + 32;
+  float out = w3[32];
+#pragma unroll 4
+  for (int j = 0; j < kDensMid; ++j) {
+    float s = b2[j];
+#pragma unroll
+    for (int k = 0; k < kDensMid; ++k) s += w2[j * 32 + k] * fmaxf(h1[k], 0.f);
+    out += w3[j] * fmaxf(s, 0.f);
+  }
+  return softplus_torch(out + f.dshift);
+}
+
+}  // namespace ngf

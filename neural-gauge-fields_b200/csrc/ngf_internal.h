@@ -1,0 +1,56 @@
+// ngf_internal.h — host-side launch interface between the C ABI (ngf_abi.cu) and the kernels (ngf_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ngf_common.cuh"
+
+namespace ngf {
+
+struct RenderArgs {
+  const float* rays;
+  long long n_rays;
+  int ray_stride;
+  int S;
+  int white_bg;
+  int img_w, img_h;            // > 0: rays are row-major pixels of an img_w x img_h image -> 8x4 pixel warp tiles
+  float* rgb;                  // [R][3], zero-initialised accumulator, finalised in place
+  float* depth;                // [R]
+  float* acc;                  // [R]
+  unsigned int* tile_counter;  // zero-initialised
+  unsigned long long* stats;   // [4]: samples_in_box, samples_density, samples_colour, mlp_tiles (accumulated)
+  int n_tiles;
+  int lbo_swap;                // debugging: swap the LBO/SBO fields of the tcgen05 smem descriptors
+};
+
+// All launchers return cudaGetLastError() after enqueueing on `st`.
+cudaError_t launch_render(const FieldDev& f, const RenderArgs& a, int mlp_impl, int num_sms, cudaStream_t st);
+cudaError_t launch_finalize(float* rgb, const float* acc, long long n_rays, int white_bg, cudaStream_t st);
+cudaError_t launch_sample_ray(const FieldDev& f, const float* rays, long long n_rays, int stride, int S, float* pts,
+                              float* t, uint8_t* inside, cudaStream_t st);
+cudaError_t launch_alpha_keep(const FieldDev& f, const float* pts, long long n, uint8_t* keep, cudaStream_t st);
+cudaError_t launch_gauge(const FieldDev& f, const float* xyz, long long n, int gauge_on, float* xy, float* yz,
+                         float* xz, cudaStream_t st);
+cudaError_t launch_density(const FieldDev& f, const float* xy, const float* yz, const float* xz, long long n,
+                           float* sigma, cudaStream_t st);
+cudaError_t launch_sigma_world(const FieldDev& f, const float* pts, long long n, int use_gauge, float* sigma,
+                               cudaStream_t st);
+cudaError_t launch_rgb(const FieldDev& f, const float* xy, const float* yz, const float* xz, const float* dirs,
+                       long long n, float* rgb, int mlp_impl, int lbo_swap, int num_sms, cudaStream_t st);
+
+// packing kernels
+cudaError_t launch_pack_plane(const float* nchw, int C, int H, int W, int DC, float* dens, __half* app,
+                              cudaStream_t st);
+cudaError_t launch_pack_gauge(const float* nchw, int H, int W, float2* out, cudaStream_t st);
+cudaError_t launch_pack_occ(const float* vol, long long n_vox, uint32_t* bits, cudaStream_t st);
+
+// ray sharding
+cudaError_t launch_shard_gather(const float* src, long long n_rays, int width, int block, int rank, int world,
+                                float* dst, cudaStream_t st);
+cudaError_t launch_shard_scatter(const float* src, long long n_rays, int width, int block, int world,
+                                 long long max_shard, float* dst, cudaStream_t st);
+
+size_t render_smem_bytes(int variant);
+uint64_t launch_count();
+
+}  // namespace ngf

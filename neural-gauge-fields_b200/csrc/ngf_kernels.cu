@@ -1,0 +1,528 @@
+// ngf_kernels.cu — sm_100a kernels of the render path and their launchers.
+//
+// ngf_render_kernel is the fused per-frame kernel that replaces Base.forward (TriPlane/models/FieldBase.py:251-312,
+// InfoInv/models/FieldBase.py:228-282) and the chunk loop around it (TriPlane/main.py:60-71):
+//
+//   persistent CTAs (256 threads, 8 warps).  Each WARP pulls tiles of 32 rays (8x4 pixel blocks when the image
+//   shape is known) from a global counter and marches them: sample position + bbox test (sample_ray), occupancy
+//   bit test (AlphaGridMask), gauge lookup (compute_gauge), density (compute_density), alpha/transmittance/weight
+//   (raw2alpha) — all in registers, nothing materialised.  Samples whose weight exceeds rayMarch_weight_thres are
+//   pushed (warp-aggregated) into a shared-memory ring.  Whenever the ring holds 128 samples the whole CTA runs one
+//   colour-MLP tile on the tensor cores (ngf_mlp.cuh) and accumulates weight*rgb into the frame with fp32 atomics.
+//   ngf_finalize_kernel adds the white background and clamps (FieldBase.py:299-302).
+#include <cuda_runtime.h>
+
+#include <atomic>
+
+#include "ngf_internal.h"
+#include "ngf_mlp.cuh"
+
+namespace ngf {
+
+static std::atomic<uint64_t> g_launches{0};
+uint64_t launch_count() { return g_launches.load(); }
+#define NGF_COUNT_LAUNCH() g_launches.fetch_add(1)
+
+constexpr float kTStop = 1e-6f;   // stop marching once transmittance <= kTStop: all later weights sum to <= 1e-6
+
+template <int V>
+struct RenderSmem {
+  using L = MlpSmem<V>;
+  static constexpr uint32_t offDmlp = L::offEnd;
+  static constexpr uint32_t kBytes = offDmlp + (V == 1 ? ((kDmlpFloats * 4 + 15) / 16) * 16 : 0);
+};
+
+size_t render_smem_bytes(int variant) { return variant == 0 ? RenderSmem<0>::kBytes : RenderSmem<1>::kBytes; }
+
+template <int V, int IMPL>
+__global__ void __launch_bounds__(kThreads, V == 0 ? 2 : 1) ngf_render_kernel(const __grid_constant__ FieldDev f,
+                                                                 const __grid_constant__ RenderArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using L = MlpSmem<V>;
+  constexpr int NW = kThreads / 32;
+  const int tid = threadIdx.x, lane = tid & 31;
+  constexpr unsigned FULL = 0xffffffffu;
+
+  mlp_setup<V, IMPL>(f, smem);
+  const float* dmlp_s = nullptr;
+  if (V == 1) {
+    float* dm = reinterpret_cast<float*>(smem + RenderSmem<V>::offDmlp);
+    for (int i = tid; i < kDmlpFloats; i += kThreads) dm[i] = __ldg(f.dmlp + i);
+    dmlp_s = dm;
+  }
+  __syncthreads();
+
+  MlpCtl* ctl = reinterpret_cast<MlpCtl*>(smem + L::offCtl);
+  volatile uint32_t* q_head = &ctl->q_head;
+  volatile uint32_t* q_tail = &ctl->q_tail;
+  volatile uint32_t* n_exh = &ctl->n_exhausted;
+  QEntry* queue = reinterpret_cast<QEntry*>(smem + L::offQueue);
+  uint32_t phase = 0;
+
+  // per-lane ray state
+  float o[3] = {0, 0, 0}, d[3] = {0, 0, 1}, t0 = 0.f, T = 1.f, acc = 0.f, dep = 0.f, last_col = 0.f;
+  int i = 0, i_end = 0;
+  long long ray = -1;
+  bool live = false;
+  bool exhausted = false;
+  uint32_t st_box = 0, st_den = 0, st_col = 0, st_tiles = 0;
+  const int S = a.S;
+
+  for (;;) {
+    // ------------------------------------------------------------------ work phase (warp-autonomous)
+    while (!exhausted) {
+      if ((*q_tail - *q_head) >= (uint32_t)kTileM) break;
+      if (!__any_sync(FULL, live)) {
+        int tile = 0;
+        if (lane == 0) tile = (int)atomicAdd(a.tile_counter, 1u);
+        tile = __shfl_sync(FULL, tile, 0);
+        if (tile >= a.n_tiles) {
+          exhausted = true;
+          if (lane == 0) atomicAdd(&ctl->n_exhausted, 1u);
+          break;
+        }
+        if (a.img_w > 0) {
+          const int tiles_x = (a.img_w + 7) >> 3;
+          const int px = (tile % tiles_x) * 8 + (lane & 7), py = (tile / tiles_x) * 4 + (lane >> 3);
+          ray = (px < a.img_w && py < a.img_h) ? (long long)py * a.img_w + px : -1;
+        } else {
+          ray = (long long)tile * 32 + lane;
+          if (ray >= a.n_rays) ray = -1;
+        }
+        if (ray >= 0) {
+          const float* rp = a.rays + ray * a.ray_stride;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { o[k] = __ldg(rp + k); d[k] = __ldg(rp + 3 + k); }
+          last_col = __ldg(rp + a.ray_stride - 1);
+          t0 = ray_t0(f, o, d);
+          int lo_i, hi_i;
+          ray_index_range(f, o, d, t0, S, lo_i, hi_i);
+          i = lo_i; i_end = hi_i + 1;
+          T = 1.f; acc = 0.f; dep = 0.f;
+          live = i < i_end;
+          if (!live) {                                   // ray misses the box: background only
+            a.acc[ray] = 0.f;
+            a.depth[ray] = last_col;
+            ray = -1;
+          }
+        }
+        continue;
+      }
+      // ---- skip empty space until this lane finds a sample that needs the field (or runs out)
+      bool found = false;
+      float t = 0.f, p[3] = {0, 0, 0};
+      while (live && !found) {
+        t = sample_t(f, t0, i);
+        bool in = sample_pos(f, o, d, t, p);
+        if (in) ++st_box;
+        if (in && f.has_occ) in = occ_keep(f, p);
+        if (in) found = true;
+        else if (++i >= i_end) live = false;
+      }
+      // ---- density + alpha compositing weights for the found samples (lanes converge here)
+      bool push = false;
+      QEntry e;
+      if (found) {
+        float n[3];
+        unit_coords(f, p, n);
+        gauge_coords(f, n, V == 0 && f.gauge_on, e.c);
+        const float sigma = (V == 0) ? sigma_triplane(f, e.c) : sigma_infoinv(f, e.c, dmlp_s);
+        ++st_den;
+        // raw2alpha (FieldBase.py:12-19) with dists from the rounded t values (FieldBase.py:258, 288)
+        const float tn = sample_t(f, t0, i + 1);
+        const float delta = (i == S - 1) ? 0.f : __fmul_rn(__fsub_rn(tn, t), f.dscale);
+        const float alpha = __fsub_rn(1.f, expf(-__fmul_rn(sigma, delta)));
+        const float w = __fmul_rn(alpha, T);
+        T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f));
+        acc += w;
+        dep += w * t;
+        push = w > f.wthres;
+        e.w = w;
+        e.id = (int)ray;
+        if (++i >= i_end || T <= kTStop) live = false;
+      }
+      const unsigned pm = __ballot_sync(FULL, push);
+      if (pm) {
+        uint32_t base = 0;
+        const int leader = __ffs(pm) - 1;
+        if (lane == leader) base = atomicAdd(&ctl->q_tail, (uint32_t)__popc(pm));
+        base = __shfl_sync(FULL, base, leader);
+        if (push) {
+          ++st_col;
+          const uint32_t slot = (base + __popc(pm & ((1u << lane) - 1u))) & (kQueueCap - 1);
+          float4* dst = reinterpret_cast<float4*>(&queue[slot]);
+          dst[0] = make_float4(e.c[0], e.c[1], e.c[2], e.c[3]);
+          dst[1] = make_float4(e.c[4], e.c[5], e.w, __int_as_float(e.id));
+        }
+      }
+      if (!live && ray >= 0) {                           // ray finished: acc_map / depth_map (FieldBase.py:296,305-306)
+        a.acc[ray] = acc;
+        a.depth[ray] = dep + (1.f - acc) * last_col;
+        ray = -1;
+      }
+    }
+    // ------------------------------------------------------------------ CTA sync point
+    __syncthreads();
+    const uint32_t head = *q_head;
+    const uint32_t cnt = *q_tail - head;
+    const bool all_exh = (*n_exh == (uint32_t)NW);
+    if (cnt >= (uint32_t)kTileM || (all_exh && cnt > 0)) {
+      const uint32_t take = cnt < (uint32_t)kTileM ? cnt : (uint32_t)kTileM;
+      if (take < (uint32_t)kTileM) {
+        if (tid >= (int)take && tid < kTileM) {
+          float4* dst = reinterpret_cast<float4*>(&queue[(head + tid) & (kQueueCap - 1)]);
+          dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+          dst[1] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        }
+        __syncthreads();
+      }
+      mlp_tile<V, IMPL, true>(f, smem, head, phase, a.rays + 3, a.ray_stride, a.rgb, a.lbo_swap);
+      if (tid == 0) { *q_head = head + take; ++st_tiles; }
+      __syncthreads();
+      continue;
+    }
+    if (all_exh) break;
+  }
+
+  mlp_teardown<IMPL>(smem, L::offCtl);
+
+  // statistics
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    st_box += __shfl_xor_sync(FULL, st_box, s);
+    st_den += __shfl_xor_sync(FULL, st_den, s);
+    st_col += __shfl_xor_sync(FULL, st_col, s);
+  }
+  if (lane == 0) {
+    atomicAdd(a.stats + 0, (unsigned long long)st_box);
+    atomicAdd(a.stats + 1, (unsigned long long)st_den);
+    atomicAdd(a.stats + 2, (unsigned long long)st_col);
+  }
+  if (tid == 0) atomicAdd(a.stats + 3, (unsigned long long)st_tiles);
+}
+
+// rgb_map = clamp(sum w*rgb + [white_bg](1 - acc), 0, 1)   (FieldBase.py:297-302)
+__global__ void ngf_finalize_kernel(float* __restrict__ rgb, const float* __restrict__ acc, long long n_rays,
+                                    int white_bg) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * 3) return;
+  float v = rgb[i];
+  if (white_bg) v += 1.f - acc[i / 3];
+  rgb[i] = fminf(fmaxf(v, 0.f), 1.f);
+}
+
+template <int V, int IMPL>
+static cudaError_t launch_render_t(const FieldDev& f, const RenderArgs& a, int num_sms, cudaStream_t st) {
+  auto kern = ngf_render_kernel<V, IMPL>;
+  const size_t smem = RenderSmem<V>::kBytes;
+  static bool configured = false;
+  static int occ = 1;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    configured = true;
+  }
+  long long want = ((long long)a.n_tiles + (kThreads / 32) - 1) / (kThreads / 32);
+  long long grid = (long long)num_sms * occ;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, kThreads, smem, st>>>(f, a);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_render(const FieldDev& f, const RenderArgs& a, int mlp_impl, int num_sms, cudaStream_t st) {
+  if (f.variant == 0) return mlp_impl == 0 ? launch_render_t<0, 0>(f, a, num_sms, st) : launch_render_t<0, 1>(f, a, num_sms, st);
+  return mlp_impl == 0 ? launch_render_t<1, 0>(f, a, num_sms, st) : launch_render_t<1, 1>(f, a, num_sms, st);
+}
+
+cudaError_t launch_finalize(float* rgb, const float* acc, long long n_rays, int white_bg, cudaStream_t st) {
+  if (n_rays <= 0) return cudaSuccess;
+  long long n = n_rays * 3;
+  ngf_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rgb, acc, n_rays, white_bg);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// ==========================================================================================================
+// Point-wise kernels (API parity with the reference's public methods)
+// ==========================================================================================================
+
+// Base.sample_ray, eval branch (FieldBase.py:118-137)
+__global__ void ngf_sample_ray_kernel(const __grid_constant__ FieldDev f, const float* __restrict__ rays,
+                                      long long n_rays, int stride, int S, float* __restrict__ pts,
+                                      float* __restrict__ tout, uint8_t* __restrict__ inside) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_rays * S) return;
+  long long r = idx / S;
+  int i = (int)(idx - r * S);
+  const float* rp = rays + r * stride;
+  float o[3] = {rp[0], rp[1], rp[2]}, d[3] = {rp[3], rp[4], rp[5]};
+  float t0 = ray_t0(f, o, d);
+  float t = sample_t(f, t0, i), p[3];
+  bool in = sample_pos(f, o, d, t, p);
+  pts[idx * 3 + 0] = p[0]; pts[idx * 3 + 1] = p[1]; pts[idx * 3 + 2] = p[2];
+  tout[idx] = t;
+  inside[idx] = in ? 1 : 0;
+}
+
+// AlphaGridMask.sample_alpha(pts) > 0 (FieldBase.py:33-37)
+__global__ void ngf_alpha_keep_kernel(const __grid_constant__ FieldDev f, const float* __restrict__ pts, long long n,
+                                      uint8_t* __restrict__ keep) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float p[3] = {pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2]};
+  keep[i] = (!f.has_occ || occ_keep(f, p)) ? 1 : 0;
+}
+
+// compute_gauge (Field.py:53-75) / transform (InfoInv Field.py:43-50) on normalised coordinates
+__global__ void ngf_gauge_kernel(const __grid_constant__ FieldDev f, const float* __restrict__ xyz, long long n,
+                                 int gauge_on, float* __restrict__ xy, float* __restrict__ yz,
+                                 float* __restrict__ xz) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float nn[3] = {xyz[i * 3], xyz[i * 3 + 1], xyz[i * 3 + 2]}, c[6];
+  gauge_coords(f, nn, f.variant == 0 && gauge_on && f.gauge[0].g != nullptr, c);
+  xy[i * 2] = c[0]; xy[i * 2 + 1] = c[1];
+  yz[i * 2] = c[2]; yz[i * 2 + 1] = c[3];
+  xz[i * 2] = c[4]; xz[i * 2 + 1] = c[5];
+}
+
+// compute_density (Field.py:77-91 / InfoInv Field.py:52-70)
+__global__ void ngf_density_kernel(const __grid_constant__ FieldDev f, const float* __restrict__ xy,
+                                   const float* __restrict__ yz, const float* __restrict__ xz, long long n,
+                                   float* __restrict__ sigma) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float c[6] = {xy[i * 2], xy[i * 2 + 1], yz[i * 2], yz[i * 2 + 1], xz[i * 2], xz[i * 2 + 1]};
+  sigma[i] = f.variant == 0 ? sigma_triplane(f, c) : sigma_infoinv(f, c, f.dmlp);
+}
+
+// compute_alpha's field evaluation (FieldBase.py:140-156): world points -> sigma, 0 where the mask rejects
+__global__ void ngf_sigma_world_kernel(const __grid_constant__ FieldDev f, const float* __restrict__ pts, long long n,
+                                       int use_gauge, float* __restrict__ sigma) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float p[3] = {pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2]};
+  float s = 0.f;
+  if (!f.has_occ || occ_keep(f, p)) {
+    float nn[3], c[6];
+    unit_coords(f, p, nn);
+    gauge_coords(f, nn, f.variant == 0 && use_gauge && f.gauge[0].g != nullptr, c);
+    s = f.variant == 0 ? sigma_triplane(f, c) : sigma_infoinv(f, c, f.dmlp);
+  }
+  sigma[i] = s;
+}
+
+// compute_rgb (Field.py:93-105 / InfoInv Field.py:72-89): persistent CTAs, 128 rows per MLP tile
+template <int V, int IMPL>
+__global__ void __launch_bounds__(kThreads, 2) ngf_rgb_kernel(const __grid_constant__ FieldDev f,
+                                                              const float* __restrict__ xy,
+                                                              const float* __restrict__ yz,
+                                                              const float* __restrict__ xz,
+                                                              const float* __restrict__ dirs, long long n,
+                                                              float* __restrict__ rgb, int lbo_swap) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using L = MlpSmem<V>;
+  mlp_setup<V, IMPL>(f, smem);
+  __syncthreads();
+  QEntry* queue = reinterpret_cast<QEntry*>(smem + L::offQueue);
+  uint32_t phase = 0;
+  const long long n_tiles = (n + kTileM - 1) / kTileM;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (threadIdx.x < kTileM) {
+      long long r = tile * kTileM + threadIdx.x;
+      float4* dst = reinterpret_cast<float4*>(&queue[threadIdx.x]);
+      if (r < n) {
+        dst[0] = make_float4(xy[r * 2], xy[r * 2 + 1], yz[r * 2], yz[r * 2 + 1]);
+        dst[1] = make_float4(xz[r * 2], xz[r * 2 + 1], 1.f, __int_as_float((int)r));
+      } else {
+        dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[1] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+      }
+    }
+    __syncthreads();
+    mlp_tile<V, IMPL, false>(f, smem, 0u, phase, dirs, 3, rgb, lbo_swap);
+  }
+  mlp_teardown<IMPL>(smem, L::offCtl);
+}
+
+template <int V, int IMPL>
+static cudaError_t launch_rgb_t(const FieldDev& f, const float* xy, const float* yz, const float* xz,
+                                const float* dirs, long long n, float* rgb, int lbo_swap, int num_sms,
+                                cudaStream_t st) {
+  auto kern = ngf_rgb_kernel<V, IMPL>;
+  const size_t smem = MlpSmem<V>::offEnd;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  long long n_tiles = (n + kTileM - 1) / kTileM;
+  long long grid = (long long)num_sms * 2;
+  if (grid > n_tiles) grid = n_tiles;
+  kern<<<(unsigned)grid, kThreads, smem, st>>>(f, xy, yz, xz, dirs, n, rgb, lbo_swap);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rgb(const FieldDev& f, const float* xy, const float* yz, const float* xz, const float* dirs,
+                       long long n, float* rgb, int mlp_impl, int lbo_swap, int num_sms, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  if (f.variant == 0)
+    return mlp_impl == 0 ? launch_rgb_t<0, 0>(f, xy, yz, xz, dirs, n, rgb, lbo_swap, num_sms, st)
+                         : launch_rgb_t<0, 1>(f, xy, yz, xz, dirs, n, rgb, lbo_swap, num_sms, st);
+  return mlp_impl == 0 ? launch_rgb_t<1, 0>(f, xy, yz, xz, dirs, n, rgb, lbo_swap, num_sms, st)
+                       : launch_rgb_t<1, 1>(f, xy, yz, xz, dirs, n, rgb, lbo_swap, num_sms, st);
+}
+
+static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+cudaError_t launch_sample_ray(const FieldDev& f, const float* rays, long long n_rays, int stride, int S, float* pts,
+                              float* t, uint8_t* inside, cudaStream_t st) {
+  long long n = n_rays * S;
+  if (n <= 0) return cudaSuccess;
+  ngf_sample_ray_kernel<<<blocks_for(n, 256), 256, 0, st>>>(f, rays, n_rays, stride, S, pts, t, inside);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+cudaError_t launch_alpha_keep(const FieldDev& f, const float* pts, long long n, uint8_t* keep, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  ngf_alpha_keep_kernel<<<blocks_for(n, 256), 256, 0, st>>>(f, pts, n, keep);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+cudaError_t launch_gauge(const FieldDev& f, const float* xyz, long long n, int gauge_on, float* xy, float* yz,
+                         float* xz, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  ngf_gauge_kernel<<<blocks_for(n, 256), 256, 0, st>>>(f, xyz, n, gauge_on, xy, yz, xz);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+cudaError_t launch_density(const FieldDev& f, const float* xy, const float* yz, const float* xz, long long n,
+                           float* sigma, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  ngf_density_kernel<<<blocks_for(n, 128), 128, 0, st>>>(f, xy, yz, xz, n, sigma);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+cudaError_t launch_sigma_world(const FieldDev& f, const float* pts, long long n, int use_gauge, float* sigma,
+                               cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  ngf_sigma_world_kernel<<<blocks_for(n, 128), 128, 0, st>>>(f, pts, n, use_gauge, sigma);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// ==========================================================================================================
+// Packing kernels: reference NCHW fp32 parameters -> gather-friendly shadows
+// ==========================================================================================================
+// plane [C][H][W] -> dens [H][W][DC] fp32 + app [H][W][C-DC] fp16
+__global__ void ngf_pack_plane_kernel(const float* __restrict__ src, int C, int H, int W, int DC,
+                                      float* __restrict__ dens, __half* __restrict__ app) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over C*H*W, x fastest (coalesced reads)
+  long long hw = (long long)H * W;
+  if (idx >= hw * C) return;
+  int c = (int)(idx / hw);
+  long long t = idx - (long long)c * hw;
+  float v = src[idx];
+  if (c < DC) dens[t * DC + c] = v;
+  else app[t * (C - DC) + (c - DC)] = __float2half_rn(v);
+}
+
+// gauge [2][H][W] -> float2 [H][W]
+__global__ void ngf_pack_gauge_kernel(const float* __restrict__ src, long long hw, float2* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hw) return;
+  out[i] = make_float2(src[i], src[hw + i]);
+}
+
+// occupancy volume fp32 (>0 == occupied) -> bits
+__global__ void ngf_pack_occ_kernel(const float* __restrict__ vol, long long n_vox, uint32_t* __restrict__ bits) {
+  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w * 32 >= n_vox) return;
+  uint32_t m = 0;
+  for (int b = 0; b < 32; ++b) {
+    long long i = w * 32 + b;
+    if (i < n_vox && vol[i] > 0.f) m |= 1u << b;
+  }
+  bits[w] = m;
+}
+
+cudaError_t launch_pack_plane(const float* nchw, int C, int H, int W, int DC, float* dens, __half* app,
+                              cudaStream_t st) {
+  long long n = (long long)C * H * W;
+  ngf_pack_plane_kernel<<<blocks_for(n, 256), 256, 0, st>>>(nchw, C, H, W, DC, dens, app);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_gauge(const float* nchw, int H, int W, float2* out, cudaStream_t st) {
+  long long hw = (long long)H * W;
+  ngf_pack_gauge_kernel<<<blocks_for(hw, 256), 256, 0, st>>>(nchw, hw, out);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_occ(const float* vol, long long n_vox, uint32_t* bits, cudaStream_t st) {
+  long long words = (n_vox + 31) / 32;
+  ngf_pack_occ_kernel<<<blocks_for(words, 256), 256, 0, st>>>(vol, n_vox, bits);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// ==========================================================================================================
+// Ray sharding: ray g belongs to rank (g / block) % world, local index
+// (g / (block*world)) * block + g % block.
+// ==========================================================================================================
+__global__ void ngf_shard_gather_kernel(const float* __restrict__ src, long long n_rays, int width, int block,
+                                        int rank, int world, long long n_local, float* __restrict__ dst) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_local * width) return;
+  long long l = idx / width;
+  int c = (int)(idx - l * width);
+  long long g = ((l / block) * world + rank) * block + (l % block);
+  dst[idx] = src[g * width + c];
+}
+
+__global__ void ngf_shard_scatter_kernel(const float* __restrict__ src, long long n_rays, int width, int block,
+                                         int world, long long max_shard, float* __restrict__ dst) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_rays * width) return;
+  long long g = idx / width;
+  int c = (int)(idx - g * width);
+  long long blk = g / block;
+  int rank = (int)(blk % world);
+  long long l = (blk / world) * block + (g % block);
+  dst[idx] = src[((long long)rank * max_shard + l) * width + c];
+}
+
+static long long shard_count(long long n, int block, int rank, int world) {
+  long long per_cycle = (long long)block * world;
+  long long full = n / per_cycle, rem = n - full * per_cycle;
+  long long extra = rem - (long long)rank * block;
+  if (extra < 0) extra = 0;
+  if (extra > block) extra = block;
+  return full * block + extra;
+}
+
+cudaError_t launch_shard_gather(const float* src, long long n_rays, int width, int block, int rank, int world,
+                                float* dst, cudaStream_t st) {
+  long long nl = shard_count(n_rays, block, rank, world);
+  if (nl <= 0) return cudaSuccess;
+  ngf_shard_gather_kernel<<<blocks_for(nl * width, 256), 256, 0, st>>>(src, n_rays, width, block, rank, world, nl, dst);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+cudaError_t launch_shard_scatter(const float* src, long long n_rays, int width, int block, int world,
+                                 long long max_shard, float* dst, cudaStream_t st) {
+  if (n_rays <= 0) return cudaSuccess;
+  ngf_shard_scatter_kernel<<<blocks_for(n_rays * width, 256), 256, 0, st>>>(src, n_rays, width, block, world,
+                                                                            max_shard, dst);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+}  // namespace ngf

@@ -1,0 +1,440 @@
+"""Host-side mirror of the reference's ``Base`` field class (``TriPlane/models/FieldBase.py:44-312`` and
+``InfoInv/models/FieldBase.py``): same constructor, attributes, parameter names and method signatures, with the
+render path executed by ``libngf_b200.so`` (hand-written sm_100a CUDA) through the C ABI in
+``include/ngf_b200.h``.
+
+There is deliberately no CPU implementation here: a field living on the CPU, a missing shared library or a
+non-Blackwell GPU raises.  Training-time forward (``is_train=True``: jittered sampling + autograd,
+FieldBase.py:128-130) is outside the current scope and raises ``NotImplementedError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def _cuda_stream_ptr(device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class AlphaGridMask(torch.nn.Module):
+    """Binary occupancy volume with its own box (reference: FieldBase.py:22-40).  ``sample_alpha`` answers through
+    the owning field's packed bit grid; it returns 1.0 / 0.0 where the reference returns the trilinear value — every
+    caller only tests ``> 0`` (FieldBase.py:145,239,264)."""
+
+    def __init__(self, device, aabb, alpha_volume):
+        super().__init__()
+        self.device = device
+        self.aabb = aabb.to(self.device)
+        self.aabbSize = self.aabb[1] - self.aabb[0]
+        self.invgridSize = 1.0 / self.aabbSize * 2
+        self.alpha_volume = alpha_volume.view(1, 1, *alpha_volume.shape[-3:])
+        self.gridSize = torch.LongTensor(
+            [alpha_volume.shape[-1], alpha_volume.shape[-2], alpha_volume.shape[-3]]).to(self.device)
+        self._owner = None      # set by Base when the mask is attached
+
+    def normalize_coord(self, xyz_sampled):
+        return (xyz_sampled - self.aabb[0]) * self.invgridSize - 1
+
+    def sample_alpha(self, xyz_sampled):
+        if self._owner is None:
+            raise RuntimeError("AlphaGridMask is not attached to a field (assign it to field.alphaMask first)")
+        return self._owner()._alpha_keep(xyz_sampled).float()
+
+
+class Base(torch.nn.Module):
+    VARIANT = _lib.NGF_TRIPLANE
+
+    def __init__(self, aabb, gridSize, device, alphaMask=None, near_far=[2.0, 6.0], alphaMask_thres=0.001,
+                 distance_scale=25, rayMarch_weight_thres=0.0001, step_ratio=2.0, **model_kw):
+        super().__init__()
+        self.device = torch.device(device) if not isinstance(device, torch.device) else device
+        self.aabb = aabb.to(self.device) if isinstance(aabb, torch.Tensor) else torch.tensor(aabb, device=self.device)
+        self._alphaMask = None
+        self._handle = None
+        self._handle_sig = None
+        self._mlp_impl = _lib.MLP_TCGEN05
+        self.alphaMask = alphaMask
+        self.alphaMask_thres = alphaMask_thres
+        self.distance_scale = distance_scale
+        self.rayMarch_weight_thres = rayMarch_weight_thres
+        self.near_far = near_far
+        self.step_ratio = step_ratio
+        self.init_para(gridSize)
+        self.init_model(device=self.device, **model_kw)
+
+    # ------------------------------------------------------------------ bookkeeping (FieldBase.py:63-74)
+    def init_para(self, gridSize):
+        self.aabbSize = self.aabb[1] - self.aabb[0]
+        self.invaabbSize = 2.0 / self.aabbSize
+        self.gridSize = torch.LongTensor(list(gridSize)).to(self.device)
+        self.units = self.aabbSize / (self.gridSize - 1)
+        self.stepSize = torch.mean(self.units) * self.step_ratio
+        self.aabbDiag = torch.sqrt(torch.sum(torch.square(self.aabbSize)))
+        self.nSamples = int((self.aabbDiag / self.stepSize).item()) + 1
+        self._invalidate()
+
+    def init_model(self, **kw):
+        raise NotImplementedError
+
+    @property
+    def alphaMask(self):
+        return self._alphaMask
+
+    def __setattr__(self, name, value):
+        # nn.Module.__setattr__ would register an AlphaGridMask as a sub-module and bypass a property setter;
+        # intercept it so the mask is attached to this field and the packed handle is refreshed.
+        if name == "alphaMask":
+            object.__setattr__(self, "_alphaMask", value)
+            if value is not None:
+                value._owner = weakref.ref(self)
+            self._invalidate()
+            return
+        super().__setattr__(name, value)
+
+    def normalize_coord(self, xyz_sampled):
+        return (xyz_sampled - self.aabb[0]) * self.invaabbSize - 1
+
+    def get_optparam_groups(self, lr_init_spatial=0.02, lr_init_network=0.001):
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ checkpoint format (FieldBase.py:94-116)
+    def get_kwargs(self):
+        return {'aabb': self.aabb, 'gridSize': self.gridSize.tolist(), 'alphaMask_thres': self.alphaMask_thres,
+                'distance_scale': self.distance_scale, 'rayMarch_weight_thres': self.rayMarch_weight_thres,
+                'near_far': self.near_far, 'step_ratio': self.step_ratio}
+
+    def save(self, path):
+        ckpt = {'kwargs': self.get_kwargs(), 'state_dict': self.state_dict()}
+        if self.alphaMask is not None:
+            alpha_volume = self.alphaMask.alpha_volume.bool().cpu().numpy()
+            ckpt.update({'alphaMask.shape': alpha_volume.shape})
+            ckpt.update({'alphaMask.mask': np.packbits(alpha_volume.reshape(-1))})
+            ckpt.update({'alphaMask.aabb': self.alphaMask.aabb.cpu()})
+        torch.save(ckpt, path)
+
+    def load(self, ckpt):
+        if 'alphaMask.aabb' in ckpt.keys():
+            length = int(np.prod(ckpt['alphaMask.shape']))
+            alpha_volume = torch.from_numpy(
+                np.unpackbits(ckpt['alphaMask.mask'])[:length].reshape(ckpt['alphaMask.shape']))
+            self.alphaMask = AlphaGridMask(self.device, ckpt['alphaMask.aabb'].to(self.device),
+                                           alpha_volume.float().to(self.device))
+        self.load_state_dict(ckpt['state_dict'])
+        self._invalidate()
+
+    # ------------------------------------------------------------------ C-ABI handle management
+    def _invalidate(self):
+        self._handle_sig = None
+
+    def _free_handle(self):
+        if getattr(self, "_handle", None):
+            _lib.load().ngf_field_free(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._free_handle()
+        except Exception:
+            pass
+
+    def _require_cuda(self):
+        if self.device.type != "cuda":
+            raise RuntimeError("ngf_b200 fields run on a CUDA device only (there is no CPU fallback); "
+                               f"this field was constructed with device={self.device}")
+
+    def _signature(self):
+        """Cheap staleness key (no device reads): parameter storage + in-place version counters, the mask, and the
+        python-side scalars.  aabb / stepSize / nSamples only change through init_para(), which invalidates."""
+        sig = [(p.data_ptr(), p._version) for p in self.parameters()]
+        am = self.alphaMask
+        sig.append(None if am is None else (id(am), am.alpha_volume.data_ptr(), am.alpha_volume._version))
+        sig.append((tuple(float(x) for x in self.near_far), float(self.distance_scale),
+                    float(self.rayMarch_weight_thres)))
+        return sig
+
+    def _fill_common(self, d: _lib.NgfFieldDesc, keep: list):
+        def lin(mod, need_bias=True):
+            w = _f32c(mod.weight)
+            keep.append(w)
+            b = None
+            if mod.bias is not None:
+                b = _f32c(mod.bias)
+                keep.append(b)
+            return _lib.NgfLinear(w.data_ptr(), b.data_ptr() if b is not None else None, mod.in_features,
+                                  mod.out_features)
+
+        planes = [self.plane_xy, self.plane_yz, self.plane_xz]
+        for i, p in enumerate(planes):
+            t = _f32c(p)
+            keep.append(t)
+            d.plane[i] = t.data_ptr()
+            d.plane_h[i], d.plane_w[i] = t.shape[2], t.shape[3]
+        d.plane_c = planes[0].shape[1]
+        d.rgb_basis = lin(self.rgb_decoder.basis)
+        d.rgb_l1, d.rgb_l2, d.rgb_l3 = (lin(self.rgb_decoder.mlp[i]) for i in (0, 2, 4))
+        d.view_pe = int(self.rgb_decoder.view_pe)
+        d.density_shift = -10.0
+        aabb = self.aabb.detach().float().cpu()
+        inv = self.invaabbSize.detach().float().cpu()
+        for k in range(3):
+            d.aabb[k] = float(aabb[0, k])
+            d.aabb[3 + k] = float(aabb[1, k])
+            d.inv_aabb_size[k] = float(inv[k])
+        d.step_size = float(self.stepSize.detach().float().cpu())
+        d.n_samples = int(self.nSamples)
+        d.near_t, d.far_t = float(self.near_far[0]), float(self.near_far[1])
+        d.distance_scale = float(self.distance_scale)
+        d.weight_thres = float(self.rayMarch_weight_thres)
+        am = self.alphaMask
+        if am is not None:
+            vol = _f32c(am.alpha_volume)
+            keep.append(vol)
+            d.alpha_volume = vol.data_ptr()
+            D_, H_, W_ = vol.shape[-3:]
+            d.alpha_dims[0], d.alpha_dims[1], d.alpha_dims[2] = W_, H_, D_
+            ab = am.aabb.detach().float().cpu()
+            ai = am.invgridSize.detach().float().cpu()
+            for k in range(3):
+                d.alpha_aabb[k] = float(ab[0, k])
+                d.alpha_aabb[3 + k] = float(ab[1, k])
+                d.alpha_inv[k] = float(ai[k])
+        else:
+            d.alpha_volume = None
+
+    def _fill_desc(self, d: _lib.NgfFieldDesc, keep: list):
+        raise NotImplementedError
+
+    def _ensure_handle(self):
+        self._require_cuda()
+        sig = self._signature()
+        if self._handle is not None and sig == self._handle_sig:
+            return self._handle
+        lib = _lib.load()
+        d = _lib.NgfFieldDesc()
+        keep: list = []
+        self._fill_desc(d, keep)
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        torch.cuda.synchronize(self.device)
+        self._free_handle()
+        h = C.c_void_p()
+        _lib.check(lib.ngf_field_pack(C.byref(d), dev_index, C.byref(h)), "ngf_field_pack")
+        self._handle = h
+        self._handle_sig = sig
+        return h
+
+    def set_mlp_impl(self, name: str):
+        """'tcgen05' (default) or 'simt' (CUDA-core cross-check of the same packed weights)."""
+        self._mlp_impl = {"tcgen05": _lib.MLP_TCGEN05, "simt": _lib.MLP_SIMT}[name]
+
+    # ------------------------------------------------------------------ the render path
+    def _set_switches(self, lib, h, **fwd_kw):
+        pass
+
+    @torch.no_grad()
+    def forward(self, rays_chunk, white_bg=True, is_train=False, N_samples=-1, image_width=0, **fwd_kw):
+        """Reference: Base.forward (FieldBase.py:251-312).  Returns {'rgb_map': [R,3], 'depth_map': [R]} on the
+        field's device.  ``image_width`` (optional, not in the reference) tells the kernel that the rays are the
+        row-major pixels of an image so warps can take 8x4 pixel blocks."""
+        if is_train:
+            raise NotImplementedError("training-time forward (jittered samples + autograd) is not part of the "
+                                      "B200 render path yet (SURVEY.md §8f row 3)")
+        h = self._ensure_handle()
+        lib = _lib.load()
+        self._set_switches(lib, h, **fwd_kw)
+        rays = rays_chunk
+        if rays.device != self.device:
+            rays = rays.to(self.device, non_blocking=True)
+        rays = _f32c(rays)
+        if rays.dim() != 2 or rays.shape[1] < 6:
+            raise ValueError(f"rays must be [R, >=6], got {tuple(rays.shape)}")
+        R = rays.shape[0]
+        rgb = torch.empty((R, 3), dtype=torch.float32, device=self.device)
+        depth = torch.empty((R,), dtype=torch.float32, device=self.device)
+        acc = torch.empty((R,), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.ngf_field_render(h, rays.data_ptr(), R, rays.shape[1], int(N_samples), int(bool(white_bg)),
+                                            int(image_width), rgb.data_ptr(), depth.data_ptr(), acc.data_ptr(),
+                                            self._mlp_impl, _cuda_stream_ptr(self.device)), "ngf_field_render")
+        self._last_acc = acc
+        return {'rgb_map': rgb, 'depth_map': depth}
+
+    @torch.no_grad()
+    def render_host(self, rays_host, rgb_host=None, depth_host=None, white_bg=True, N_samples=-1, image_width=0,
+                    **fwd_kw):
+        """Whole-frame render through HOST buffers (ngf_field_render_host): H2D, kernels and D2H are chunked and
+        overlapped inside the library.  ``rays_host`` should be pinned for full copy bandwidth."""
+        h = self._ensure_handle()
+        lib = _lib.load()
+        self._set_switches(lib, h, **fwd_kw)
+        if rays_host.device.type != "cpu" or rays_host.dtype != torch.float32 or not rays_host.is_contiguous():
+            raise ValueError("rays_host must be a contiguous fp32 CPU tensor")
+        R = rays_host.shape[0]
+        if rgb_host is None:
+            rgb_host = torch.empty((R, 3), dtype=torch.float32).pin_memory()
+        if depth_host is None:
+            depth_host = torch.empty((R,), dtype=torch.float32).pin_memory()
+        _lib.check(lib.ngf_field_render_host(h, rays_host.data_ptr(), R, rays_host.shape[1], int(N_samples),
+                                             int(bool(white_bg)), int(image_width), rgb_host.data_ptr(),
+                                             depth_host.data_ptr(), self._mlp_impl), "ngf_field_render_host")
+        return rgb_host, depth_host
+
+    def last_stats(self) -> dict:
+        """Counters of the last device-side render (forces a stream sync)."""
+        st = _lib.NgfStats()
+        _lib.check(_lib.load().ngf_field_stats(self._ensure_handle(), C.byref(st), _cuda_stream_ptr(self.device)))
+        return {k: int(getattr(st, k)) for k, _ in st._fields_}
+
+    # ------------------------------------------------------------------ point-wise API parity
+    def _pts_call(self, fn_name, inputs, out_shapes, out_dtypes, *extra_before_out, extra_after=()):
+        raise NotImplementedError
+
+    @torch.no_grad()
+    def sample_ray(self, rays_o, rays_d, is_train=True, N_samples=-1):
+        """Reference: Base.sample_ray (FieldBase.py:118-137), eval branch.  -> (rays_pts [R,S,3], interpx [R,S],
+        ~mask_outbbox [R,S] bool)."""
+        if is_train:
+            raise NotImplementedError("jittered training-time sampling is not part of the B200 render path yet")
+        h = self._ensure_handle()
+        S = N_samples if N_samples > 0 else self.nSamples
+        rays = _f32c(torch.cat([rays_o, rays_d], -1).to(self.device))
+        R = rays.shape[0]
+        pts = torch.empty((R, S, 3), dtype=torch.float32, device=self.device)
+        t = torch.empty((R, S), dtype=torch.float32, device=self.device)
+        inside = torch.empty((R, S), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().ngf_field_sample_ray(h, rays.data_ptr(), R, 6, S, pts.data_ptr(), t.data_ptr(),
+                                                        inside.data_ptr(), _cuda_stream_ptr(self.device)))
+        return pts, t, inside.bool()
+
+    @torch.no_grad()
+    def _alpha_keep(self, xyz):
+        h = self._ensure_handle()
+        pts = _f32c(xyz.to(self.device)).view(-1, 3)
+        keep = torch.empty((pts.shape[0],), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().ngf_field_alpha_keep(h, pts.data_ptr(), pts.shape[0], keep.data_ptr(),
+                                                        _cuda_stream_ptr(self.device)))
+        return keep.bool()
+
+    @torch.no_grad()
+    def _coords(self, valid_xyz, gauge_on: bool):
+        h = self._ensure_handle()
+        xyz = _f32c(valid_xyz.to(self.device)).view(-1, 3)
+        n = xyz.shape[0]
+        outs = [torch.empty((n, 2), dtype=torch.float32, device=self.device) for _ in range(3)]
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().ngf_field_gauge(h, xyz.data_ptr(), n, int(gauge_on), outs[0].data_ptr(),
+                                                   outs[1].data_ptr(), outs[2].data_ptr(),
+                                                   _cuda_stream_ptr(self.device)))
+        return tuple(outs)
+
+    @torch.no_grad()
+    def _density(self, xy, yz, xz):
+        h = self._ensure_handle()
+        a, b, c = (_f32c(t.to(self.device)).view(-1, 2) for t in (xy, yz, xz))
+        n = a.shape[0]
+        out = torch.empty((n,), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().ngf_field_density(h, a.data_ptr(), b.data_ptr(), c.data_ptr(), n, out.data_ptr(),
+                                                     _cuda_stream_ptr(self.device)))
+        return out
+
+    @torch.no_grad()
+    def _rgb(self, xy, yz, xz, view_sampled):
+        h = self._ensure_handle()
+        a, b, c = (_f32c(t.to(self.device)).view(-1, 2) for t in (xy, yz, xz))
+        v = _f32c(view_sampled.to(self.device)).view(-1, 3)
+        n = a.shape[0]
+        out = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().ngf_field_rgb(h, a.data_ptr(), b.data_ptr(), c.data_ptr(), v.data_ptr(), n,
+                                                 out.data_ptr(), self._mlp_impl, _cuda_stream_ptr(self.device)))
+        return out
+
+    @torch.no_grad()
+    def _sigma_world(self, xyz_locs, use_gauge=False):
+        h = self._ensure_handle()
+        pts = _f32c(xyz_locs.to(self.device)).view(-1, 3)
+        out = torch.empty((pts.shape[0],), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().ngf_field_sigma_world(h, pts.data_ptr(), pts.shape[0], int(use_gauge),
+                                                         out.data_ptr(), _cuda_stream_ptr(self.device)))
+        return out
+
+    # ------------------------------------------------------------------ occupancy maintenance (FieldBase.py:140-215)
+    @torch.no_grad()
+    def compute_alpha(self, xyz_locs, length=1, **kw):
+        """Reference: Base.compute_alpha (FieldBase.py:140-159): alpha = 1 - exp(-sigma * length) with the gauge off."""
+        self._apply_alpha_kw(**kw)
+        sigma = self._sigma_world(xyz_locs.view(-1, 3), use_gauge=False)
+        return (1 - torch.exp(-sigma * length)).view(xyz_locs.shape[:-1])
+
+    def _apply_alpha_kw(self, **kw):
+        pass
+
+    @torch.no_grad()
+    def getDenseAlpha(self, gridSize=None, **kw):
+        """Reference: Base.getDenseAlpha (FieldBase.py:161-177)."""
+        gridSize = self.gridSize if gridSize is None else gridSize
+        gs = [int(g) for g in gridSize]
+        samples = torch.stack(torch.meshgrid(torch.linspace(0, 1, gs[0]), torch.linspace(0, 1, gs[1]),
+                                             torch.linspace(0, 1, gs[2]), indexing="ij"), -1).to(self.device)
+        dense_xyz = self.aabb[0] * (1 - samples) + self.aabb[1] * samples
+        alpha = torch.zeros_like(dense_xyz[..., 0])
+        for i in range(gs[0]):
+            alpha[i] = self.compute_alpha(dense_xyz[i].view(-1, 3), self.stepSize, **kw).view((gs[1], gs[2]))
+        return alpha, dense_xyz
+
+    @torch.no_grad()
+    def updateAlphaMask(self, gridSize=(200, 200, 200), **kw):
+        """Reference: Base.updateAlphaMask (FieldBase.py:179-215): dense alpha -> 3x3x3 max-pool -> threshold ->
+        new AlphaGridMask; returns the tight box of the occupied voxels."""
+        gs = [int(g) for g in gridSize]
+        alpha, dense_xyz = self.getDenseAlpha(gs, **kw)
+        dense_xyz = dense_xyz.transpose(0, 2).contiguous()
+        alpha = alpha.clamp(0, 1).transpose(0, 2).contiguous()[None, None]
+        alpha = F.max_pool3d(alpha, kernel_size=3, padding=1, stride=1).view(gs[::-1])
+        alpha[alpha >= self.alphaMask_thres] = 1
+        alpha[alpha < self.alphaMask_thres] = 0
+        self.alphaMask = AlphaGridMask(self.device, self.aabb, alpha)
+        valid_xyz = dense_xyz[alpha > 0.5]
+        new_aabb = torch.stack((valid_xyz.amin(0), valid_xyz.amax(0)))
+        return new_aabb
+
+    @torch.no_grad()
+    def filtering_rays(self, all_rays, all_rgbs, N_samples=256, chunk=10240 * 5, bbox_only=False):
+        """Reference: Base.filtering_rays (FieldBase.py:217-246).  Keeps rays that hit the box (bbox_only) or pass
+        through an occupied cell."""
+        N = int(torch.tensor(all_rays.shape[:-1]).prod())
+        flat = all_rays.reshape(N, all_rays.shape[-1])
+        keep = []
+        for s in range(0, N, chunk):
+            rays_chunk = flat[s:s + chunk].to(self.device)
+            rays_o, rays_d = rays_chunk[..., :3], rays_chunk[..., 3:6]
+            if bbox_only:
+                vec = torch.where(rays_d == 0, torch.full_like(rays_d, 1e-6), rays_d)
+                rate_a = (self.aabb[1] - rays_o) / vec
+                rate_b = (self.aabb[0] - rays_o) / vec
+                t_min = torch.minimum(rate_a, rate_b).amax(-1)
+                t_max = torch.maximum(rate_a, rate_b).amin(-1)
+                mask = t_max > t_min
+            else:
+                pts, _, _ = self.sample_ray(rays_o, rays_d, N_samples=N_samples, is_train=False)
+                mask = self._alpha_keep(pts.view(-1, 3)).view(pts.shape[:-1]).any(-1)
+            keep.append(mask.cpu())
+        mask_filtered = torch.cat(keep).view(all_rgbs.shape[:-1])
+        return all_rays[mask_filtered], all_rgbs[mask_filtered]

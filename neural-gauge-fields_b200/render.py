@@ -1,0 +1,101 @@
+"""``renderer`` with the reference's signature (TriPlane/main.py:60-71, InfoInv/main.py:61-72) and the multi-GPU
+ray-sharded frame render (interleaved ray blocks per rank + one all-gather of the frame).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .field_base import _cuda_stream_ptr
+
+
+@torch.no_grad()
+def renderer(rays, field, chunk=4096, N_samples=-1, white_bg=True, is_train=False, device='cuda', image_width=0,
+             **fwd_kw):
+    """Reference: ``renderer`` (TriPlane/main.py:60-71).  The reference slices the frame into ``chunk``-ray pieces
+    and calls the field once per piece; the fused kernel takes the whole frame in one launch, so ``chunk`` is
+    accepted for signature compatibility and ignored.  ``fwd_kw`` defaults to what the reference passes
+    (``iteration=30001`` for TriPlane, main.py:67; ``infoinv`` for InfoInv)."""
+    if not fwd_kw and hasattr(field, "gauge_start"):
+        fwd_kw = {"iteration": 30001}
+    out = field(rays, is_train=is_train, white_bg=white_bg, N_samples=N_samples, image_width=image_width, **fwd_kw)
+    return out['rgb_map'], out['depth_map']
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ray sharding: global ray g belongs to rank (g // block) % world; local index (g // (block*world))*block + g % block
+# ---------------------------------------------------------------------------------------------------------------
+def shard_count(n_rays: int, block: int, rank: int, world: int) -> int:
+    n = _lib.load().ngf_shard_count(n_rays, block, rank, world)
+    if n < 0:
+        raise ValueError("bad shard arguments")
+    return int(n)
+
+
+def shard_index(n_rays: int, block: int, rank: int, world: int) -> torch.Tensor:
+    """Global indices of the rays rank owns, in local order (host-side index arithmetic, used by CPU tests and as
+    the specification of ngf_shard_gather/scatter)."""
+    g = torch.arange(n_rays)
+    return g[((g // block) % world) == rank]
+
+
+def shard_rays(rays: torch.Tensor, block: int, rank: int, world: int) -> torch.Tensor:
+    """Rows of ``rays`` [R, C] this rank renders.  CUDA tensors go through ngf_shard_gather."""
+    if world == 1:
+        return rays
+    R, Cn = rays.shape
+    if rays.is_cuda:
+        n = shard_count(R, block, rank, world)
+        out = torch.empty((n, Cn), dtype=torch.float32, device=rays.device)
+        src = rays.contiguous()
+        with torch.cuda.device(rays.device):
+            _lib.check(_lib.load().ngf_shard_gather(src.data_ptr(), R, Cn, block, rank, world, out.data_ptr(),
+                                                    _cuda_stream_ptr(rays.device)))
+        return out
+    return rays[shard_index(R, block, rank, world)]
+
+
+def unshard_frame(gathered: torch.Tensor, n_rays: int, block: int, world: int) -> torch.Tensor:
+    """Inverse of the all-gather: ``gathered`` [world, max_shard, C] (rank-major) -> [n_rays, C] in frame order."""
+    world_, max_shard, Cn = gathered.shape
+    assert world_ == world
+    if gathered.is_cuda:
+        out = torch.empty((n_rays, Cn), dtype=torch.float32, device=gathered.device)
+        src = gathered.contiguous()
+        with torch.cuda.device(gathered.device):
+            _lib.check(_lib.load().ngf_shard_scatter(src.data_ptr(), n_rays, Cn, block, world, max_shard,
+                                                     out.data_ptr(), _cuda_stream_ptr(gathered.device)))
+        return out
+    out = torch.empty((n_rays, Cn), dtype=gathered.dtype)
+    for r in range(world):
+        idx = shard_index(n_rays, block, r, world)
+        out[idx] = gathered[r, :idx.numel()]
+    return out
+
+
+def frame_allgather(local: torch.Tensor, n_rays: int, block: int, group=None) -> torch.Tensor:
+    """All-gather the per-rank [n_local, C] results of a ray-sharded frame and restore frame order.
+    One collective per frame (NCCL on GPU; gloo in the CPU tests)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    max_shard = -(-(-(-n_rays // block)) // world) * block          # ceil(ceil(n/block)/world)*block
+    buf = torch.zeros((max_shard, local.shape[1]), dtype=local.dtype, device=local.device)
+    buf[:local.shape[0]] = local
+    out = torch.empty((world, max_shard, local.shape[1]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out.view(world * max_shard, -1), buf, group=group)
+    return unshard_frame(out, n_rays, block, world)
+
+
+@torch.no_grad()
+def render_frame_sharded(rays, field, block=2048, N_samples=-1, white_bg=True, group=None, **fwd_kw):
+    """Render one frame with its rays dealt to the ranks of ``group`` in interleaved blocks and return the full
+    [R, 4] (rgb, depth) frame on every rank."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    R = rays.shape[0]
+    mine = shard_rays(rays, block, rank, world)
+    rgb, depth = renderer(mine, field, N_samples=N_samples, white_bg=white_bg, **fwd_kw)
+    local = torch.cat([rgb, depth[:, None]], 1)
+    return frame_allgather(local, R, block, group)

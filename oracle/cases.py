@@ -1,0 +1,135 @@
+"""TEST INFRASTRUCTURE — the parity cases shared by ``oracle/make_golden.py`` (which runs the imported reference
+on them in the build container) and ``tests/`` (which run the oracle restatement and the CUDA path on them).
+
+Every case is regenerated from seeds by ``ngf_b200.synth``; a golden file stores only the reference's outputs and a
+checksum of the inputs, so fixtures stay small (tests/golden/*.npz).
+"""
+from __future__ import annotations
+
+import functools
+import hashlib
+import importlib.util
+import os
+from dataclasses import dataclass, field as dc_field
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load_synth():
+    # loaded by path so that importing the cases never imports the product package (and its CUDA library)
+    spec = importlib.util.spec_from_file_location("_ngf_synth", os.path.join(_ROOT, "neural-gauge-fields_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+synth = _load_synth()
+
+
+@dataclass
+class Case:
+    name: str
+    variant: str = "triplane"            # "triplane" | "infoinv"
+    kind: str = "hull"                   # synth.field_state kind
+    config: str = "C1"
+    pose: int = 0
+    n_samples: int = 64                  # forward(N_samples=...); -1 = field.nSamples
+    white_bg: bool = True
+    mask: bool = True                    # attach an alpha mask
+    gauge_on: bool = True                # TriPlane: iteration >= gauge_start
+    infoinv: bool = True                 # InfoInv: forward(infoinv=...)
+    res: Tuple[int, int, int] = (256, 256, 256)       # plane resolution (X, Y, Z)
+    aabb: Optional[list] = None          # model box (default synth.AABB); the mask keeps the default box
+    step_ratio: Optional[float] = None
+    seed: int = 1234
+    ray_cols: int = 6                    # 8: two extra columns (the last one feeds the depth background term)
+    max_rays: int = 0                    # > 0: keep a strided subset of the frame's rays
+    extra: dict = dc_field(default_factory=dict)
+
+
+CASES = [
+    Case("tp_hull_c1"),
+    Case("tp_fog_c1", kind="fog"),
+    Case("tp_rand_c1", kind="rand"),
+    Case("tp_hull_nomask", mask=False),
+    Case("tp_hull_nogauge", gauge_on=False, pose=3),
+    Case("tp_fog_blackbg", kind="fog", white_bg=False, pose=5),
+    Case("tp_fog_full_march", kind="fog", n_samples=-1, step_ratio=3.0, pose=7, max_rays=1024),
+    # after up_sampling / shrink (Field.py:108-132): non-square planes, tighter model box, mask keeps its own box
+    Case("tp_fog_shrunk", kind="fog", res=(200, 168, 232), aabb=[[-1.1, -0.9, -1.2], [1.0, 0.95, 1.25]], pose=11),
+    Case("tp_rand_cols8", kind="rand", ray_cols=8, pose=2, max_rays=2048),
+    Case("ii_hull_c1", variant="infoinv"),
+    Case("ii_fog_c1", variant="infoinv", kind="fog", pose=4),
+    Case("ii_rand_noinv", variant="infoinv", kind="rand", infoinv=False, pose=6, max_rays=2048),
+    Case("ii_fog_shrunk", variant="infoinv", kind="fog", res=(180, 256, 140), aabb=[[-1.0, -1.2, -0.8], [1.2, 1.0, 1.1]],
+         pose=9, white_bg=False),
+]
+CASE_BY_NAME = {c.name: c for c in CASES}
+
+
+@functools.lru_cache(maxsize=8)
+def _field_state(variant, kind, seed, res):
+    return synth.field_state(variant, kind, seed=seed, res=res)       # treated as read-only by every user
+
+
+@functools.lru_cache(maxsize=4)
+def _occupancy(kind):
+    return synth.occupancy_volume(kind)
+
+
+def build_inputs(case: Case):
+    """-> (state_dict, ctor kwargs, occupancy volume or None, rays [R, ray_cols])."""
+    kw = synth.field_kwargs(case.config)
+    if case.step_ratio is not None:
+        kw["step_ratio"] = case.step_ratio
+    grid = list(case.res)
+    kw["gridSize"] = grid
+    if case.aabb is not None:
+        kw["aabb"] = torch.tensor(case.aabb, dtype=torch.float32)
+    state = _field_state(case.variant, case.kind, case.seed, tuple(case.res))
+    occ = _occupancy(case.kind) if case.mask else None
+    rays = synth.config_rays(case.config, case.pose)
+    if case.max_rays and rays.shape[0] > case.max_rays:
+        rays = rays[:: rays.shape[0] // case.max_rays][: case.max_rays].contiguous()
+    if case.ray_cols > 6:
+        g = torch.Generator().manual_seed(case.seed + 1)
+        rays = torch.cat([rays, torch.rand((rays.shape[0], case.ray_cols - 6), generator=g) * 4 + 2], 1).contiguous()
+    return state, kw, occ, rays
+
+
+def mask_aabb() -> torch.Tensor:
+    """The alpha mask always covers the default box (it is built before ``shrink`` in the reference's training
+    schedule, main.py:333-342), so shrunk cases exercise a mask box different from the model box."""
+    return torch.tensor(synth.AABB, dtype=torch.float32)
+
+
+def fingerprint(state, rays, occ) -> str:
+    h = hashlib.sha256()
+    for k in sorted(state):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(state[k].numpy()).tobytes())
+    h.update(np.ascontiguousarray(rays.numpy()).tobytes())
+    if occ is not None:
+        h.update(np.packbits(occ.numpy() > 0).tobytes())
+    return h.hexdigest()
+
+
+def golden_path(name: str) -> str:
+    return os.path.join(_ROOT, "tests", "golden", f"{name}.npz")
+
+
+# point-wise fixture: inputs for compute_gauge / compute_density / compute_rgb / sample_alpha / sample_ray
+def pointwise_inputs(n: int = 2048, seed: int = 7):
+    g = torch.Generator().manual_seed(seed)
+    xyz = torch.rand((n, 3), generator=g) * 2.2 - 1.1          # some points outside [-1,1]^3 (zero padding)
+    xyz[:16] = torch.tensor([-1.0, 0.0, 1.0])[torch.randint(0, 3, (16, 3), generator=g)]   # exact lattice points
+    dirs = torch.randn((n, 3), generator=g)
+    dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+    world = (torch.rand((n, 3), generator=g) * 2 - 1) * 1.6
+    lattice = torch.linspace(-1.5, 1.5, 256)
+    world[:64] = lattice[torch.randint(0, 256, (64, 3), generator=g)]                      # exact voxel centres
+    return xyz.contiguous(), dirs.contiguous(), world.contiguous()
