@@ -119,7 +119,7 @@ typedef struct NgfStats {
   uint64_t samples_in_box;  /* samples inside the box after the conservative range clip   */
   uint64_t samples_density; /* density evaluations: valid samples (bbox and alpha mask)    */
   uint64_t samples_colour;  /* colour-MLP evaluations: weight > weight_thres               */
-  uint64_t mlp_tiles;       /* 128-sample tensor-core tiles issued                         */
+  uint64_t mlp_tiles;       /* 128-sample colour-MLP tiles issued                          */
 } NgfStats;
 
 typedef struct NgfField_* NgfField;
@@ -130,9 +130,9 @@ const char* ngf_last_error(void);
 uint64_t ngf_launch_count(void);
 
 /*
- * Build the device-side shadows of a field on `device`: channels-last fp32 density texels, channels-last fp16
- * appearance texels, float2 gauge texels, bit-packed occupancy grid, folded (basis . mlp.0) fp16 weights in
- * tcgen05 shared-memory layout.
+ * Build the device-side shadows of a field on `device`: density texels projected through the density head
+ * (TriPlane) or channels-last fp32 (InfoInv), channels-last fp16 appearance texels, float2 gauge texels,
+ * bit-packed occupancy grids, folded (basis . mlp.0) fp16 weights in tcgen05 shared-memory layout.
  * Replaces: TriPlane.__init__/init_model + Base.load (Field.py:14-32, FieldBase.py:111-116) as far as the
  * render path is concerned.  Synchronous.
  */
@@ -171,6 +171,15 @@ int ngf_field_set_infoinv(NgfField f, int32_t on);
 
 /* Copy the counters of the last render on `stream` (synchronises that stream). */
 int ngf_field_stats(NgfField f, NgfStats* out, void* stream);
+
+/*
+ * Device-side timing of the two render kernels (bench.py's roofline): after ngf_field_timing_begin every
+ * ngf_field_render brackets its ngf_march_kernel and ngf_colour_kernel launches with CUDA events recorded on the
+ * launching stream (up to `capacity` march+colour pairs; 0 switches it off).  ngf_field_timing_read synchronises
+ * the recorded events and returns the number of pairs timed and the summed durations in milliseconds, then rearms.
+ */
+int ngf_field_timing_begin(NgfField f, int32_t capacity);
+int ngf_field_timing_read(NgfField f, int32_t* n_launches, double* march_ms, double* colour_ms);
 
 /*
  * Point-wise queries (API parity with the reference's public methods).

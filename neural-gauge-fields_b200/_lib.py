@@ -60,6 +60,9 @@ SIGNATURES = {
     "ngf_field_set_gauge": (C.c_int, [C.c_void_p, C.c_int32]),
     "ngf_field_set_infoinv": (C.c_int, [C.c_void_p, C.c_int32]),
     "ngf_field_stats": (C.c_int, [C.c_void_p, C.POINTER(NgfStats), C.c_void_p]),
+    "ngf_field_timing_begin": (C.c_int, [C.c_void_p, C.c_int32]),
+    "ngf_field_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                        C.POINTER(C.c_double)]),
     "ngf_field_sample_ray": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "ngf_field_alpha_keep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

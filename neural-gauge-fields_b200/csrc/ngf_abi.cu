@@ -57,12 +57,13 @@ struct HostChunk {            // one in-flight chunk of the host-buffer render p
   float* depth = nullptr;
   float* acc = nullptr;
   unsigned int* counters = nullptr;
+  QEntry* queue = nullptr;
+  long long queue_cap = 0;
 };
 
 struct NgfField_ {
   int device = 0;
   int num_sms = 0;
-  int lbo_swap = 0;
   int has_gauge = 0;
   FieldDev dev{};
   int n_samples_default = 0;
@@ -72,6 +73,9 @@ struct NgfField_ {
   __half* app[3] = {nullptr, nullptr, nullptr};
   float2* gauge[3] = {nullptr, nullptr, nullptr};
   uint32_t* occ = nullptr;
+  uint32_t* occ2 = nullptr;
+  uint32_t* occ_coarse = nullptr;
+  float* dsum[3] = {nullptr, nullptr, nullptr};
   float* dmlp = nullptr;
   __half* w1p = nullptr;
   __half* w2p = nullptr;
@@ -79,7 +83,12 @@ struct NgfField_ {
   // render workspace
   float* acc_ws = nullptr;
   long long acc_cap = 0;
-  unsigned int* counters = nullptr;   // [0] tile counter, [2..9] = 4 x u64 stats
+  unsigned int* counters = nullptr;   // [0] tile counter, [1] queue count, [2..9] = 4 x u64 stats
+  QEntry* queue = nullptr;            // colour work items of the device-resident path
+  long long queue_cap = 0;
+  // kernel timing (ngf_field_timing_*)
+  std::vector<cudaEvent_t> ev;        // 3 per timed march+colour pair
+  int ev_used = 0;
   // host path
   HostChunk chunk[2];
   long long chunk_cap = 0;
@@ -91,16 +100,25 @@ static const int kCounterBytes = 64;
 static void free_chunks(NgfField_* h) {
   for (auto& c : h->chunk) {
     if (c.stream) cudaStreamDestroy(c.stream);
-    cudaFree(c.rays); cudaFree(c.rgb); cudaFree(c.depth); cudaFree(c.acc); cudaFree(c.counters);
+    cudaFree(c.rays); cudaFree(c.rgb); cudaFree(c.depth); cudaFree(c.acc); cudaFree(c.counters); cudaFree(c.queue);
     c = HostChunk{};
   }
   h->chunk_cap = 0;
 }
 
+static void free_events(NgfField_* h) {
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  h->ev.clear();
+  h->ev_used = 0;
+}
+
 static void free_all(NgfField_* h) {
+  free_events(h);
   for (int i = 0; i < 3; ++i) { cudaFree(h->dens[i]); cudaFree(h->app[i]); cudaFree(h->gauge[i]); }
-  cudaFree(h->occ); cudaFree(h->dmlp); cudaFree(h->w1p); cudaFree(h->w2p); cudaFree(h->tail);
-  cudaFree(h->acc_ws); cudaFree(h->counters);
+  for (int i = 0; i < 3; ++i) cudaFree(h->dsum[i]);
+  cudaFree(h->occ); cudaFree(h->occ2); cudaFree(h->occ_coarse);
+  cudaFree(h->dmlp); cudaFree(h->w1p); cudaFree(h->w2p); cudaFree(h->tail);
+  cudaFree(h->acc_ws); cudaFree(h->counters); cudaFree(h->queue);
   free_chunks(h);
 }
 
@@ -203,6 +221,7 @@ static int pack_params(NgfField_* h, const NgfFieldDesc* d, bool allocate) {
     if (allocate) {
       CU(dev_alloc(&h->dens[i], hw * DC));
       CU(dev_alloc(&h->app[i], hw * AC));
+      if (V == 0) CU(dev_alloc(&h->dsum[i], hw));
     } else if (H != f.plane[i].H || W != f.plane[i].W) {
       return fail(NGF_EINVAL, "repack: plane[%d] changed shape (%dx%d -> %dx%d); pack a new handle", i, f.plane[i].H,
                   f.plane[i].W, H, W);
@@ -214,7 +233,7 @@ static int pack_params(NgfField_* h, const NgfFieldDesc* d, bool allocate) {
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaFree(tmp);
     CU(e);
-    f.plane[i] = PlaneDev{h->dens[i], h->app[i], H, W, (float)(W - 1), (float)(H - 1)};
+    f.plane[i] = PlaneDev{h->dens[i], h->dsum[i], h->app[i], H, W, (float)(W - 1), (float)(H - 1)};
   }
   // ---- gauge planes
   for (int i = 0; i < 3; ++i) {
@@ -236,10 +255,12 @@ static int pack_params(NgfField_* h, const NgfFieldDesc* d, bool allocate) {
     CU(e);
     f.gauge[i] = GaugeDev{h->gauge[i], H, W, (float)(W - 1), (float)(H - 1)};
   }
-  // ---- occupancy grid
+  // ---- occupancy grid: raw bits, "any corner" brick grid, coarse grid, occupied box
+  cudaFree(h->occ); cudaFree(h->occ2); cudaFree(h->occ_coarse);
+  h->occ = h->occ2 = h->occ_coarse = nullptr;
   if (d->alpha_volume) {
-    const long long n = (long long)d->alpha_dims[0] * d->alpha_dims[1] * d->alpha_dims[2];
-    if (h->occ) { cudaFree(h->occ); h->occ = nullptr; }
+    const int W = d->alpha_dims[0], H = d->alpha_dims[1], D = d->alpha_dims[2];
+    const long long n = (long long)W * H * D;
     CU(dev_alloc(&h->occ, (size_t)((n + 31) / 32)));
     float* tmp = nullptr;
     CU(dev_alloc(&tmp, (size_t)n));
@@ -248,14 +269,46 @@ static int pack_params(NgfField_* h, const NgfFieldDesc* d, bool allocate) {
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaFree(tmp);
     CU(e);
-    f.occ = h->occ;
-    f.occ_w = d->alpha_dims[0]; f.occ_h = d->alpha_dims[1]; f.occ_d = d->alpha_dims[2];
+    const int nxb = (W + 1 + 3) / 4, nyb = (H + 1 + 3) / 4, nzb = (D + 1 + 1) / 2;
+    const int cx = (W + 1 + 7) / 8, cy = (H + 1 + 7) / 8, cz = (D + 1 + 7) / 8;
+    const size_t n2 = (size_t)nxb * nyb * nzb, nc = ((size_t)cx * cy * cz + 31) / 32;
+    CU(dev_alloc(&h->occ2, n2));
+    CU(dev_alloc(&h->occ_coarse, nc));
+    CU(cudaMemset(h->occ2, 0, n2 * sizeof(uint32_t)));
+    CU(cudaMemset(h->occ_coarse, 0, nc * sizeof(uint32_t)));
+    int* bbox_dev = nullptr;
+    CU(dev_alloc(&bbox_dev, 6));
+    int bbox[6] = {1 << 30, 1 << 30, 1 << 30, -1, -1, -1};
+    e = cudaMemcpy(bbox_dev, bbox, sizeof(bbox), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_pack_occ2(h->occ, W, H, D, h->occ2, nxb, nyb, nzb, h->occ_coarse, cx, cy, cz, bbox_dev, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(bbox, bbox_dev, sizeof(bbox), cudaMemcpyDeviceToHost);
+    cudaFree(bbox_dev);
+    CU(e);
+    f.occ = h->occ; f.occ2 = h->occ2; f.occ_coarse = h->occ_coarse;
+    f.occ_w = W; f.occ_h = H; f.occ_d = D;
+    f.occ2_nxb = nxb; f.occ2_nyb = nyb; f.occ_cx = cx; f.occ_cy = cy;
     f.has_occ = 1;
-    for (int k = 0; k < 3; ++k) { f.occ_lo[k] = d->alpha_aabb[k]; f.occ_inv[k] = d->alpha_inv[k]; }
+    const int dims[3] = {W, H, D};
+    for (int k = 0; k < 3; ++k) {
+      f.occ_lo[k] = d->alpha_aabb[k];
+      f.occ_inv[k] = d->alpha_inv[k];
+      // A kept sample has floor(fi) + 1 in [bbox_min, bbox_max], i.e. fi in [bbox_min - 1, bbox_max); half a cell of
+      // slack covers the rounding of the fi chain.  World x = lo + fi / (dim - 1) * size.
+      const double size = (double)d->alpha_aabb[3 + k] - (double)d->alpha_aabb[k];
+      const double cell = dims[k] > 1 ? size / (dims[k] - 1) : size;
+      if (bbox[3 + k] < 0) {                 // empty mask: nothing can be kept
+        f.clip_lo[k] = 1.f; f.clip_hi[k] = -1.f;
+      } else if (dims[k] > 1) {
+        f.clip_lo[k] = (float)(d->alpha_aabb[k] + (bbox[k] - 1.5) * cell);
+        f.clip_hi[k] = (float)(d->alpha_aabb[k] + (bbox[3 + k] + 0.5) * cell);
+      } else {
+        f.clip_lo[k] = -INFINITY; f.clip_hi[k] = INFINITY;
+      }
+    }
   } else {
-    if (h->occ) { cudaFree(h->occ); h->occ = nullptr; }
-    f.occ = nullptr; f.has_occ = 0; f.occ_w = f.occ_h = f.occ_d = 1;
-    for (int k = 0; k < 3; ++k) { f.occ_lo[k] = 0.f; f.occ_inv[k] = 0.f; }
+    f.occ = f.occ2 = f.occ_coarse = nullptr; f.has_occ = 0; f.occ_w = f.occ_h = f.occ_d = 1;
+    f.occ2_nxb = f.occ2_nyb = f.occ_cx = f.occ_cy = 1;
+    for (int k = 0; k < 3; ++k) { f.occ_lo[k] = 0.f; f.occ_inv[k] = 0.f; f.clip_lo[k] = -INFINITY; f.clip_hi[k] = INFINITY; }
   }
   // ---- density head
   std::vector<float> w, b;
@@ -265,6 +318,14 @@ static int pack_params(NgfField_* h, const NgfFieldDesc* d, bool allocate) {
     memcpy(f.dw, w.data(), 48 * sizeof(float));
     f.db = b[0];
     f.dmlp = nullptr;
+    float* w_dev = nullptr;
+    CU(dev_alloc(&w_dev, (size_t)48));
+    cudaError_t e = cudaMemcpy(w_dev, w.data(), 48 * sizeof(float), cudaMemcpyHostToDevice);
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i)
+      e = launch_pack_dsum(h->dens[i], (long long)f.plane[i].H * f.plane[i].W, 16, w_dev + 16 * i, h->dsum[i], 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(w_dev);
+    CU(e);
   } else {
     std::vector<float> m(kDmlpFloats, 0.f), w2, b2, w3, b3;
     CU(fetch(w, d->dens_l1.w, 32 * 72)); CU(fetch(b, d->dens_l1.b, 32));
@@ -352,8 +413,6 @@ int ngf_field_pack(const NgfFieldDesc* desc, int device, NgfField* out) {
   NgfField_* h = new NgfField_();
   h->device = device;
   CU(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
-  const char* sw = getenv("NGF_UMMA_SWAP");
-  h->lbo_swap = (sw && sw[0] == '1') ? 1 : 0;
   rc = pack_params(h, desc, true);
   if (rc) { free_all(h); delete h; return rc; }
   *out = h;
@@ -378,30 +437,79 @@ void ngf_field_free(NgfField h) {
   delete h;
 }
 
-static int render_dev(NgfField h, const float* rays, long long n_rays, int ray_stride, int n_samples, int white_bg,
-                      int tile_w, float* rgb, float* depth, float* acc, unsigned int* counters, bool reset_stats,
-                      int mlp_impl, cudaStream_t st) {
-  if (n_rays == 0) return NGF_OK;
-  RenderArgs a{};
-  a.rays = rays; a.n_rays = n_rays; a.ray_stride = ray_stride;
-  a.S = n_samples > 0 ? n_samples : h->n_samples_default;
-  if (a.S < 1) return fail(NGF_EINVAL, "n_samples resolves to %d", a.S);
-  a.white_bg = white_bg ? 1 : 0;
-  if (tile_w > 0 && n_rays % tile_w == 0) {
-    a.img_w = tile_w; a.img_h = (int)(n_rays / tile_w);
-    a.n_tiles = ((a.img_w + 7) / 8) * ((a.img_h + 3) / 4);
-  } else {
-    a.img_w = 0; a.img_h = 0;
-    a.n_tiles = (int)((n_rays + 31) / 32);
+// Colour-queue budget: the march kernel may emit up to n_rays * S work items of 32 bytes; a render is split into
+// ray batches so that the worst case fits the workspace (4 GiB by default: one 800x800x192 frame is one batch).
+static long long queue_budget_items() {
+  static long long v = 0;
+  if (v == 0) {
+    const char* e = getenv("NGF_QUEUE_MIB");
+    long long mib = e ? atoll(e) : 4096;
+    if (mib < 1) mib = 1;
+    v = mib * (1ll << 20) / (long long)sizeof(QEntry);
   }
-  a.rgb = rgb; a.depth = depth; a.acc = acc;
-  a.tile_counter = counters;
-  a.stats = reinterpret_cast<unsigned long long*>(counters + 2);
-  a.lbo_swap = h->lbo_swap;
-  CU(cudaMemsetAsync(counters, 0, reset_stats ? kCounterBytes : 8, st));
-  CU(cudaMemsetAsync(rgb, 0, (size_t)n_rays * 3 * sizeof(float), st));
-  CU(launch_render(h->dev, a, mlp_impl, h->num_sms, st));
-  CU(launch_finalize(rgb, acc, n_rays, a.white_bg, st));
+  return v;
+}
+
+static int ensure_queue(QEntry** q, long long* cap, long long want, cudaStream_t st) {
+  if (*cap >= want) return NGF_OK;
+  CU(cudaStreamSynchronize(st));
+  cudaFree(*q);
+  *q = nullptr; *cap = 0;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(q), (size_t)want * sizeof(QEntry));
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(NGF_ENOMEM, "colour queue of %lld MiB: %s", want * (long long)sizeof(QEntry) >> 20, cudaGetErrorString(e)); }
+  *cap = want;
+  return NGF_OK;
+}
+
+static int render_dev(NgfField h, const float* rays, long long n_rays, int ray_stride, int n_samples, int white_bg,
+                      int tile_w, float* rgb, float* depth, float* acc, unsigned int* counters, QEntry** queue,
+                      long long* queue_cap, int mlp_impl, cudaStream_t st) {
+  if (n_rays == 0) return NGF_OK;
+  const int S = n_samples > 0 ? n_samples : h->n_samples_default;
+  if (S < 1) return fail(NGF_EINVAL, "n_samples resolves to %d", S);
+  const bool img = tile_w > 0 && n_rays % tile_w == 0;
+  // rays per batch: worst-case queue use within budget; whole 4-row groups when image-tiled, whole warps otherwise
+  long long per = queue_budget_items() / S;
+  const long long unit = img ? 4ll * tile_w : 32;
+  per = per / unit * unit;
+  if (per < unit) per = unit;
+  if (per > n_rays) per = n_rays;
+  long long want = per * S;
+  if (want > 0xfffffff0ll) { per = 0xfffffff0ll / S / unit * unit; want = per * S; }
+  int rc = ensure_queue(queue, queue_cap, want, st);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(counters + 2, 0, kCounterBytes - 8, st));
+  for (long long s0 = 0; s0 < n_rays; s0 += per) {
+    const long long n = (n_rays - s0) < per ? (n_rays - s0) : per;
+    RenderArgs a{};
+    a.rays = rays + s0 * ray_stride; a.n_rays = n; a.ray_stride = ray_stride;
+    a.S = S;
+    a.white_bg = white_bg ? 1 : 0;
+    if (img) {
+      a.img_w = tile_w; a.img_h = (int)(n / tile_w);
+      a.n_tiles = ((a.img_w + 7) / 8) * ((a.img_h + 3) / 4);
+    } else {
+      a.img_w = 0; a.img_h = 0;
+      a.n_tiles = (int)((n + 31) / 32);
+    }
+    a.rgb = rgb + s0 * 3; a.depth = depth + s0; a.acc = acc + s0;
+    a.tile_counter = counters;
+    a.queue_count = counters + 1;
+    a.queue = *queue;
+    a.queue_cap = (unsigned int)(n * S < want ? n * S : want);
+    a.stats = reinterpret_cast<unsigned long long*>(counters + 2);
+    CU(cudaMemsetAsync(counters, 0, 8, st));
+    const bool timed = h->ev_used + 3 <= (int)h->ev.size();
+    if (timed) CU(cudaEventRecord(h->ev[h->ev_used], st));
+    CU(launch_march(h->dev, a, h->num_sms, st));
+    if (timed) CU(cudaEventRecord(h->ev[h->ev_used + 1], st));
+    CU(launch_colour(h->dev, a, mlp_impl, h->num_sms, st));
+    if (timed) {
+      CU(cudaEventRecord(h->ev[h->ev_used + 2], st));
+      h->ev_used += 3;
+    }
+  }
+  CU(launch_finalize(rgb, acc, n_rays, white_bg ? 1 : 0, st));
   return NGF_OK;
 }
 
@@ -429,7 +537,7 @@ int ngf_field_render(NgfField h, const float* rays_dev, int64_t n_rays, int32_t 
     acc = h->acc_ws;
   }
   return render_dev(h, rays_dev, n_rays, ray_stride, n_samples, white_bg, tile_w, rgb_dev, depth_dev, acc,
-                    h->counters, true, mlp_impl, st);
+                    h->counters, &h->queue, &h->queue_cap, mlp_impl, st);
 }
 
 int ngf_field_render_host(NgfField h, const float* rays_host, int64_t n_rays, int32_t ray_stride,
@@ -473,7 +581,7 @@ int ngf_field_render_host(NgfField h, const float* rays_host, int64_t n_rays, in
     CU(cudaMemcpyAsync(c.rays, rays_host + s * ray_stride, (size_t)n * ray_stride * sizeof(float),
                        cudaMemcpyHostToDevice, c.stream));
     int rc = render_dev(h, c.rays, n, ray_stride, n_samples, white_bg, img ? tile_w : 0, c.rgb, c.depth, c.acc,
-                        c.counters, true, mlp_impl, c.stream);
+                        c.counters, &c.queue, &c.queue_cap, mlp_impl, c.stream);
     if (rc) return rc;
     CU(cudaMemcpyAsync(rgb_host + s * 3, c.rgb, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
     CU(cudaMemcpyAsync(depth_host + s, c.depth, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
@@ -504,6 +612,35 @@ int ngf_field_stats(NgfField h, NgfStats* out, void* stream) {
   CU(cudaMemcpy(s, h->counters + 2, sizeof(s), cudaMemcpyDeviceToHost));
   out->rays = 0;
   out->samples_in_box = s[0]; out->samples_density = s[1]; out->samples_colour = s[2]; out->mlp_tiles = s[3];
+  return NGF_OK;
+}
+
+int ngf_field_timing_begin(NgfField h, int32_t capacity) {
+  if (!h) return fail(NGF_EINVAL, "field is NULL");
+  if (capacity < 0 || capacity > 65536) return fail(NGF_EINVAL, "capacity=%d", capacity);
+  DeviceGuard g(h->device);
+  free_events(h);
+  h->ev.resize((size_t)capacity * 3);
+  for (auto& e : h->ev) e = nullptr;
+  for (auto& e : h->ev) CU(cudaEventCreate(&e));
+  return NGF_OK;
+}
+
+int ngf_field_timing_read(NgfField h, int32_t* n_launches, double* march_ms, double* colour_ms) {
+  if (!h || !n_launches || !march_ms || !colour_ms) return fail(NGF_EINVAL, "NULL argument");
+  DeviceGuard g(h->device);
+  double sm = 0.0, sc = 0.0;
+  for (int i = 0; i + 2 < h->ev_used; i += 3) {
+    float a = 0.f, b = 0.f;
+    CU(cudaEventSynchronize(h->ev[i + 2]));
+    CU(cudaEventElapsedTime(&a, h->ev[i], h->ev[i + 1]));
+    CU(cudaEventElapsedTime(&b, h->ev[i + 1], h->ev[i + 2]));
+    sm += a; sc += b;
+  }
+  *n_launches = h->ev_used / 3;
+  *march_ms = sm;
+  *colour_ms = sc;
+  h->ev_used = 0;
   return NGF_OK;
 }
 
@@ -556,7 +693,7 @@ int ngf_field_rgb(NgfField h, const float* xy_dev, const float* yz_dev, const fl
   if (!xy_dev || !yz_dev || !xz_dev || !viewdirs_dev || !rgb_dev) return fail(NGF_EINVAL, "NULL pointer");
   if (n > 0x7fffffffll) return fail(NGF_EINVAL, "n too large");
   if (mlp_impl != NGF_MLP_TCGEN05 && mlp_impl != NGF_MLP_SIMT) return fail(NGF_EINVAL, "mlp_impl=%d", mlp_impl);
-  CU(launch_rgb(h->dev, xy_dev, yz_dev, xz_dev, viewdirs_dev, n, rgb_dev, mlp_impl, h->lbo_swap, h->num_sms, st));
+  CU(launch_rgb(h->dev, xy_dev, yz_dev, xz_dev, viewdirs_dev, n, rgb_dev, mlp_impl, h->num_sms, st));
   return NGF_OK;
 }
 

@@ -23,7 +23,8 @@ template <> struct Cfg<1> {       // InfoInv
 };
 
 struct PlaneDev {
-  const float* dens;              // [H][W][DC] fp32, channels-last
+  const float* dens;              // [H][W][DC] fp32, channels-last (InfoInv: feeds the density MLP)
+  const float* dsum;              // [H][W] fp32: <density channels, density_decoder.weight slice> per texel (TriPlane)
   const __half* app;              // [H][W][AC] fp16, channels-last
   int H, W;
   float wm1, hm1;                 // float(W-1), float(H-1)
@@ -43,11 +44,17 @@ struct FieldDev {
   int infoinv;
   float lo[3], hi[3], inv[3];
   float step, near_t, far_t, dscale, wthres, dshift;
-  // occupancy ("alpha mask") bit grid
-  const uint32_t* occ;            // bit (z*H + y)*W + x
+  // occupancy ("alpha mask"): raw bit grid + derived acceleration grids (built by ngf_field_pack)
+  const uint32_t* occ;            // raw volume bits, bit (z*H + y)*W + x
+  const uint32_t* occ2;           // "any of the 8 cell corners set" grid over cells x0 in [-1, W-1] (index x0+1),
+                                  // 4x4x2-cell bricks per 32-bit word
+  const uint32_t* occ_coarse;     // any occ2 bit set in an 8x8x8 block of occ2 cells, linear bits
   int occ_w, occ_h, occ_d;
+  int occ2_nxb, occ2_nyb;         // bricks per row / per slab of occ2
+  int occ_cx, occ_cy;             // coarse grid row / slab sizes
   int has_occ;
   float occ_lo[3], occ_inv[3];
+  float clip_lo[3], clip_hi[3];   // world box containing every sample the mask can keep (conservative)
   // TriPlane density head Linear(48,1)
   float dw[48];
   float db;
@@ -87,12 +94,16 @@ __device__ __forceinline__ void ray_index_range(const FieldDev& f, const float o
   bool empty = false;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
+    // with an alpha mask only samples inside clip_lo..clip_hi (a superset of the occupied cells) can be kept
+    const float lo = f.has_occ ? fmaxf(f.lo[k], f.clip_lo[k]) : f.lo[k];
+    const float hi = f.has_occ ? fminf(f.hi[k], f.clip_hi[k]) : f.hi[k];
+    if (lo > hi) empty = true;
     if (d[k] == 0.f) {                       // p_k == o_k exactly for every sample
-      if (f.lo[k] > o[k] || o[k] > f.hi[k]) empty = true;
+      if (lo > o[k] || o[k] > hi) empty = true;
       continue;
     }
     float inv_d = 1.f / d[k];
-    float a = (f.hi[k] - o[k]) * inv_d, b = (f.lo[k] - o[k]) * inv_d;
+    float a = (hi - o[k]) * inv_d, b = (lo - o[k]) * inv_d;
     float m = 4e-6f * (fabsf(o[k]) + fabsf(d[k]) * f.far_t + fmaxf(fabsf(f.lo[k]), fabsf(f.hi[k]))) * fabsf(inv_d);
     t_in = fmaxf(t_in, fminf(a, b) - m);     // NaN operands are ignored by fminf/fmaxf: axis left unconstrained
     t_out = fminf(t_out, fmaxf(a, b) + m);
@@ -136,6 +147,9 @@ __device__ __forceinline__ bool occ_bit(const FieldDev& f, int x, int y, int z) 
   return (__ldg(f.occ + (idx >> 5)) >> (idx & 31)) & 1u;
 }
 
+// Fast path: when no coordinate is an exact lattice value all 8 corners carry non-zero weight, so the answer is
+// the precomputed "any corner set" bit of the cell (one load, after an L1-resident coarse test).  Exact lattice
+// coordinates (measure zero, but the reference's own dense alpha grid produces them) take the 8-corner path.
 __device__ __forceinline__ bool occ_keep(const FieldDev& f, const float p[3]) {
   float fi[3];
   int i0[3];
@@ -149,6 +163,16 @@ __device__ __forceinline__ bool occ_keep(const FieldDev& f, const float p[3]) {
     frac[k] = fi[k] != fl;
     fl = fminf(fmaxf(fl, -2.f), (float)dims[k] + 1.f);
     i0[k] = (int)fl;
+  }
+  if (frac[0] && frac[1] && frac[2]) {
+    const int X = i0[0] + 1, Y = i0[1] + 1, Z = i0[2] + 1;
+    if ((unsigned)X > (unsigned)f.occ_w || (unsigned)Y > (unsigned)f.occ_h || (unsigned)Z > (unsigned)f.occ_d)
+      return false;
+    const uint32_t cb = ((uint32_t)(Z >> 3) * (uint32_t)f.occ_cy + (uint32_t)(Y >> 3)) * (uint32_t)f.occ_cx + (uint32_t)(X >> 3);
+    if (!((__ldg(f.occ_coarse + (cb >> 5)) >> (cb & 31)) & 1u)) return false;
+    const uint32_t word = ((uint32_t)(Z >> 1) * (uint32_t)f.occ2_nyb + (uint32_t)(Y >> 2)) * (uint32_t)f.occ2_nxb + (uint32_t)(X >> 2);
+    const uint32_t bit = (uint32_t)(X & 3) | ((uint32_t)(Y & 3) << 2) | ((uint32_t)(Z & 1) << 4);
+    return (__ldg(f.occ2 + word) >> bit) & 1u;
   }
   bool keep = false;
 #pragma unroll
@@ -234,26 +258,16 @@ __device__ __forceinline__ float softplus_torch(float x) { return x > 20.f ? x :
 
 // ---------------------------------------------------------------------------------------------------------
 // compute_density, TriPlane (Field.py:77-91): 3 x bilinear over channels [0,16), Linear(48,1), softplus(.-10).
-// The blend and the dot product are fused: sum_taps w_tap * <texel, dw_plane>.
-// ---------------------------------------------------------------------------------------------------------
+// Both steps are linear, so the Linear is applied per texel when the field is packed (PlaneDev::dsum) and the
+// lookup blends one scalar per tap: sum_planes sum_taps w_tap * <texel, weight slice>.
 __device__ __forceinline__ float sigma_triplane(const FieldDev& f, const float c[6]) {
   float acc = f.db;
 #pragma unroll
   for (int pl = 0; pl < 3; ++pl) {
     const PlaneDev& P = f.plane[pl];
     Taps t = make_taps(c[2 * pl], c[2 * pl + 1], P.W, P.H, P.wm1, P.hm1);
-    const float* w = f.dw + 16 * pl;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float4* tex = reinterpret_cast<const float4*>(P.dens) + (size_t)t.off[k] * 4;
-      float s = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float4 a = __ldg(tex + q);
-        s += a.x * w[4 * q] + a.y * w[4 * q + 1] + a.z * w[4 * q + 2] + a.w * w[4 * q + 3];
-      }
-      acc += t.w[k] * s;
-    }
+    for (int k = 0; k < 4; ++k) acc += t.w[k] * __ldg(P.dsum + t.off[k]);
   }
   return softplus_torch(acc + f.dshift);
 }

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "ngf_common.cuh"
+#include "ngf_queue.h"
 
 namespace ngf {
 
@@ -14,17 +15,20 @@ struct RenderArgs {
   int S;
   int white_bg;
   int img_w, img_h;            // > 0: rays are row-major pixels of an img_w x img_h image -> 8x4 pixel warp tiles
-  float* rgb;                  // [R][3], zero-initialised accumulator, finalised in place
+  float* rgb;                  // [R][3]: zeroed by the march kernel, accumulated by the colour kernel, finalised in place
   float* depth;                // [R]
   float* acc;                  // [R]
   unsigned int* tile_counter;  // zero-initialised
+  unsigned int* queue_count;   // zero-initialised: colour work items appended so far
+  QEntry* queue;               // [queue_cap] colour work items (march kernel -> colour kernel)
+  unsigned int queue_cap;
   unsigned long long* stats;   // [4]: samples_in_box, samples_density, samples_colour, mlp_tiles (accumulated)
   int n_tiles;
-  int lbo_swap;                // debugging: swap the LBO/SBO fields of the tcgen05 smem descriptors
 };
 
 // All launchers return cudaGetLastError() after enqueueing on `st`.
-cudaError_t launch_render(const FieldDev& f, const RenderArgs& a, int mlp_impl, int num_sms, cudaStream_t st);
+cudaError_t launch_march(const FieldDev& f, const RenderArgs& a, int num_sms, cudaStream_t st);
+cudaError_t launch_colour(const FieldDev& f, const RenderArgs& a, int mlp_impl, int num_sms, cudaStream_t st);
 cudaError_t launch_finalize(float* rgb, const float* acc, long long n_rays, int white_bg, cudaStream_t st);
 cudaError_t launch_sample_ray(const FieldDev& f, const float* rays, long long n_rays, int stride, int S, float* pts,
                               float* t, uint8_t* inside, cudaStream_t st);
@@ -36,13 +40,18 @@ cudaError_t launch_density(const FieldDev& f, const float* xy, const float* yz, 
 cudaError_t launch_sigma_world(const FieldDev& f, const float* pts, long long n, int use_gauge, float* sigma,
                                cudaStream_t st);
 cudaError_t launch_rgb(const FieldDev& f, const float* xy, const float* yz, const float* xz, const float* dirs,
-                       long long n, float* rgb, int mlp_impl, int lbo_swap, int num_sms, cudaStream_t st);
+                       long long n, float* rgb, int mlp_impl, int num_sms, cudaStream_t st);
 
 // packing kernels
 cudaError_t launch_pack_plane(const float* nchw, int C, int H, int W, int DC, float* dens, __half* app,
                               cudaStream_t st);
 cudaError_t launch_pack_gauge(const float* nchw, int H, int W, float2* out, cudaStream_t st);
 cudaError_t launch_pack_occ(const float* vol, long long n_vox, uint32_t* bits, cudaStream_t st);
+// raw bits -> "any corner set" brick grid + coarse grid + occupied index box (bbox[6] = min xyz, max xyz of occ2 cells)
+cudaError_t launch_pack_occ2(const uint32_t* bits, int W, int H, int D, uint32_t* occ2, int nxb, int nyb, int nzb,
+                             uint32_t* coarse, int cx, int cy, int cz, int* bbox, cudaStream_t st);
+// TriPlane: dsum[t] = <dens[t][0..DC), w[0..DC)>
+cudaError_t launch_pack_dsum(const float* dens, long long hw, int DC, const float* w_dev, float* dsum, cudaStream_t st);
 
 // ray sharding
 cudaError_t launch_shard_gather(const float* src, long long n_rays, int width, int block, int rank, int world,
@@ -50,7 +59,6 @@ cudaError_t launch_shard_gather(const float* src, long long n_rays, int width, i
 cudaError_t launch_shard_scatter(const float* src, long long n_rays, int width, int block, int world,
                                  long long max_shard, float* dst, cudaStream_t st);
 
-size_t render_smem_bytes(int variant);
 uint64_t launch_count();
 
 }  // namespace ngf

@@ -1,15 +1,18 @@
 // ngf_kernels.cu — sm_100a kernels of the render path and their launchers.
 //
-// ngf_render_kernel is the fused per-frame kernel that replaces Base.forward (TriPlane/models/FieldBase.py:251-312,
-// InfoInv/models/FieldBase.py:228-282) and the chunk loop around it (TriPlane/main.py:60-71):
+// The per-frame path that replaces Base.forward (TriPlane/models/FieldBase.py:251-312, InfoInv/models/
+// FieldBase.py:228-282) and the chunk loop around it (TriPlane/main.py:60-71) is a family of three kernels:
 //
-//   persistent CTAs (256 threads, 8 warps).  Each WARP pulls tiles of 32 rays (8x4 pixel blocks when the image
-//   shape is known) from a global counter and marches them: sample position + bbox test (sample_ray), occupancy
-//   bit test (AlphaGridMask), gauge lookup (compute_gauge), density (compute_density), alpha/transmittance/weight
-//   (raw2alpha) — all in registers, nothing materialised.  Samples whose weight exceeds rayMarch_weight_thres are
-//   pushed (warp-aggregated) into a shared-memory ring.  Whenever the ring holds 128 samples the whole CTA runs one
-//   colour-MLP tile on the tensor cores (ngf_mlp.cuh) and accumulates weight*rgb into the frame with fp32 atomics.
-//   ngf_finalize_kernel adds the white background and clamps (FieldBase.py:299-302).
+//   ngf_march_kernel     one ray per lane, warps own 8x4-pixel tiles (dynamic tile counter).  Sample position + bbox
+//                        test (sample_ray), occupancy test on the packed bit grids (AlphaGridMask), gauge lookup
+//                        (compute_gauge), density (compute_density), alpha / transmittance / weight (raw2alpha) and
+//                        the acc / depth sums — all in registers, nothing materialised.  Samples whose weight
+//                        exceeds rayMarch_weight_thres are compacted (warp ballot -> per-warp shared-memory stage ->
+//                        32-entry coalesced bursts) into a device queue of 32-byte colour work items.
+//   ngf_colour_kernel    persistent CTAs take 128-item tiles of that queue: bilinear gather of the appearance
+//                        texels straight into the tcgen05 A operand, the colour MLP on the tensor cores with
+//                        accumulators in TMEM (ngf_mlp.cuh), sigmoid, weight * rgb accumulated per ray.
+//   ngf_finalize_kernel  white background + clamp (FieldBase.py:299-302).
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -24,167 +27,148 @@ uint64_t launch_count() { return g_launches.load(); }
 #define NGF_COUNT_LAUNCH() g_launches.fetch_add(1)
 
 constexpr float kTStop = 1e-6f;   // stop marching once transmittance <= kTStop: all later weights sum to <= 1e-6
+constexpr int kMarchThreads = 256;
+constexpr int kMarchWarps = kMarchThreads / 32;
+constexpr int kStage = 64;        // staged colour items per warp (flushed 32 at a time)
 
 template <int V>
-struct RenderSmem {
-  using L = MlpSmem<V>;
-  static constexpr uint32_t offDmlp = L::offEnd;
+struct MarchSmem {
+  static constexpr uint32_t offStage = 0;
+  static constexpr uint32_t offDmlp = offStage + kMarchWarps * kStage * sizeof(QEntry);
   static constexpr uint32_t kBytes = offDmlp + (V == 1 ? ((kDmlpFloats * 4 + 15) / 16) * 16 : 0);
 };
 
-size_t render_smem_bytes(int variant) { return variant == 0 ? RenderSmem<0>::kBytes : RenderSmem<1>::kBytes; }
-
-template <int V, int IMPL>
-__global__ void __launch_bounds__(kThreads, V == 0 ? 2 : 1) ngf_render_kernel(const __grid_constant__ FieldDev f,
-                                                                 const __grid_constant__ RenderArgs a) {
+template <int V>
+__global__ void __launch_bounds__(kMarchThreads, V == 0 ? 3 : 1) ngf_march_kernel(const __grid_constant__ FieldDev f,
+                                                                const __grid_constant__ RenderArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  using L = MlpSmem<V>;
-  constexpr int NW = kThreads / 32;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr unsigned FULL = 0xffffffffu;
-
-  mlp_setup<V, IMPL>(f, smem);
+  float4* stage = reinterpret_cast<float4*>(smem + MarchSmem<V>::offStage) + warp * kStage * 2;   // 2 float4 per item
   const float* dmlp_s = nullptr;
   if (V == 1) {
-    float* dm = reinterpret_cast<float*>(smem + RenderSmem<V>::offDmlp);
-    for (int i = tid; i < kDmlpFloats; i += kThreads) dm[i] = __ldg(f.dmlp + i);
+    float* dm = reinterpret_cast<float*>(smem + MarchSmem<V>::offDmlp);
+    for (int i = tid; i < kDmlpFloats; i += kMarchThreads) dm[i] = __ldg(f.dmlp + i);
     dmlp_s = dm;
+    __syncthreads();
   }
-  __syncthreads();
-
-  MlpCtl* ctl = reinterpret_cast<MlpCtl*>(smem + L::offCtl);
-  volatile uint32_t* q_head = &ctl->q_head;
-  volatile uint32_t* q_tail = &ctl->q_tail;
-  volatile uint32_t* n_exh = &ctl->n_exhausted;
-  QEntry* queue = reinterpret_cast<QEntry*>(smem + L::offQueue);
-  uint32_t phase = 0;
 
   // per-lane ray state
   float o[3] = {0, 0, 0}, d[3] = {0, 0, 1}, t0 = 0.f, T = 1.f, acc = 0.f, dep = 0.f, last_col = 0.f;
   int i = 0, i_end = 0;
   long long ray = -1;
   bool live = false;
-  bool exhausted = false;
-  uint32_t st_box = 0, st_den = 0, st_col = 0, st_tiles = 0;
+  int n_staged = 0;                                      // warp-uniform
+  uint32_t st_box = 0, st_den = 0, st_col = 0;
   const int S = a.S;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  auto flush = [&](int n) {                              // write the first n (<= 32) staged items to the queue
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(a.queue_count, (uint32_t)n);
+    base = __shfl_sync(FULL, base, 0);
+    float4* dst = reinterpret_cast<float4*>(a.queue + base);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int idx = lane + 32 * h;
+      if (idx < 2 * n && base + (uint32_t)(idx >> 1) < a.queue_cap) dst[idx] = stage[idx];
+    }
+  };
 
   for (;;) {
-    // ------------------------------------------------------------------ work phase (warp-autonomous)
-    while (!exhausted) {
-      if ((*q_tail - *q_head) >= (uint32_t)kTileM) break;
-      if (!__any_sync(FULL, live)) {
-        int tile = 0;
-        if (lane == 0) tile = (int)atomicAdd(a.tile_counter, 1u);
-        tile = __shfl_sync(FULL, tile, 0);
-        if (tile >= a.n_tiles) {
-          exhausted = true;
-          if (lane == 0) atomicAdd(&ctl->n_exhausted, 1u);
-          break;
-        }
-        if (a.img_w > 0) {
-          const int tiles_x = (a.img_w + 7) >> 3;
-          const int px = (tile % tiles_x) * 8 + (lane & 7), py = (tile / tiles_x) * 4 + (lane >> 3);
-          ray = (px < a.img_w && py < a.img_h) ? (long long)py * a.img_w + px : -1;
-        } else {
-          ray = (long long)tile * 32 + lane;
-          if (ray >= a.n_rays) ray = -1;
-        }
-        if (ray >= 0) {
-          const float* rp = a.rays + ray * a.ray_stride;
+    if (!__any_sync(FULL, live)) {
+      int tile = 0;
+      if (lane == 0) tile = (int)atomicAdd(a.tile_counter, 1u);
+      tile = __shfl_sync(FULL, tile, 0);
+      if (tile >= a.n_tiles) break;
+      if (a.img_w > 0) {
+        const int tiles_x = (a.img_w + 7) >> 3;
+        const int px = (tile % tiles_x) * 8 + (lane & 7), py = (tile / tiles_x) * 4 + (lane >> 3);
+        ray = (px < a.img_w && py < a.img_h) ? (long long)py * a.img_w + px : -1;
+      } else {
+        ray = (long long)tile * 32 + lane;
+        if (ray >= a.n_rays) ray = -1;
+      }
+      if (ray >= 0) {
+        const float* rp = a.rays + ray * a.ray_stride;
 #pragma unroll
-          for (int k = 0; k < 3; ++k) { o[k] = __ldg(rp + k); d[k] = __ldg(rp + 3 + k); }
-          last_col = __ldg(rp + a.ray_stride - 1);
-          t0 = ray_t0(f, o, d);
-          int lo_i, hi_i;
-          ray_index_range(f, o, d, t0, S, lo_i, hi_i);
-          i = lo_i; i_end = hi_i + 1;
-          T = 1.f; acc = 0.f; dep = 0.f;
-          live = i < i_end;
-          if (!live) {                                   // ray misses the box: background only
-            a.acc[ray] = 0.f;
-            a.depth[ray] = last_col;
-            ray = -1;
-          }
-        }
-        continue;
-      }
-      // ---- skip empty space until this lane finds a sample that needs the field (or runs out)
-      bool found = false;
-      float t = 0.f, p[3] = {0, 0, 0};
-      while (live && !found) {
-        t = sample_t(f, t0, i);
-        bool in = sample_pos(f, o, d, t, p);
-        if (in) ++st_box;
-        if (in && f.has_occ) in = occ_keep(f, p);
-        if (in) found = true;
-        else if (++i >= i_end) live = false;
-      }
-      // ---- density + alpha compositing weights for the found samples (lanes converge here)
-      bool push = false;
-      QEntry e;
-      if (found) {
-        float n[3];
-        unit_coords(f, p, n);
-        gauge_coords(f, n, V == 0 && f.gauge_on, e.c);
-        const float sigma = (V == 0) ? sigma_triplane(f, e.c) : sigma_infoinv(f, e.c, dmlp_s);
-        ++st_den;
-        // raw2alpha (FieldBase.py:12-19) with dists from the rounded t values (FieldBase.py:258, 288)
-        const float tn = sample_t(f, t0, i + 1);
-        const float delta = (i == S - 1) ? 0.f : __fmul_rn(__fsub_rn(tn, t), f.dscale);
-        const float alpha = __fsub_rn(1.f, expf(-__fmul_rn(sigma, delta)));
-        const float w = __fmul_rn(alpha, T);
-        T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f));
-        acc += w;
-        dep += w * t;
-        push = w > f.wthres;
-        e.w = w;
-        e.id = (int)ray;
-        if (++i >= i_end || T <= kTStop) live = false;
-      }
-      const unsigned pm = __ballot_sync(FULL, push);
-      if (pm) {
-        uint32_t base = 0;
-        const int leader = __ffs(pm) - 1;
-        if (lane == leader) base = atomicAdd(&ctl->q_tail, (uint32_t)__popc(pm));
-        base = __shfl_sync(FULL, base, leader);
-        if (push) {
-          ++st_col;
-          const uint32_t slot = (base + __popc(pm & ((1u << lane) - 1u))) & (kQueueCap - 1);
-          float4* dst = reinterpret_cast<float4*>(&queue[slot]);
-          dst[0] = make_float4(e.c[0], e.c[1], e.c[2], e.c[3]);
-          dst[1] = make_float4(e.c[4], e.c[5], e.w, __int_as_float(e.id));
+        for (int k = 0; k < 3; ++k) { o[k] = __ldg(rp + k); d[k] = __ldg(rp + 3 + k); }
+        last_col = __ldg(rp + a.ray_stride - 1);
+        t0 = ray_t0(f, o, d);
+        int lo_i, hi_i;
+        ray_index_range(f, o, d, t0, S, lo_i, hi_i);
+        i = lo_i; i_end = hi_i + 1;
+        T = 1.f; acc = 0.f; dep = 0.f;
+        live = i < i_end;
+        float* rgb = a.rgb + ray * 3;                    // the colour kernel accumulates into it
+        rgb[0] = 0.f; rgb[1] = 0.f; rgb[2] = 0.f;
+        if (!live) {                                     // no sample can be kept: background only
+          a.acc[ray] = 0.f;
+          a.depth[ray] = last_col;
+          ray = -1;
         }
       }
-      if (!live && ray >= 0) {                           // ray finished: acc_map / depth_map (FieldBase.py:296,305-306)
-        a.acc[ray] = acc;
-        a.depth[ray] = dep + (1.f - acc) * last_col;
-        ray = -1;
-      }
-    }
-    // ------------------------------------------------------------------ CTA sync point
-    __syncthreads();
-    const uint32_t head = *q_head;
-    const uint32_t cnt = *q_tail - head;
-    const bool all_exh = (*n_exh == (uint32_t)NW);
-    if (cnt >= (uint32_t)kTileM || (all_exh && cnt > 0)) {
-      const uint32_t take = cnt < (uint32_t)kTileM ? cnt : (uint32_t)kTileM;
-      if (take < (uint32_t)kTileM) {
-        if (tid >= (int)take && tid < kTileM) {
-          float4* dst = reinterpret_cast<float4*>(&queue[(head + tid) & (kQueueCap - 1)]);
-          dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-          dst[1] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        }
-        __syncthreads();
-      }
-      mlp_tile<V, IMPL, true>(f, smem, head, phase, a.rays + 3, a.ray_stride, a.rgb, a.lbo_swap);
-      if (tid == 0) { *q_head = head + take; ++st_tiles; }
-      __syncthreads();
       continue;
     }
-    if (all_exh) break;
+    // ---- skip empty space until this lane finds a sample that needs the field (or runs out)
+    bool found = false;
+    float t = 0.f, p[3] = {0, 0, 0};
+    while (live && !found) {
+      t = sample_t(f, t0, i);
+      bool in = sample_pos(f, o, d, t, p);
+      if (in) ++st_box;
+      if (in && f.has_occ) in = occ_keep(f, p);
+      if (in) found = true;
+      else if (++i >= i_end) live = false;
+    }
+    // ---- density + alpha compositing weights for the found samples (lanes converge here)
+    bool push = false;
+    float c[6], w = 0.f;
+    if (found) {
+      float n[3];
+      unit_coords(f, p, n);
+      gauge_coords(f, n, V == 0 && f.gauge_on, c);
+      const float sigma = (V == 0) ? sigma_triplane(f, c) : sigma_infoinv(f, c, dmlp_s);
+      ++st_den;
+      // raw2alpha (FieldBase.py:12-19) with dists from the rounded t values (FieldBase.py:258, 288)
+      const float tn = sample_t(f, t0, i + 1);
+      const float delta = (i == S - 1) ? 0.f : __fmul_rn(__fsub_rn(tn, t), f.dscale);
+      const float alpha = __fsub_rn(1.f, expf(-__fmul_rn(sigma, delta)));
+      w = __fmul_rn(alpha, T);
+      T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f));
+      acc += w;
+      dep += w * t;
+      push = w > f.wthres;
+      if (++i >= i_end || T <= kTStop) live = false;
+    }
+    const unsigned pm = __ballot_sync(FULL, push);
+    if (pm) {
+      if (push) {
+        ++st_col;
+        const int slot = n_staged + __popc(pm & lt_mask);
+        stage[2 * slot] = make_float4(c[0], c[1], c[2], c[3]);
+        stage[2 * slot + 1] = make_float4(c[4], c[5], w, __int_as_float((int)ray));
+      }
+      n_staged += __popc(pm);
+      __syncwarp();
+      if (n_staged >= 32) {
+        flush(32);
+        const int rem = n_staged - 32;                   // <= 31 items move to the front of the stage
+        float4 m0 = make_float4(0, 0, 0, 0), m1 = m0;
+        if (lane < rem) { m0 = stage[64 + 2 * lane]; m1 = stage[64 + 2 * lane + 1]; }
+        __syncwarp();
+        if (lane < rem) { stage[2 * lane] = m0; stage[2 * lane + 1] = m1; }
+        __syncwarp();
+        n_staged = rem;
+      }
+    }
+    if (!live && ray >= 0) {                             // ray finished: acc_map / depth_map (FieldBase.py:296,305-306)
+      a.acc[ray] = acc;
+      a.depth[ray] = dep + (1.f - acc) * last_col;
+      ray = -1;
+    }
   }
-
-  mlp_teardown<IMPL>(smem, L::offCtl);
+  if (n_staged > 0) flush(n_staged);
 
   // statistics
 #pragma unroll
@@ -198,7 +182,37 @@ __global__ void __launch_bounds__(kThreads, V == 0 ? 2 : 1) ngf_render_kernel(co
     atomicAdd(a.stats + 1, (unsigned long long)st_den);
     atomicAdd(a.stats + 2, (unsigned long long)st_col);
   }
-  if (tid == 0) atomicAdd(a.stats + 3, (unsigned long long)st_tiles);
+}
+
+// Colour MLP over the compacted queue: persistent CTAs, one 128-item tile per iteration.
+template <int V, int IMPL>
+__global__ void __launch_bounds__(kThreads, 2) ngf_colour_kernel(const __grid_constant__ FieldDev f,
+                                                                 const __grid_constant__ RenderArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using L = MlpSmem<V>;
+  uint32_t count = *reinterpret_cast<volatile const uint32_t*>(a.queue_count);
+  if (count > a.queue_cap) count = a.queue_cap;
+  const uint32_t n_tiles = (count + kTileM - 1) / kTileM;
+  if (blockIdx.x >= n_tiles) return;
+  mlp_setup<V, IMPL>(f, smem);
+  __syncthreads();
+  float4* q = reinterpret_cast<float4*>(smem + L::offQueue);
+  const float4* src = reinterpret_cast<const float4*>(a.queue);
+  uint32_t phase = 0;
+  uint32_t done = 0;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++done) {
+    const uint32_t first = tile * kTileM;
+    {
+      const uint32_t item = first + (threadIdx.x >> 1);
+      float4 v = (threadIdx.x & 1) ? make_float4(0.f, 0.f, 0.f, __int_as_float(-1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (item < count) v = __ldg(src + (size_t)first * 2 + threadIdx.x);
+      q[threadIdx.x] = v;
+    }
+    __syncthreads();
+    mlp_tile<V, IMPL, true>(f, smem, 0u, phase, a.rays + 3, a.ray_stride, a.rgb);
+  }
+  mlp_teardown<IMPL>(smem, L::offCtl);
+  if (threadIdx.x == 0) atomicAdd(a.stats + 3, (unsigned long long)done);
 }
 
 // rgb_map = clamp(sum w*rgb + [white_bg](1 - acc), 0, 1)   (FieldBase.py:297-302)
@@ -211,32 +225,63 @@ __global__ void ngf_finalize_kernel(float* __restrict__ rgb, const float* __rest
   rgb[i] = fminf(fmaxf(v, 0.f), 1.f);
 }
 
-template <int V, int IMPL>
-static cudaError_t launch_render_t(const FieldDev& f, const RenderArgs& a, int num_sms, cudaStream_t st) {
-  auto kern = ngf_render_kernel<V, IMPL>;
-  const size_t smem = RenderSmem<V>::kBytes;
-  static bool configured = false;
-  static int occ = 1;
-  if (!configured) {
+static int blocks_per_sm(const void* kern, int threads, size_t smem) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    occ = 1;
+  }
+  return occ;
+}
+
+template <int V>
+static cudaError_t launch_march_t(const FieldDev& f, const RenderArgs& a, int num_sms, cudaStream_t st) {
+  auto kern = ngf_march_kernel<V>;
+  const size_t smem = MarchSmem<V>::kBytes;
+  static int occ = 0;
+  if (occ == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) occ = 1;
-    configured = true;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    occ = blocks_per_sm(reinterpret_cast<const void*>(kern), kMarchThreads, smem);
   }
-  long long want = ((long long)a.n_tiles + (kThreads / 32) - 1) / (kThreads / 32);
+  long long want = ((long long)a.n_tiles + kMarchWarps - 1) / kMarchWarps;
   long long grid = (long long)num_sms * occ;
   if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, kMarchThreads, smem, st>>>(f, a);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+template <int V, int IMPL>
+static cudaError_t launch_colour_t(const FieldDev& f, const RenderArgs& a, int num_sms, cudaStream_t st) {
+  auto kern = ngf_colour_kernel<V, IMPL>;
+  const size_t smem = MlpSmem<V>::offEnd;
+  static int occ = 0;
+  if (occ == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    occ = blocks_per_sm(reinterpret_cast<const void*>(kern), kThreads, smem);
+    if (occ > 2) occ = 2;
+  }
+  long long grid = (long long)num_sms * occ;
+  long long worst = ((long long)a.queue_cap + kTileM - 1) / kTileM;
+  if (grid > worst) grid = worst;
   if (grid < 1) grid = 1;
   kern<<<(unsigned)grid, kThreads, smem, st>>>(f, a);
   NGF_COUNT_LAUNCH();
   return cudaGetLastError();
 }
 
-cudaError_t launch_render(const FieldDev& f, const RenderArgs& a, int mlp_impl, int num_sms, cudaStream_t st) {
-  if (f.variant == 0) return mlp_impl == 0 ? launch_render_t<0, 0>(f, a, num_sms, st) : launch_render_t<0, 1>(f, a, num_sms, st);
-  return mlp_impl == 0 ? launch_render_t<1, 0>(f, a, num_sms, st) : launch_render_t<1, 1>(f, a, num_sms, st);
+cudaError_t launch_march(const FieldDev& f, const RenderArgs& a, int num_sms, cudaStream_t st) {
+  return f.variant == 0 ? launch_march_t<0>(f, a, num_sms, st) : launch_march_t<1>(f, a, num_sms, st);
+}
+
+cudaError_t launch_colour(const FieldDev& f, const RenderArgs& a, int mlp_impl, int num_sms, cudaStream_t st) {
+  if (f.variant == 0) return mlp_impl == 0 ? launch_colour_t<0, 0>(f, a, num_sms, st) : launch_colour_t<0, 1>(f, a, num_sms, st);
+  return mlp_impl == 0 ? launch_colour_t<1, 0>(f, a, num_sms, st) : launch_colour_t<1, 1>(f, a, num_sms, st);
 }
 
 cudaError_t launch_finalize(float* rgb, const float* acc, long long n_rays, int white_bg, cudaStream_t st) {
@@ -324,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 2) ngf_rgb_kernel(const __grid_const
                                                               const float* __restrict__ yz,
                                                               const float* __restrict__ xz,
                                                               const float* __restrict__ dirs, long long n,
-                                                              float* __restrict__ rgb, int lbo_swap) {
+                                                              float* __restrict__ rgb) {
   extern __shared__ __align__(128) uint8_t smem[];
   using L = MlpSmem<V>;
   mlp_setup<V, IMPL>(f, smem);
@@ -345,15 +390,14 @@ __global__ void __launch_bounds__(kThreads, 2) ngf_rgb_kernel(const __grid_const
       }
     }
     __syncthreads();
-    mlp_tile<V, IMPL, false>(f, smem, 0u, phase, dirs, 3, rgb, lbo_swap);
+    mlp_tile<V, IMPL, false>(f, smem, 0u, phase, dirs, 3, rgb);
   }
   mlp_teardown<IMPL>(smem, L::offCtl);
 }
 
 template <int V, int IMPL>
 static cudaError_t launch_rgb_t(const FieldDev& f, const float* xy, const float* yz, const float* xz,
-                                const float* dirs, long long n, float* rgb, int lbo_swap, int num_sms,
-                                cudaStream_t st) {
+                                const float* dirs, long long n, float* rgb, int num_sms, cudaStream_t st) {
   auto kern = ngf_rgb_kernel<V, IMPL>;
   const size_t smem = MlpSmem<V>::offEnd;
   static bool configured = false;
@@ -365,19 +409,19 @@ static cudaError_t launch_rgb_t(const FieldDev& f, const float* xy, const float*
   long long n_tiles = (n + kTileM - 1) / kTileM;
   long long grid = (long long)num_sms * 2;
   if (grid > n_tiles) grid = n_tiles;
-  kern<<<(unsigned)grid, kThreads, smem, st>>>(f, xy, yz, xz, dirs, n, rgb, lbo_swap);
+  kern<<<(unsigned)grid, kThreads, smem, st>>>(f, xy, yz, xz, dirs, n, rgb);
   NGF_COUNT_LAUNCH();
   return cudaGetLastError();
 }
 
 cudaError_t launch_rgb(const FieldDev& f, const float* xy, const float* yz, const float* xz, const float* dirs,
-                       long long n, float* rgb, int mlp_impl, int lbo_swap, int num_sms, cudaStream_t st) {
+                       long long n, float* rgb, int mlp_impl, int num_sms, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   if (f.variant == 0)
-    return mlp_impl == 0 ? launch_rgb_t<0, 0>(f, xy, yz, xz, dirs, n, rgb, lbo_swap, num_sms, st)
-                         : launch_rgb_t<0, 1>(f, xy, yz, xz, dirs, n, rgb, lbo_swap, num_sms, st);
-  return mlp_impl == 0 ? launch_rgb_t<1, 0>(f, xy, yz, xz, dirs, n, rgb, lbo_swap, num_sms, st)
-                       : launch_rgb_t<1, 1>(f, xy, yz, xz, dirs, n, rgb, lbo_swap, num_sms, st);
+    return mlp_impl == 0 ? launch_rgb_t<0, 0>(f, xy, yz, xz, dirs, n, rgb, num_sms, st)
+                         : launch_rgb_t<0, 1>(f, xy, yz, xz, dirs, n, rgb, num_sms, st);
+  return mlp_impl == 0 ? launch_rgb_t<1, 0>(f, xy, yz, xz, dirs, n, rgb, num_sms, st)
+                       : launch_rgb_t<1, 1>(f, xy, yz, xz, dirs, n, rgb, num_sms, st);
 }
 
 static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
@@ -453,6 +497,44 @@ __global__ void ngf_pack_occ_kernel(const float* __restrict__ vol, long long n_v
   bits[w] = m;
 }
 
+// raw bits -> occ2: cell (X,Y,Z), X = x0+1 in [0,W], holds OR of the raw bits at (x0..x0+1, y0..y0+1, z0..z0+1)
+// (out-of-range corners read as 0); 4x4x2 cells per word.  One thread per occ2 cell.
+__global__ void ngf_pack_occ2_kernel(const uint32_t* __restrict__ bits, int W, int H, int D,
+                                     uint32_t* __restrict__ occ2, int nxb, int nyb, uint32_t* __restrict__ coarse,
+                                     int cx, int cy, int* __restrict__ bbox) {
+  const long long n = (long long)(W + 1) * (H + 1) * (D + 1);
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int X = (int)(idx % (W + 1)), Y = (int)((idx / (W + 1)) % (H + 1)), Z = (int)(idx / ((long long)(W + 1) * (H + 1)));
+  bool any = false;
+  for (int dz = 0; dz < 2; ++dz)
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx) {
+        const int x = X - 1 + dx, y = Y - 1 + dy, z = Z - 1 + dz;
+        if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H && (unsigned)z < (unsigned)D) {
+          const uint32_t b = ((uint32_t)z * (uint32_t)H + (uint32_t)y) * (uint32_t)W + (uint32_t)x;
+          any = any || ((bits[b >> 5] >> (b & 31)) & 1u);
+        }
+      }
+  if (!any) return;
+  const uint32_t word = ((uint32_t)(Z >> 1) * (uint32_t)nyb + (uint32_t)(Y >> 2)) * (uint32_t)nxb + (uint32_t)(X >> 2);
+  atomicOr(occ2 + word, 1u << ((X & 3) | ((Y & 3) << 2) | ((Z & 1) << 4)));
+  const uint32_t cb = ((uint32_t)(Z >> 3) * (uint32_t)cy + (uint32_t)(Y >> 3)) * (uint32_t)cx + (uint32_t)(X >> 3);
+  atomicOr(coarse + (cb >> 5), 1u << (cb & 31));
+  atomicMin(bbox + 0, X); atomicMin(bbox + 1, Y); atomicMin(bbox + 2, Z);
+  atomicMax(bbox + 3, X); atomicMax(bbox + 4, Y); atomicMax(bbox + 5, Z);
+}
+
+// dsum[t] = sum_c dens[t][c] * w[c]
+__global__ void ngf_pack_dsum_kernel(const float* __restrict__ dens, long long hw, int DC, const float* __restrict__ w,
+                                     float* __restrict__ dsum) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= hw) return;
+  float s = 0.f;
+  for (int c = 0; c < DC; ++c) s += dens[t * DC + c] * w[c];
+  dsum[t] = s;
+}
+
 cudaError_t launch_pack_plane(const float* nchw, int C, int H, int W, int DC, float* dens, __half* app,
                               cudaStream_t st) {
   long long n = (long long)C * H * W;
@@ -469,6 +551,19 @@ cudaError_t launch_pack_gauge(const float* nchw, int H, int W, float2* out, cuda
 cudaError_t launch_pack_occ(const float* vol, long long n_vox, uint32_t* bits, cudaStream_t st) {
   long long words = (n_vox + 31) / 32;
   ngf_pack_occ_kernel<<<blocks_for(words, 256), 256, 0, st>>>(vol, n_vox, bits);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_occ2(const uint32_t* bits, int W, int H, int D, uint32_t* occ2, int nxb, int nyb, int nzb,
+                             uint32_t* coarse, int cx, int cy, int cz, int* bbox, cudaStream_t st) {
+  (void)nzb; (void)cz;
+  const long long n = (long long)(W + 1) * (H + 1) * (D + 1);
+  ngf_pack_occ2_kernel<<<blocks_for(n, 256), 256, 0, st>>>(bits, W, H, D, occ2, nxb, nyb, coarse, cx, cy, bbox);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_dsum(const float* dens, long long hw, int DC, const float* w_dev, float* dsum, cudaStream_t st) {
+  ngf_pack_dsum_kernel<<<blocks_for(hw, 256), 256, 0, st>>>(dens, hw, DC, w_dev, dsum);
   NGF_COUNT_LAUNCH();
   return cudaGetLastError();
 }

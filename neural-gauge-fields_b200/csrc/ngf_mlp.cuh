@@ -17,19 +17,15 @@
 // offset LBO = rows * 16 B.  Element (row r, col k) lives at (k/8)*rows*16 + r*16 + (k%8)*2.
 #pragma once
 #include "ngf_common.cuh"
+#include "ngf_queue.h"
 
 namespace ngf {
 
 constexpr int kTileM = 128;                 // samples per MLP tile == UMMA M
 constexpr int kThreads = 256;               // CTA size of every kernel that calls mlp_tile
-constexpr int kQueueCap = 512;              // ring of pending colour samples (power of two)
+constexpr int kQueueCap = 128;              // work items of the tile in flight (power of two)
 constexpr uint32_t kTmemCols = 128;         // 64 fp32 columns per layer accumulator
 
-struct __align__(16) QEntry {               // one colour sample waiting for the MLP
-  float c[6];                               // plane coordinates after the gauge: u_xy v_xy u_yz v_yz u_xz v_xz
-  float w;                                  // compositing weight
-  int id;                                   // ray (render) or row (point-wise) index; -1 = padding
-};
 
 // ----------------------------------------------------------------------------------------------------------
 // PTX wrappers (sm_100a)
@@ -139,11 +135,7 @@ struct MlpSmem {
 struct MlpCtl {               // lives at offCtl
   uint64_t bar;               // mbarrier for tcgen05.commit
   uint32_t tmem_base;
-  uint32_t q_head;            // ring counters (monotonic; slot = counter & (kQueueCap-1))
-  uint32_t q_tail;
-  uint32_t n_exhausted;       // warps that have run out of ray tiles
-  uint32_t phase;             // unused in smem (phase is tracked in registers); kept for debugging
-  uint32_t pad;
+  uint32_t pad[5];
 };
 
 // Copy the packed weights into shared memory, allocate TMEM, init the mbarrier.  All threads call it.
@@ -164,9 +156,6 @@ __device__ __forceinline__ void mlp_setup(const FieldDev& f, uint8_t* smem) {
   for (int i = tid; i < (int)(L::kABytes / 16); i += kThreads) da[i] = make_uint4(0, 0, 0, 0);
   MlpCtl* ctl = reinterpret_cast<MlpCtl*>(smem + L::offCtl);
   if (tid == 0) {
-    ctl->q_head = 0;
-    ctl->q_tail = 0;
-    ctl->n_exhausted = 0;
     ctl->tmem_base = 0;
     if (IMPL == 0) {
       mbar_init(&ctl->bar, 1);
@@ -305,8 +294,7 @@ __device__ __forceinline__ void mlp_gather(const FieldDev& f, uint8_t* smem, uin
 // ----------------------------------------------------------------------------------------------------------
 template <int V, int IMPL, bool ATOMIC>
 __device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint32_t head, uint32_t& phase,
-                                         const float* __restrict__ dir, int dir_stride, float* __restrict__ out,
-                                         int lbo_swap) {
+                                         const float* __restrict__ dir, int dir_stride, float* __restrict__ out) {
   using L = MlpSmem<V>;
   constexpr int NKC = L::NKC;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -323,8 +311,7 @@ __device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint3
     fence_async_smem();
     __syncthreads();
     const uint32_t tmem = ctl->tmem_base;
-    const uint32_t lboA = lbo_swap ? 128u : kTileM * 16u, sboA = lbo_swap ? kTileM * 16u : 128u;
-    const uint32_t lboB = lbo_swap ? 128u : kMid * 16u, sboB = lbo_swap ? kMid * 16u : 128u;
+    constexpr uint32_t lboA = kTileM * 16u, sboA = 128u, lboB = kMid * 16u, sboB = 128u;
     constexpr uint32_t idesc = umma_idesc(kTileM, kMid);
     // ---- layer 1: [128 x K1] x [K1 x 64] -> TMEM columns [0,64)
     if (tid == 0) {
@@ -382,8 +369,7 @@ __device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint3
     tc_fence_before();
     __syncthreads();
     const uint32_t tmem = ctl->tmem_base;
-    const uint32_t lboA = lbo_swap ? 128u : kTileM * 16u, sboA = lbo_swap ? kTileM * 16u : 128u;
-    const uint32_t lboB = lbo_swap ? 128u : kMid * 16u, sboB = lbo_swap ? kMid * 16u : 128u;
+    constexpr uint32_t lboA = kTileM * 16u, sboA = 128u, lboB = kMid * 16u, sboB = 128u;
     constexpr uint32_t idesc = umma_idesc(kTileM, kMid);
     // ---- layer 2: [128 x 64] x [64 x 64] -> TMEM columns [64,128)
     if (tid == 0) {

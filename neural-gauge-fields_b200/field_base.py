@@ -78,13 +78,22 @@ class Base(torch.nn.Module):
 
     # ------------------------------------------------------------------ bookkeeping (FieldBase.py:63-74)
     def init_para(self, gridSize):
-        self.aabbSize = self.aabb[1] - self.aabb[0]
-        self.invaabbSize = 2.0 / self.aabbSize
-        self.gridSize = torch.LongTensor(list(gridSize)).to(self.device)
-        self.units = self.aabbSize / (self.gridSize - 1)
-        self.stepSize = torch.mean(self.units) * self.step_ratio
-        self.aabbDiag = torch.sqrt(torch.sum(torch.square(self.aabbSize)))
-        self.nSamples = int((self.aabbDiag / self.stepSize).item()) + 1
+        # Evaluated on the CPU whatever the field's device: a CUDA torch.mean can round differently from the CPU
+        # one by an ulp, and stepSize feeds every sample position (one ulp there moves samples across mask
+        # boundaries).  The reference's CPU path is the parity target.
+        aabb = self.aabb.detach().float().cpu()
+        size = aabb[1] - aabb[0]
+        grid = torch.LongTensor([int(g) for g in gridSize])
+        units = size / (grid - 1)
+        step = torch.mean(units) * self.step_ratio
+        diag = torch.sqrt(torch.sum(torch.square(size)))
+        self.aabbSize = size.to(self.device)
+        self.invaabbSize = (2.0 / size).to(self.device)
+        self.gridSize = grid.to(self.device)
+        self.units = units.to(self.device)
+        self.stepSize = step.to(self.device)
+        self.aabbDiag = diag.to(self.device)
+        self.nSamples = int((diag / step).item()) + 1
         self._invalidate()
 
     def init_model(self, **kw):
@@ -297,6 +306,16 @@ class Base(torch.nn.Module):
         st = _lib.NgfStats()
         _lib.check(_lib.load().ngf_field_stats(self._ensure_handle(), C.byref(st), _cuda_stream_ptr(self.device)))
         return {k: int(getattr(st, k)) for k, _ in st._fields_}
+
+    def kernel_timing(self, capacity: int):
+        """Arm (capacity > 0) or disarm (0) CUDA-event timing of the march / colour kernels (ngf_field_timing_begin)."""
+        _lib.check(_lib.load().ngf_field_timing_begin(self._ensure_handle(), int(capacity)))
+
+    def kernel_timing_read(self):
+        """-> (march+colour pairs timed, march milliseconds, colour milliseconds) since the last read."""
+        n, a, b = C.c_int32(), C.c_double(), C.c_double()
+        _lib.check(_lib.load().ngf_field_timing_read(self._ensure_handle(), C.byref(n), C.byref(a), C.byref(b)))
+        return int(n.value), float(a.value), float(b.value)
 
     # ------------------------------------------------------------------ point-wise API parity
     def _pts_call(self, fn_name, inputs, out_shapes, out_dtypes, *extra_before_out, extra_after=()):

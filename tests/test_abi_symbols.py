@@ -37,9 +37,9 @@ def test_library_is_sm100a_and_uses_tcgen05(lib):
     import ngf_b200
     out = subprocess.run(["cuobjdump", "-lelf", ngf_b200._lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3ngf17ngf_render_kernelILi0ELi0EEEvNS_8FieldDevENS_10RenderArgsE",
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3ngf17ngf_colour_kernelILi0ELi0EEEvNS_8FieldDevENS_10RenderArgsE",
                            ngf_b200._lib.LIB_PATH], capture_output=True, text=True).stdout
-    assert "UTCHMMA" in sass or "UTCMMA" in sass, "render kernel has no tcgen05 MMA in its SASS"
+    assert "UTCHMMA" in sass or "UTCMMA" in sass, "colour kernel has no tcgen05 MMA in its SASS"
 
 
 def test_argument_validation_without_gpu(lib):

@@ -33,6 +33,7 @@ def test_render_matches_reference_golden(name, impl):
     assert K.fingerprint(state, rays, occ) == str(gold["fingerprint"])
     f, rgb, depth = _render_cuda(case, state, kw, occ, rays, impl)
     assert f.nSamples == int(gold["n_samples"])
+    assert np.float32(f.stepSize.item()) == gold["step_size"]
     st = f.last_stats()
     assert st["samples_density"] > 0
     err = np.abs(rgb.numpy() - gold["rgb"]).max()
