@@ -39,7 +39,7 @@ struct MarchSmem {
 };
 
 template <int V>
-__global__ void __launch_bounds__(kMarchThreads, V == 0 ? 3 : 1) ngf_march_kernel(const __grid_constant__ FieldDev f,
+__global__ void __launch_bounds__(kMarchThreads, V == 0 ? 3 : 2) ngf_march_kernel(const __grid_constant__ FieldDev f,
                                                                 const __grid_constant__ RenderArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -225,13 +225,21 @@ __global__ void ngf_finalize_kernel(float* __restrict__ rgb, const float* __rest
   rgb[i] = fminf(fmaxf(v, 0.f), 1.f);
 }
 
-static int blocks_per_sm(const void* kern, int threads, size_t smem) {
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) {
-    cudaGetLastError();
-    occ = 1;
-  }
-  return occ;
+// Resident CTAs per SM from the kernel's own resource use (registers, shared memory, threads).
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for the tcgen05 kernels here although two CTAs fit
+// (ncu: register and shared-memory limits both 2), so the limits are evaluated directly.
+static int blocks_per_sm(const void* kern, int threads, size_t dyn_smem) {
+  cudaFuncAttributes fa{};
+  if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) { cudaGetLastError(); return 1; }
+  const int regs_per_warp = ((fa.numRegs * 32 + 511) / 512) * 512;        // allocation granularity: 512 regs / warp
+  const int warps = (threads + 31) / 32;
+  int by_regs = 65536 / (regs_per_warp * warps);
+  int by_smem = (int)((227 * 1024 + 1024) / (dyn_smem + fa.sharedSizeBytes + 1024));
+  int by_threads = 2048 / threads;
+  int occ = by_regs < by_smem ? by_regs : by_smem;
+  if (by_threads < occ) occ = by_threads;
+  if (occ > 32) occ = 32;
+  return occ < 1 ? 1 : occ;
 }
 
 template <int V>

@@ -1,0 +1,38 @@
+"""Summarise an .ncu-rep (read here, no GPU needed): per captured launch the metrics the roofline uses.
+Usage: python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [--lines N]"""
+import csv
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__grid_size", "launch__block_size",
+        "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "launch__waves_per_multiprocessor", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.sum",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__cycles_elapsed.max"]
+
+
+def raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    return rows[0], rows[1], rows[2:]
+
+
+def main():
+    rep = sys.argv[1]
+    hdr, units, rows = raw(rep)
+    ki = hdr.index("Kernel Name")
+    for r in rows:
+        print("==", r[ki][:100])
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                print(f"   {k:78s} {r[i]:>18s} {units[i]}")
+
+
+if __name__ == "__main__":
+    main()

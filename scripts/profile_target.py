@@ -1,0 +1,36 @@
+"""Small ncu target: N whole-frame renders of BASELINE configs[1] in the sparse ("hull") or dense regime.
+Usage: python scripts/profile_target.py hull|dense|infoinv [n_renders]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import ngf_b200
+from ngf_b200 import synth
+
+regime = sys.argv[1] if len(sys.argv) > 1 else "hull"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+dev = torch.device("cuda", 0)
+kw = synth.field_kwargs("C2")
+if regime == "infoinv":
+    f = ngf_b200.InfoInvTriPlane(kw["aabb"], kw["gridSize"], dev, near_far=kw["near_far"], step_ratio=kw["step_ratio"],
+                                 distance_scale=25, rayMarch_weight_thres=1e-4)
+    synth.load_into(f, synth.field_state("infoinv", "hull"), synth.occupancy_volume("hull"), ngf_b200.AlphaGridMask)
+    fwd = dict(infoinv=True)
+else:
+    thres = -1.0 if regime == "dense" else 1e-4
+    f = ngf_b200.TriPlane(kw["aabb"], kw["gridSize"], dev, near_far=kw["near_far"], step_ratio=kw["step_ratio"],
+                          distance_scale=25, rayMarch_weight_thres=thres, gauge_start=0)
+    st = synth.field_state("triplane", "fog" if regime == "dense" else "hull")
+    if regime == "dense":
+        st["density_decoder.bias"] = st["density_decoder.bias"] - 12.0
+        synth.load_into(f, st)
+    else:
+        synth.load_into(f, st, synth.occupancy_volume("hull"), ngf_b200.AlphaGridMask)
+    fwd = dict(iteration=30001)
+rays = [synth.config_rays("C2", p).to(dev) for p in range(2)]
+for i in range(n):
+    f(rays[i % 2], white_bg=True, N_samples=192, image_width=800, **fwd)
+torch.cuda.synchronize()
+print(regime, f.last_stats())
