@@ -220,6 +220,56 @@ int ngf_shard_gather(const float* src_dev, int64_t n_rays, int32_t width, int32_
 int ngf_shard_scatter(const float* src_dev, int64_t n_rays, int32_t width, int32_t block, int32_t world,
                       int64_t max_shard, float* dst_dev, void* stream);
 
+/* =====================================================================================================
+ * UV-Mapping (NeuTex) render path.  Reference (paths relative to /root/reference/UV-Mapping):
+ * NeuTex.forward (model/model.py:27-59) = cube_ray_generation (model/renderer.py:79-141) -> GeometryMlpDecoder
+ * (model/decoder.py:201-237) -> GaugeTransform (model/gauge_fields.py:8-74) -> TextureMlpDecoder
+ * (model/decoder.py:11-121) -> ray_march / simple_tone_map (model/renderer.py:4-11,176-247), as called per 1024-ray
+ * chunk by test.py:108-114 through Model.test (model/model.py:362-373).  primitive_type = 'square'.
+ * ===================================================================================================== */
+typedef struct NgfNeutexDesc {
+  NgfLinear geometry[12];   /* net_geometry_decoder.block.{0,2,...,22}: 63->256, 10 x 256->256, 256->1          */
+  NgfLinear gauge[5];       /* gauge_transform.encoder.{linear1, linear2, linear_list.0, linear_list.1, last_linear} */
+  NgfLinear tex_block1[6];  /* net_texture.block1.{0,2,...,10}: 42->256, 5 x 256->256                            */
+  NgfLinear tex_color1;     /* net_texture.color1: 256->3                                                        */
+  NgfLinear tex_block2[5];  /* net_texture.block2.{0,2,4,6,8}: 295->256, 3 x 256->256, 256->3                    */
+  int32_t sample_num;       /* opt.sample_num (64)                                                               */
+  float jitter;             /* 0.05, hard-coded at model/model.py:30                                             */
+  const float* texture;     /* TextureMlpDecoder.cubemap_ after load_square: [h][w][c] fp32 in [0,1], or NULL    */
+  int32_t tex_h, tex_w, tex_c;
+} NgfNeutexDesc;
+
+typedef struct NgfNeutex_* NgfNeutex;
+
+/* Pack the three MLP stacks into tcgen05 operand order (fp16; the gauge network as hi+lo split fp16).  Parameter
+ * pointers may be host or device memory.  Synchronous. */
+int ngf_neutex_pack(const NgfNeutexDesc* desc, int device, NgfNeutex* out);
+void ngf_neutex_free(NgfNeutex h);
+
+/*
+ * Render rays of ONE camera: replaces NeuTex.forward(camera_position[1,3], ray_direction[1,R,3], background_color[1,3])
+ * -> output["color"] [1,R,3], output["transmittance"] [1,R].
+ *   noise_dev  [R][64] U[0,1) numbers the reference draws with torch.rand inside cube_ray_generation
+ *              (renderer.py:113-118), or NULL for no jitter
+ *   background_dev  [3] or NULL (model.py:48-49)
+ */
+int ngf_neutex_render(NgfNeutex h, const float* campos_dev, const float* raydir_dev, const float* background_dev,
+                      const float* noise_dev, int64_t n_rays, float* color_dev, float* transmittance_dev, void* stream);
+/* Same through HOST buffers (what test.py's chunk loop does with model.set_input / .cpu()); returns when the results
+ * are in color_host / transmittance_host. */
+int ngf_neutex_render_host(NgfNeutex h, const float* campos_host, const float* raydir_host, const float* background_host,
+                           const float* noise_host, int64_t n_rays, float* color_host, float* transmittance_host);
+/* In-cube samples the last render evaluated (synchronises `stream`). */
+int ngf_neutex_last_valid_samples(NgfNeutex h, uint64_t* n_valid, void* stream);
+/* Per-sample view of the last render (tests): (sigma, r, g, b) of samples [first_sample, first_sample+n) — defined only
+ * where the corresponding valid_mask bit is set — and the per-ray 64-bit in-cube masks (bit i = sample i), i.e. the
+ * density / radiance / valid tensors NeuTex.forward hands to ray_march (model.py:40-47).  Synchronises the device. */
+int ngf_neutex_copy_samples(NgfNeutex h, int64_t first_sample, int64_t n, float* sigma_rgb_host, uint64_t* valid_mask_host,
+                            int64_t first_ray, int64_t n_mask_rays);
+/* CUDA-event timing of the three kernels of a render (ray generation | MLP | march), as ngf_field_timing_*. */
+int ngf_neutex_timing_begin(NgfNeutex h, int32_t capacity);
+int ngf_neutex_timing_read(NgfNeutex h, int32_t* n_renders, double* raygen_ms, double* mlp_ms, double* march_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,7 @@ Layout (only what the path needs):
   _lib.py       ctypes binding of the C ABI
   field_base.py / triplane.py / infoinv.py / networks.py
                 host-side mirrors of the reference's model classes (same names, ctor, forward signature)
+  neutex.py     host-side mirror of the UV-Mapping ``NeuTex`` module (render path)
   render.py     ``renderer`` (reference: TriPlane/main.py:60-71) + multi-GPU ray sharding
   synth.py      seeded synthetic cameras / fields used by tests and bench (no dataset exists offline)
 
@@ -14,6 +15,7 @@ from . import _lib  # noqa: F401
 from .field_base import AlphaGridMask, Base  # noqa: F401
 from .triplane import TriPlane  # noqa: F401
 from .infoinv import TriPlane as InfoInvTriPlane  # noqa: F401
+from .neutex import NeuTex  # noqa: F401
 from .render import renderer, render_frame_sharded, shard_rays, unshard_frame  # noqa: F401
 
 __version__ = "0.1.0"

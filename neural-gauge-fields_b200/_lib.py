@@ -40,6 +40,13 @@ class NgfFieldDesc(C.Structure):
     ]
 
 
+class NgfNeutexDesc(C.Structure):
+    _fields_ = [("geometry", NgfLinear * 12), ("gauge", NgfLinear * 5), ("tex_block1", NgfLinear * 6),
+                ("tex_color1", NgfLinear), ("tex_block2", NgfLinear * 5), ("sample_num", C.c_int32),
+                ("jitter", C.c_float), ("texture", C.c_void_p), ("tex_h", C.c_int32), ("tex_w", C.c_int32),
+                ("tex_c", C.c_int32)]
+
+
 class NgfStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("samples_in_box", C.c_uint64), ("samples_density", C.c_uint64),
                 ("samples_colour", C.c_uint64), ("mlp_tiles", C.c_uint64)]
@@ -73,6 +80,17 @@ SIGNATURES = {
     "ngf_field_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                 C.c_int32, C.c_void_p]),
     "ngf_field_sigma_world": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ngf_neutex_pack": (C.c_int, [C.POINTER(NgfNeutexDesc), C.c_int, C.POINTER(C.c_void_p)]),
+    "ngf_neutex_free": (None, [C.c_void_p]),
+    "ngf_neutex_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
+    "ngf_neutex_render_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_void_p]),
+    "ngf_neutex_last_valid_samples": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
+    "ngf_neutex_copy_samples": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
+    "ngf_neutex_timing_begin": (C.c_int, [C.c_void_p, C.c_int32]),
+    "ngf_neutex_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double)]),
     "ngf_shard_count": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "ngf_shard_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_void_p]),

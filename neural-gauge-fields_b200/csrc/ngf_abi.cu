@@ -27,6 +27,15 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// shared with ngf_neutex_abi.cu
+int ngf_set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
 #define CU(expr)                                                                                          \
   do {                                                                                                    \
     cudaError_t _e = (expr);                                                                              \

@@ -24,6 +24,7 @@ namespace ngf {
 
 static std::atomic<uint64_t> g_launches{0};
 uint64_t launch_count() { return g_launches.load(); }
+void count_launch() { g_launches.fetch_add(1); }
 #define NGF_COUNT_LAUNCH() g_launches.fetch_add(1)
 
 constexpr float kTStop = 1e-6f;   // stop marching once transmittance <= kTStop: all later weights sum to <= 1e-6

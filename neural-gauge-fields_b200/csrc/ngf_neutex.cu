@@ -1,0 +1,500 @@
+// ngf_neutex.cu — sm_100a kernels of the UV-Mapping (NeuTex) render path (see ngf_neutex.cuh for the reference map).
+//
+//   ntx_raygen_kernel   cube_ray_generation (model/renderer.py:79-141), one ray per thread: slab test, jittered
+//                       segment lengths, end points by a double-precision running sum (torch's CPU cumsum accumulates
+//                       in double), mid points, p = campos + raydir * mid, strict in-cube test.  In-cube samples are
+//                       compacted (warp prefix sum, one atomic per warp) into a work list.
+//   ntx_mlp_kernel      persistent CTAs (one per SM), 256-sample tiles.  Every K=16 weight slice streamed from L2 by a
+//                       producer warp (cp.async.bulk -> mbarrier ring) feeds two M=128 tcgen05.mma tiles whose
+//                       accumulators fill the SM's TMEM (2 x 256 fp32 columns); 256 worker threads own one sample
+//                       row each: they build the sinusoidal encodings, run the epilogues TMEM -> bias/activation ->
+//                       fp16 -> shared-memory A operand of the next layer, and evaluate the narrow heads
+//                       (density, uv, colour) in fp32.  The gauge network runs split-fp16 (hi + lo, 3 MMAs per slice)
+//                       because its output is multiplied by 2^9 inside PE(uv, 10).
+//   ntx_march_kernel    ray_march + alpha_blend + background + simple_tone_map (model/renderer.py:4-11,176-247;
+//                       model/model.py:46-50), one ray per thread, transmittance as a double running product.
+#include "ngf_neutex.cuh"
+
+#include <atomic>
+
+#include "ngf_mlp.cuh"
+
+namespace ngf {
+uint64_t launch_count();
+void count_launch();
+namespace ntx {
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX helpers beyond ngf_mlp.cuh
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// shared-memory map of ntx_mlp_kernel
+constexpr uint32_t kKGroupBytes = kRows * 16;            // one 8-wide K group of the 256-row A operand
+constexpr uint32_t offA = 0;                             // [32 K groups][256 rows][8 halves]  (split: lo half at +64 KiB)
+constexpr uint32_t kABytes = 32 * kKGroupBytes;          // 131072
+constexpr uint32_t offA2 = offA + kABytes;               // view-direction operand, K = 48
+constexpr uint32_t kA2Bytes = 6 * kKGroupBytes;          // 24576
+constexpr uint32_t offRing = offA2 + kA2Bytes;
+constexpr uint32_t offBar = offRing + kStages * kStageBytes;
+constexpr uint32_t kSmemBytes = offBar + 256;
+constexpr uint32_t kALoOff = 16 * kKGroupBytes;          // lo operand of split layers (K <= 128)
+
+struct Bars {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t acc_ready;
+  uint64_t a_ready;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+// ---------------------------------------------------------------------------------------------------------
+// A-operand writers.  Element (row r, column k) lives at (k / 8) * kKGroupBytes + r * 16 + (k % 8) * 2.
+// ---------------------------------------------------------------------------------------------------------
+template <int NG, bool SPLIT>
+__device__ __forceinline__ void store_groups(uint8_t* A, int row, const float* v) {
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = v[8 * g + 2 * e], b = v[8 * g + 2 * e + 1];
+      __half2 h = __floats2half2_rn(a, b);
+      hi[e] = *reinterpret_cast<uint32_t*>(&h);
+      if (SPLIT) {
+        float2 back = __half22float2(h);
+        __half2 l = __floats2half2_rn(a - back.x, b - back.y);
+        lo[e] = *reinterpret_cast<uint32_t*>(&l);
+      }
+    }
+    *reinterpret_cast<uint4*>(A + g * kKGroupBytes + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (SPLIT) *reinterpret_cast<uint4*>(A + kALoOff + g * kKGroupBytes + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// [x, sin(x_d * 2^f), cos(x_d * 2^f)] with column order of util.py:427-438 (d-major, then f), zero padded to 8*NG
+template <int D, int F, int NG, bool SPLIT>
+__device__ __forceinline__ void write_encoding(uint8_t* A, int row, const float* x) {
+  float v[8 * NG];
+#pragma unroll
+  for (int i = 0; i < 8 * NG; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    v[d] = x[d];
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      float s, c;
+      sincosf(x[d] * (float)(1 << f), &s, &c);
+      v[D + d * F + f] = s;
+      v[D + D * F + d * F + f] = c;
+    }
+  }
+  store_groups<NG, SPLIT>(A, row, v);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Epilogue of one layer for one row: TMEM -> + bias -> activation -> (fp16 A operand of the next layer) and/or
+// fp32 dot products with up to 3 head weight rows.
+// ---------------------------------------------------------------------------------------------------------
+template <int N, int ACT, bool WRITE, bool SPLIT, int NH>
+__device__ __forceinline__ void epilogue(uint32_t taddr, const float* __restrict__ bias, uint8_t* A, int row,
+                                         const float* __restrict__ headw, float* hacc) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    tmem_ld32(taddr + c0, v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + q);
+      v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = ACT == 0 ? fmaxf(v[j], 0.f) : fmaxf(v[j], 0.2f * v[j]);
+    if (NH > 0) {
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        float s = hacc[h];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(headw + h * N + c0) + q);
+          s += v[4 * q] * w.x + v[4 * q + 1] * w.y + v[4 * q + 2] * w.z + v[4 * q + 3] * w.w;
+        }
+        hacc[h] = s;
+      }
+    }
+    if (WRITE) store_groups<4, SPLIT>(A + (c0 / 8) * kKGroupBytes, row, v);
+  }
+}
+
+// sample_square (util.py:277-282): bilinear, align_corners=False, border padding, over tex [h][w][c]
+__device__ __forceinline__ void sample_texture(const NetDev& net, float u, float v, float out[3]) {
+  const int W = net.tex_w, H = net.tex_h, C = net.tex_c;
+  float ix = ((u + 1.f) * (float)W - 1.f) * 0.5f, iy = ((v + 1.f) * (float)H - 1.f) * 0.5f;
+  ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
+  iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
+  const float fx = ix - x0f, fy = iy - y0f;
+  const float w00 = (1.f - fx) * (1.f - fy), w10 = fx * (1.f - fy), w01 = (1.f - fx) * fy, w11 = fx * fy;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int cc = c < C ? c : C - 1;
+    float s = w00 * __ldg(net.texture + ((size_t)y0 * W + x0) * C + cc);
+    if (x1 < W) s += w10 * __ldg(net.texture + ((size_t)y0 * W + x1) * C + cc);
+    if (y1 < H) s += w01 * __ldg(net.texture + ((size_t)y1 * W + x0) * C + cc);
+    if (x1 < W && y1 < H) s += w11 * __ldg(net.texture + ((size_t)y1 * W + x1) * C + cc);
+    out[c] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_constant__ NetDev net,
+                                                              const __grid_constant__ RenderArgsN a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Bars* bars = reinterpret_cast<Bars*>(smem + offBar);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t count = *reinterpret_cast<volatile const unsigned int*>(a.counters);
+  const uint32_t n_tiles = (count + kRows - 1) / kRows;
+  if (blockIdx.x >= n_tiles) return;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    mbar_init(&bars->acc_ready, 1);
+    mbar_init(&bars->a_ready, kWorkerThreads / 32);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == 8) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 9) {
+    // ------------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < kNumLayers; ++l) {
+          const LayerDesc& L = net.layer[l];
+          const int nk = (L.K + L.Kext) / 16;
+          for (int kk = 0; kk < nk; ++kk, ++it) {
+            const uint32_t s = it % kStages;
+            mbar_wait(&bars->empty[s], ((it / kStages) & 1u) ^ 1u);
+            mbar_expect_tx(&bars->full[s], L.chunk_bytes);
+            bulk_g2s(smem + offRing + s * kStageBytes, net.wpack + L.w_off + (size_t)kk * L.chunk_bytes, L.chunk_bytes,
+                     &bars->full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, par_a = 0;
+      const uint32_t a0 = smem_u32(smem + offA), a2 = smem_u32(smem + offA2), r0 = smem_u32(smem + offRing);
+      for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < kNumLayers; ++l) {
+          const LayerDesc& L = net.layer[l];
+          const int nk_main = L.K / 16, nk = (L.K + L.Kext) / 16;
+          const uint32_t idesc = umma_idesc(128, L.N);
+          const uint32_t lboB = (uint32_t)L.N * 16u;
+          mbar_wait(&bars->a_ready, par_a);
+          par_a ^= 1u;
+          tc_fence_after();
+          for (int kk = 0; kk < nk; ++kk, ++it) {
+            const uint32_t s = it % kStages;
+            mbar_wait(&bars->full[s], (it / kStages) & 1u);
+            tc_fence_after();
+            const uint32_t abase = kk < nk_main ? a0 + (uint32_t)kk * 2u * kKGroupBytes
+                                                : a2 + (uint32_t)(kk - nk_main) * 2u * kKGroupBytes;
+            const uint32_t bbase = r0 + s * kStageBytes;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const uint32_t d = tmem + (uint32_t)half * 256u;
+              const uint32_t ah = abase + (uint32_t)half * 128u * 16u;
+              const uint64_t da_hi = umma_desc(ah, kKGroupBytes, 128u);
+              const uint64_t db_hi = umma_desc(bbase, lboB, 128u);
+              umma_f16(d, da_hi, db_hi, idesc, kk > 0);
+              if (L.split) {
+                const uint64_t da_lo = umma_desc(ah + kALoOff, kKGroupBytes, 128u);
+                const uint64_t db_lo = umma_desc(bbase + (uint32_t)L.N * 32u, lboB, 128u);
+                umma_f16(d, da_lo, db_hi, idesc, 1u);
+                umma_f16(d, da_hi, db_lo, idesc, 1u);
+              }
+            }
+            umma_commit(&bars->empty[s]);
+          }
+          umma_commit(&bars->acc_ready);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ row workers (warps 0..7)
+    const int half = warp >> 2;
+    const int row = half * 128 + (warp & 3) * 32 + lane;
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)half * 256u;
+    uint8_t* A = smem + offA;
+    uint32_t par_acc = 0;
+    auto signal_a = [&]() {
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->a_ready);
+    };
+    auto wait_acc = [&]() {
+      mbar_wait(&bars->acc_ready, par_acc);
+      par_acc ^= 1u;
+      tc_fence_after();
+    };
+    const float* heads = net.heads;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const uint32_t item = tile * kRows + row;
+      int id = -1;
+      float p[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
+      if (item < count) {
+        const float4 e = __ldg(a.work + item);
+        id = __float_as_int(e.x);
+        p[0] = e.y; p[1] = e.z; p[2] = e.w;
+        const float* rd = a.raydir + (size_t)(id >> 6) * 3;
+        dir[0] = __ldg(rd); dir[1] = __ldg(rd + 1); dir[2] = __ldg(rd + 2);
+      }
+      int l = 0;
+      // ---- geometry: [p, PE(p,10)] -> 256 -> 10 x 256 (ReLU) -> 1 -> softplus          (decoder.py:201-237)
+      write_encoding<3, 10, 8, false>(A, row, p);
+      signal_a();
+      for (; l < 10; ++l) {
+        wait_acc();
+        epilogue<256, 0, true, false, 0>(taddr, net.bias + net.layer[l].b_off, A, row, nullptr, nullptr);
+        signal_a();
+      }
+      float raw = 0.f;
+      wait_acc();
+      epilogue<256, 0, false, false, 1>(taddr, net.bias + net.layer[l].b_off, A, row, heads + kHeadGeo, &raw);
+      ++l;
+      const float sigma = softplus_t(raw + __ldg(heads + kHeadGeoB));
+      // ---- gauge: [p, PE(p,10)] -> 64 -> 128 -> 128 -> 128 (ReLU) -> 2 -> tanh, split fp16   (gauge_fields.py:8-74)
+      write_encoding<3, 10, 8, true>(A, row, p);
+      signal_a();
+      wait_acc();
+      epilogue<64, 0, true, true, 0>(taddr, net.bias + net.layer[l].b_off, A, row, nullptr, nullptr);
+      ++l;
+      signal_a();
+      for (int r = 0; r < 2; ++r, ++l) {
+        wait_acc();
+        epilogue<128, 0, true, true, 0>(taddr, net.bias + net.layer[l].b_off, A, row, nullptr, nullptr);
+        signal_a();
+      }
+      float uvr[2] = {0.f, 0.f};
+      wait_acc();
+      epilogue<128, 0, false, true, 2>(taddr, net.bias + net.layer[l].b_off, A, row, heads + kHeadGauge, uvr);
+      ++l;
+      float uv[2] = {tanhf(uvr[0] + __ldg(heads + kHeadGaugeB)), tanhf(uvr[1] + __ldg(heads + kHeadGaugeB + 1))};
+      // ---- texture block1: [uv, PE(uv,10)] -> 256 -> 5 x 256 (LeakyReLU 0.2); color1 256 -> 3 softplus   (decoder.py:56-78)
+      write_encoding<2, 10, 6, false>(A, row, uv);
+      write_encoding<3, 6, 6, false>(smem + offA2, row, dir);
+      signal_a();
+      for (int r = 0; r < 5; ++r, ++l) {
+        wait_acc();
+        epilogue<256, 1, true, false, 0>(taddr, net.bias + net.layer[l].b_off, A, row, nullptr, nullptr);
+        signal_a();
+      }
+      float c1[3] = {0.f, 0.f, 0.f};
+      wait_acc();
+      epilogue<256, 1, true, false, 3>(taddr, net.bias + net.layer[l].b_off, A, row, heads + kHeadC1, c1);
+      ++l;
+      signal_a();
+#pragma unroll
+      for (int k = 0; k < 3; ++k) c1[k] = softplus_t(c1[k] + __ldg(heads + kHeadC1B + k));
+      // ---- texture block2: [h, d, PE(d,6)] -> 256 -> 3 x 256 (LeakyReLU) -> 3
+      for (int r = 0; r < 3; ++r, ++l) {
+        wait_acc();
+        epilogue<256, 1, true, false, 0>(taddr, net.bias + net.layer[l].b_off, A, row, nullptr, nullptr);
+        signal_a();
+      }
+      float c2[3] = {0.f, 0.f, 0.f};
+      wait_acc();
+      epilogue<256, 1, false, false, 3>(taddr, net.bias + net.layer[l].b_off, A, row, heads + kHeadB2, c2);
+      float rgb[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) rgb[k] = c1[k] + c2[k] + __ldg(heads + kHeadB2B + k);
+      if (net.texture == nullptr) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) rgb[k] = fmaxf(rgb[k], 0.f);                       // (c1 + c2).clamp(min=0)
+      } else {                                                                         // decoder.py:91-103, mode 0
+        float m = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) m += fminf(fmaxf(rgb[k] * 8.f, 0.f), 1.f);
+        m = m / 3.f;
+        float tx[3];
+        sample_texture(net, uv[0], uv[1], tx);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) rgb[k] = tx[k] * m;
+      }
+      if (id >= 0) a.sample_out[id] = make_float4(sigma, rgb[0], rgb[1], rgb[2]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// cube_ray_generation (model/renderer.py:79-141)
+// ---------------------------------------------------------------------------------------------------------
+struct RaySetup {
+  float c[3], d[3], t;
+};
+
+__device__ __forceinline__ RaySetup ray_setup(const RenderArgsN& a, long long ray) {
+  RaySetup r;
+  float tmin = -INFINITY, tmax = INFINITY;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    r.c[k] = __ldg(a.campos + k);
+    r.d[k] = __ldg(a.raydir + ray * 3 + k);
+    const float t1 = __fdiv_rn(__fsub_rn(-1.f, r.c[k]), r.d[k]);
+    const float t2 = __fdiv_rn(__fsub_rn(1.f, r.c[k]), r.d[k]);
+    tmin = fmaxf(tmin, fminf(t1, t2));
+    tmax = fminf(tmax, fmaxf(t1, t2));
+  }
+  r.t = fmaxf(tmin < tmax ? tmin : 0.f, 0.f);
+  return r;
+}
+
+// seg_i = dt + dt*jitter*(U_i - 0.5) (renderer.py:111-118); dt = 2/64, dt*jitter is a Python double cast to fp32
+__device__ __forceinline__ float seg_len(float dj, float u) { return __fadd_rn(0.03125f, __fmul_rn(dj, __fsub_rn(u, 0.5f))); }
+
+template <bool EMIT>
+__device__ __forceinline__ unsigned long long walk_ray(const RenderArgsN& a, const RaySetup& r, long long ray, float dj,
+                                                       float4* dst) {
+  unsigned long long mask = 0ull;
+  double run = 0.0;
+  float e_prev = __fadd_rn(r.t, 0.f);
+  int n = 0;
+#pragma unroll 4
+  for (int i = 0; i < kS; ++i) {
+    const float u = a.noise ? __ldg(a.noise + ray * kS + i) : 0.5f;
+    run += (double)seg_len(dj, u);
+    const float e = __fadd_rn(r.t, (float)run);
+    const float mid = __fmul_rn(__fadd_rn(e_prev, e), 0.5f);
+    e_prev = e;
+    float p[3];
+    bool in = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      p[k] = __fadd_rn(r.c[k], __fmul_rn(r.d[k], mid));
+      in = in && (p[k] > -1.f) && (p[k] < 1.f);
+    }
+    if (in) {
+      mask |= 1ull << i;
+      if (EMIT) dst[n++] = make_float4(__int_as_float((int)(ray * kS + i)), p[0], p[1], p[2]);
+    }
+  }
+  return mask;
+}
+
+__global__ void __launch_bounds__(128) ntx_raygen_kernel(const __grid_constant__ NetDev net,
+                                                         const __grid_constant__ RenderArgsN a) {
+  const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool live = ray < a.n_rays;
+  const float dj = (float)(0.03125 * (double)net.jitter);
+  RaySetup r{};
+  unsigned long long mask = 0ull;
+  if (live) {
+    r = ray_setup(a, ray);
+    mask = walk_ray<false>(a, r, ray, dj, nullptr);
+    a.valid_mask[ray] = mask;
+  }
+  // warp prefix sum of the per-ray counts, one atomic per warp
+  const int cnt = __popcll(mask);
+  int incl = cnt;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, s);
+    if (lane >= s) incl += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned int base = 0;
+  if (lane == 31 && total > 0) base = atomicAdd(a.counters, (unsigned int)total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (cnt > 0) walk_ray<true>(a, r, ray, dj, a.work + base + (incl - cnt));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ray_march (renderer.py:176-247) + background (model.py:48-49) + simple_tone_map (renderer.py:7-8)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ntx_march_kernel(const __grid_constant__ NetDev net,
+                                                        const __grid_constant__ RenderArgsN a) {
+  const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= a.n_rays) return;
+  const float dj = (float)(0.03125 * (double)net.jitter);
+  const unsigned long long mask = a.valid_mask[ray];
+  double T = 1.0;                           // torch.cumprod on the CPU accumulates in double
+  float col[3] = {0.f, 0.f, 0.f};
+  for (int i = 0; i < kS; ++i) {
+    if (!((mask >> i) & 1ull)) continue;    // sigma * 0 -> opacity 0 -> weight 0, transmittance factor 1 + 1e-10 == 1.f
+    const float u = a.noise ? __ldg(a.noise + ray * kS + i) : 0.5f;
+    const float seg = seg_len(dj, u);
+    const float4 s = a.sample_out[ray * kS + i];
+    const float op = __fsub_rn(1.f, expf(-__fmul_rn(s.x, seg)));
+    const float w = __fmul_rn(op, (float)T);
+    col[0] += s.y * w; col[1] += s.z * w; col[2] += s.w * w;
+    T *= (double)__fadd_rn(__fsub_rn(1.f, op), 1e-10f);
+  }
+  const float bg_t = (float)T;
+  const float gamma = (float)(1.0 / 2.2);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float c = col[k];
+    if (a.background) c += __ldg(a.background + k) * bg_t;
+    a.color[ray * 3 + k] = fminf(fmaxf(powf(c + 1e-5f, gamma), 0.f), 1.f);
+  }
+  a.transmittance[ray] = bg_t;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+cudaError_t launch_neutex_raygen(const NetDev& net, const RenderArgsN& a, cudaStream_t st) {
+  if (a.n_rays <= 0) return cudaSuccess;
+  ntx_raygen_kernel<<<(unsigned)((a.n_rays + 127) / 128), 128, 0, st>>>(net, a);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_neutex_mlp(const NetDev& net, const RenderArgsN& a, int num_sms, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ntx_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  long long worst = (a.n_rays * kS + kRows - 1) / kRows;
+  long long grid = num_sms < worst ? num_sms : worst;
+  if (grid < 1) grid = 1;
+  ntx_mlp_kernel<<<(unsigned)grid, kThreads, kSmemBytes, st>>>(net, a);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_neutex_march(const NetDev& net, const RenderArgsN& a, cudaStream_t st) {
+  if (a.n_rays <= 0) return cudaSuccess;
+  ntx_march_kernel<<<(unsigned)((a.n_rays + 127) / 128), 128, 0, st>>>(net, a);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace ntx
+}  // namespace ngf

@@ -1,0 +1,374 @@
+// ngf_neutex_abi.cu — C ABI of the UV-Mapping (NeuTex) render path: weight packing, workspaces, render entry points.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/ngf_b200.h"
+#include "ngf_neutex.cuh"
+
+using namespace ngf::ntx;
+
+int ngf_set_error(int code, const char* fmt, ...);   // ngf_abi.cu
+
+#define CUN(expr)                                                                                              \
+  do {                                                                                                         \
+    cudaError_t _e = (expr);                                                                                   \
+    if (_e != cudaSuccess) return ngf_set_error(NGF_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
+                                                __FILE__, __LINE__);                                           \
+  } while (0)
+
+struct NtxChunk {
+  cudaStream_t stream = nullptr;
+  float* raydir = nullptr;
+  float* noise = nullptr;
+  float* color = nullptr;
+  float* trans = nullptr;
+};
+
+struct NgfNeutex_ {
+  int device = 0;
+  int num_sms = 0;
+  NetDev net{};
+  uint8_t* wpack = nullptr;
+  float* bias = nullptr;
+  float* heads = nullptr;
+  float* texture = nullptr;
+  // workspace for up to cap_rays rays
+  long long cap_rays = 0;
+  float4* work = nullptr;
+  float4* sample_out = nullptr;
+  unsigned long long* valid_mask = nullptr;
+  unsigned int* counters = nullptr;          // [0] work count, [1] spare, [2..3] u64 valid-sample total
+  float* cam_bg = nullptr;                   // [6]: campos, background (host path)
+  NtxChunk chunk[2];
+  long long chunk_cap = 0;
+  std::vector<cudaEvent_t> ev;               // 4 per timed render: raygen | mlp | march
+  int ev_used = 0;
+  unsigned long long last_valid = 0;
+};
+
+static void ntx_free_ws(NgfNeutex_* h) {
+  cudaFree(h->work); cudaFree(h->sample_out); cudaFree(h->valid_mask);
+  h->work = h->sample_out = nullptr; h->valid_mask = nullptr; h->cap_rays = 0;
+}
+static void ntx_free_chunks(NgfNeutex_* h) {
+  for (auto& c : h->chunk) {
+    if (c.stream) cudaStreamDestroy(c.stream);
+    cudaFree(c.raydir); cudaFree(c.noise); cudaFree(c.color); cudaFree(c.trans);
+    c = NtxChunk{};
+  }
+  h->chunk_cap = 0;
+}
+static void ntx_free_all(NgfNeutex_* h) {
+  ntx_free_ws(h);
+  ntx_free_chunks(h);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  cudaFree(h->wpack); cudaFree(h->bias); cudaFree(h->heads); cudaFree(h->texture); cudaFree(h->counters); cudaFree(h->cam_bg);
+}
+
+struct Guard {
+  int prev = -1;
+  explicit Guard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+  ~Guard() { int cur = -1; if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev); }
+};
+
+static int check_lin(const NgfLinear& l, int in_dim, int out_dim, const char* name, int idx) {
+  if (!l.w || !l.b) return ngf_set_error(NGF_EINVAL, "%s[%d]: NULL weight or bias", name, idx);
+  if (l.in_dim != in_dim || l.out_dim != out_dim)
+    return ngf_set_error(NGF_EUNSUPPORTED, "%s[%d] is %dx%d, kernels are built for %dx%d", name, idx, l.out_dim, l.in_dim,
+                         out_dim, in_dim);
+  return NGF_OK;
+}
+
+static cudaError_t fetch(std::vector<float>& dst, const float* src, size_t n) {
+  dst.resize(n);
+  return cudaMemcpy(dst.data(), src, n * sizeof(float), cudaMemcpyDefault);
+}
+
+// Append the tcgen05 K-major chunks of one layer: for each K=16 step, [hi: 2 K-groups x N rows x 8 halves][lo: same]
+static void pack_layer(std::vector<uint8_t>& out, const std::vector<float>& W, int N, int K_in, int K_total, bool split) {
+  const int nk = K_total / 16;
+  const size_t chunk = (size_t)N * 32 * (split ? 2 : 1);
+  const size_t base = out.size();
+  out.resize(base + chunk * nk, 0);
+  for (int kk = 0; kk < nk; ++kk) {
+    __half* hi = reinterpret_cast<__half*>(out.data() + base + chunk * kk);
+    __half* lo = hi + (size_t)N * 16;
+    for (int kg = 0; kg < 2; ++kg)
+      for (int r = 0; r < N; ++r)
+        for (int e = 0; e < 8; ++e) {
+          const int k = kk * 16 + kg * 8 + e;
+          const float w = k < K_in ? W[(size_t)r * K_in + k] : 0.f;
+          const __half h = __float2half_rn(w);
+          hi[((size_t)kg * N + r) * 8 + e] = h;
+          if (split) lo[((size_t)kg * N + r) * 8 + e] = __float2half_rn(w - __half2float(h));
+        }
+  }
+}
+
+extern "C" {
+
+int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
+  if (!out) return ngf_set_error(NGF_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (!d) return ngf_set_error(NGF_EINVAL, "desc is NULL");
+  if (d->sample_num != kS) return ngf_set_error(NGF_EUNSUPPORTED, "sample_num=%d (kernels are built for %d)", d->sample_num, kS);
+  int rc;
+  for (int i = 0; i < 12; ++i) {
+    const int in_dim = i == 0 ? 63 : 256, out_dim = i == 11 ? 1 : 256;
+    if ((rc = check_lin(d->geometry[i], in_dim, out_dim, "geometry", i))) return rc;
+  }
+  const int gi[5] = {63, 64, 128, 128, 128}, go[5] = {64, 128, 128, 128, 2};
+  for (int i = 0; i < 5; ++i)
+    if ((rc = check_lin(d->gauge[i], gi[i], go[i], "gauge", i))) return rc;
+  for (int i = 0; i < 6; ++i)
+    if ((rc = check_lin(d->tex_block1[i], i == 0 ? 42 : 256, 256, "tex_block1", i))) return rc;
+  if ((rc = check_lin(d->tex_color1, 256, 3, "tex_color1", 0))) return rc;
+  for (int i = 0; i < 5; ++i)
+    if ((rc = check_lin(d->tex_block2[i], i == 0 ? 295 : 256, i == 4 ? 3 : 256, "tex_block2", i))) return rc;
+  if (d->texture && (d->tex_h < 1 || d->tex_w < 1 || d->tex_c < 1)) return ngf_set_error(NGF_EINVAL, "bad texture shape");
+  int ndev = 0;
+  CUN(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return ngf_set_error(NGF_EINVAL, "device %d out of range (%d visible)", device, ndev);
+  Guard g(device);
+  int major = 0;
+  CUN(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) return ngf_set_error(NGF_EUNSUPPORTED, "device %d has compute capability %d.x; sm_100a only", device, major);
+
+  NgfNeutex_* h = new NgfNeutex_();
+  h->device = device;
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+
+  std::vector<uint8_t> wp;
+  std::vector<float> bias, heads(kHeadFloats, 0.f), W, B;
+  int li = 0;
+  auto add = [&](const NgfLinear& l, int K, int Kext, bool split) -> int {
+    if (fetch(W, l.w, (size_t)l.out_dim * l.in_dim) != cudaSuccess || fetch(B, l.b, l.out_dim) != cudaSuccess)
+      return ngf_set_error(NGF_ECUDA, "cannot read layer %d parameters: %s", li, cudaGetErrorString(cudaGetLastError()));
+    LayerDesc& L = h->net.layer[li++];
+    L.K = K; L.Kext = Kext; L.N = l.out_dim; L.split = split ? 1 : 0;
+    L.w_off = (uint32_t)wp.size();
+    L.chunk_bytes = (uint32_t)l.out_dim * 32u * (split ? 2u : 1u);
+    L.b_off = (uint32_t)bias.size();
+    pack_layer(wp, W, l.out_dim, l.in_dim, K + Kext, split);
+    bias.insert(bias.end(), B.begin(), B.end());
+    return NGF_OK;
+  };
+  auto head = [&](const NgfLinear& l, int w_off, int b_off) -> int {
+    if (fetch(W, l.w, (size_t)l.out_dim * l.in_dim) != cudaSuccess || fetch(B, l.b, l.out_dim) != cudaSuccess)
+      return ngf_set_error(NGF_ECUDA, "cannot read head parameters: %s", cudaGetErrorString(cudaGetLastError()));
+    memcpy(heads.data() + w_off, W.data(), W.size() * sizeof(float));
+    memcpy(heads.data() + b_off, B.data(), B.size() * sizeof(float));
+    return NGF_OK;
+  };
+  rc = NGF_OK;
+  for (int i = 0; i < 11 && !rc; ++i) rc = add(d->geometry[i], i == 0 ? 64 : 256, 0, false);
+  if (!rc) rc = head(d->geometry[11], kHeadGeo, kHeadGeoB);
+  for (int i = 0; i < 4 && !rc; ++i) rc = add(d->gauge[i], i < 2 ? 64 : 128, 0, true);
+  if (!rc) rc = head(d->gauge[4], kHeadGauge, kHeadGaugeB);
+  for (int i = 0; i < 6 && !rc; ++i) rc = add(d->tex_block1[i], i == 0 ? 48 : 256, 0, false);
+  if (!rc) rc = head(d->tex_color1, kHeadC1, kHeadC1B);
+  for (int i = 0; i < 4 && !rc; ++i) rc = add(d->tex_block2[i], 256, i == 0 ? 48 : 0, false);
+  if (!rc) rc = head(d->tex_block2[4], kHeadB2, kHeadB2B);
+  if (rc) { ntx_free_all(h); delete h; return rc; }
+
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->wpack), wp.size());
+  if (e == cudaSuccess) e = cudaMemcpy(h->wpack, wp.data(), wp.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->bias), bias.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(h->bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->heads), heads.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(h->heads, heads.data(), heads.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->counters), 64);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->cam_bg), 6 * sizeof(float));
+  if (e == cudaSuccess && d->texture) {
+    const size_t n = (size_t)d->tex_h * d->tex_w * d->tex_c;
+    e = cudaMalloc(reinterpret_cast<void**>(&h->texture), n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(h->texture, d->texture, n * sizeof(float), cudaMemcpyDefault);
+  }
+  if (e != cudaSuccess) {
+    ntx_free_all(h); delete h;
+    return ngf_set_error(NGF_ECUDA, "ngf_neutex_pack: %s", cudaGetErrorString(e));
+  }
+  h->net.wpack = h->wpack; h->net.bias = h->bias; h->net.heads = h->heads;
+  h->net.texture = h->texture; h->net.tex_h = d->tex_h; h->net.tex_w = d->tex_w; h->net.tex_c = d->tex_c;
+  h->net.jitter = d->jitter;
+  *out = h;
+  return NGF_OK;
+}
+
+void ngf_neutex_free(NgfNeutex h) {
+  if (!h) return;
+  Guard g(h->device);
+  cudaDeviceSynchronize();
+  ntx_free_all(h);
+  delete h;
+}
+
+static int ntx_ensure_ws(NgfNeutex_* h, long long n_rays, cudaStream_t st) {
+  if (h->cap_rays >= n_rays) return NGF_OK;
+  CUN(cudaStreamSynchronize(st));
+  ntx_free_ws(h);
+  const size_t n = (size_t)n_rays * kS;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->work), n * sizeof(float4));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->sample_out), n * sizeof(float4));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->valid_mask), (size_t)n_rays * sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    ntx_free_ws(h);
+    return ngf_set_error(NGF_ENOMEM, "NeuTex workspace for %lld rays: %s", n_rays, cudaGetErrorString(e));
+  }
+  h->cap_rays = n_rays;
+  return NGF_OK;
+}
+
+// rays per internal batch: 2 x 16 B x 64 per ray of workspace -> 1 Mi rays = 2 GiB
+static const long long kNtxBatch = 1ll << 20;
+
+static int ntx_render_dev(NgfNeutex_* h, const float* campos, const float* raydir, const float* background,
+                          const float* noise, long long n_rays, float* color, float* trans, cudaStream_t st) {
+  const long long per = n_rays < kNtxBatch ? n_rays : kNtxBatch;
+  int rc = ntx_ensure_ws(h, per, st);
+  if (rc) return rc;
+  for (long long s0 = 0; s0 < n_rays; s0 += per) {
+    const long long n = (n_rays - s0) < per ? (n_rays - s0) : per;
+    RenderArgsN a{};
+    a.campos = campos; a.raydir = raydir + s0 * 3; a.background = background;
+    a.noise = noise ? noise + s0 * kS : nullptr;
+    a.n_rays = n;
+    a.work = h->work; a.counters = h->counters; a.valid_mask = h->valid_mask; a.sample_out = h->sample_out;
+    a.color = color + s0 * 3; a.transmittance = trans + s0;
+    CUN(cudaMemsetAsync(h->counters, 0, 8, st));
+    const bool timed = h->ev_used + 4 <= (int)h->ev.size();
+    if (timed) CUN(cudaEventRecord(h->ev[h->ev_used], st));
+    CUN(launch_neutex_raygen(h->net, a, st));
+    if (timed) CUN(cudaEventRecord(h->ev[h->ev_used + 1], st));
+    CUN(launch_neutex_mlp(h->net, a, h->num_sms, st));
+    if (timed) CUN(cudaEventRecord(h->ev[h->ev_used + 2], st));
+    CUN(launch_neutex_march(h->net, a, st));
+    if (timed) {
+      CUN(cudaEventRecord(h->ev[h->ev_used + 3], st));
+      h->ev_used += 4;
+    }
+  }
+  return NGF_OK;
+}
+
+int ngf_neutex_render(NgfNeutex h, const float* campos_dev, const float* raydir_dev, const float* background_dev,
+                      const float* noise_dev, int64_t n_rays, float* color_dev, float* transmittance_dev, void* stream) {
+  if (!h) return ngf_set_error(NGF_EINVAL, "handle is NULL");
+  if (n_rays < 0 || n_rays > (1ll << 31) / kS * 16) return ngf_set_error(NGF_EINVAL, "n_rays=%lld", (long long)n_rays);
+  if (n_rays == 0) return NGF_OK;
+  if (!campos_dev || !raydir_dev || !color_dev || !transmittance_dev) return ngf_set_error(NGF_EINVAL, "NULL pointer");
+  Guard g(h->device);
+  return ntx_render_dev(h, campos_dev, raydir_dev, background_dev, noise_dev, n_rays, color_dev, transmittance_dev,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ngf_neutex_render_host(NgfNeutex h, const float* campos_host, const float* raydir_host, const float* background_host,
+                           const float* noise_host, int64_t n_rays, float* color_host, float* transmittance_host) {
+  if (!h) return ngf_set_error(NGF_EINVAL, "handle is NULL");
+  if (n_rays < 0) return ngf_set_error(NGF_EINVAL, "n_rays=%lld", (long long)n_rays);
+  if (n_rays == 0) return NGF_OK;
+  if (!campos_host || !raydir_host || !color_host || !transmittance_host) return ngf_set_error(NGF_EINVAL, "NULL pointer");
+  Guard g(h->device);
+  const long long chunk = n_rays < 65536 ? n_rays : 65536;
+  if (h->chunk_cap < chunk) {
+    ntx_free_chunks(h);
+    for (auto& c : h->chunk) {
+      CUN(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+      CUN(cudaMalloc(reinterpret_cast<void**>(&c.raydir), (size_t)chunk * 3 * sizeof(float)));
+      CUN(cudaMalloc(reinterpret_cast<void**>(&c.noise), (size_t)chunk * kS * sizeof(float)));
+      CUN(cudaMalloc(reinterpret_cast<void**>(&c.color), (size_t)chunk * 3 * sizeof(float)));
+      CUN(cudaMalloc(reinterpret_cast<void**>(&c.trans), (size_t)chunk * sizeof(float)));
+    }
+    h->chunk_cap = chunk;
+  }
+  float cb[6] = {campos_host[0], campos_host[1], campos_host[2], 0.f, 0.f, 0.f};
+  if (background_host) { cb[3] = background_host[0]; cb[4] = background_host[1]; cb[5] = background_host[2]; }
+  CUN(cudaMemcpy(h->cam_bg, cb, sizeof(cb), cudaMemcpyHostToDevice));
+  // the MLP workspace is shared, so chunks run back to back on one stream; copies of chunk i+1 overlap on the other
+  cudaStream_t run = h->chunk[0].stream, copy = h->chunk[1].stream;
+  cudaEvent_t up[2], done[2];
+  for (int i = 0; i < 2; ++i) { CUN(cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming)); CUN(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming)); }
+  int rc = NGF_OK, ci = 0;
+  for (long long s = 0; s < n_rays && rc == NGF_OK; s += chunk, ci ^= 1) {
+    const long long n = (n_rays - s) < chunk ? (n_rays - s) : chunk;
+    NtxChunk& c = h->chunk[ci];
+    cudaStreamWaitEvent(copy, done[ci], 0);               // buffers of this slot free again
+    cudaMemcpyAsync(c.raydir, raydir_host + s * 3, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, copy);
+    if (noise_host) cudaMemcpyAsync(c.noise, noise_host + s * kS, (size_t)n * kS * sizeof(float), cudaMemcpyHostToDevice, copy);
+    cudaEventRecord(up[ci], copy);
+    cudaStreamWaitEvent(run, up[ci], 0);
+    rc = ntx_render_dev(h, h->cam_bg, c.raydir, background_host ? h->cam_bg + 3 : nullptr, noise_host ? c.noise : nullptr, n,
+                        c.color, c.trans, run);
+    cudaMemcpyAsync(color_host + s * 3, c.color, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, run);
+    cudaMemcpyAsync(transmittance_host + s, c.trans, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, run);
+    cudaEventRecord(done[ci], run);
+  }
+  cudaError_t e1 = cudaStreamSynchronize(run), e2 = cudaStreamSynchronize(copy);
+  for (int i = 0; i < 2; ++i) { cudaEventDestroy(up[i]); cudaEventDestroy(done[i]); }
+  if (rc) return rc;
+  CUN(e1);
+  CUN(e2);
+  return NGF_OK;
+}
+
+int ngf_neutex_last_valid_samples(NgfNeutex h, uint64_t* n_valid, void* stream) {
+  if (!h || !n_valid) return ngf_set_error(NGF_EINVAL, "NULL argument");
+  Guard g(h->device);
+  unsigned int c = 0;
+  CUN(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+  CUN(cudaMemcpy(&c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
+  *n_valid = c;
+  return NGF_OK;
+}
+
+int ngf_neutex_copy_samples(NgfNeutex h, int64_t first_sample, int64_t n, float* sigma_rgb_host, uint64_t* valid_mask_host,
+                            int64_t first_ray, int64_t n_mask_rays) {
+  if (!h) return ngf_set_error(NGF_EINVAL, "handle is NULL");
+  Guard g(h->device);
+  CUN(cudaDeviceSynchronize());
+  if (first_sample < 0 || n < 0 || first_sample + n > h->cap_rays * kS || first_ray < 0 || n_mask_rays < 0 ||
+      first_ray + n_mask_rays > h->cap_rays)
+    return ngf_set_error(NGF_EINVAL, "range outside the last render's workspace");
+  if (sigma_rgb_host && n) CUN(cudaMemcpy(sigma_rgb_host, h->sample_out + first_sample, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
+  if (valid_mask_host && n_mask_rays)
+    CUN(cudaMemcpy(valid_mask_host, h->valid_mask + first_ray, (size_t)n_mask_rays * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return NGF_OK;
+}
+
+int ngf_neutex_timing_begin(NgfNeutex h, int32_t capacity) {
+  if (!h) return ngf_set_error(NGF_EINVAL, "handle is NULL");
+  if (capacity < 0 || capacity > 65536) return ngf_set_error(NGF_EINVAL, "capacity=%d", capacity);
+  Guard g(h->device);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  h->ev.assign((size_t)capacity * 4, nullptr);
+  h->ev_used = 0;
+  for (auto& e : h->ev) CUN(cudaEventCreate(&e));
+  return NGF_OK;
+}
+
+int ngf_neutex_timing_read(NgfNeutex h, int32_t* n_renders, double* raygen_ms, double* mlp_ms, double* march_ms) {
+  if (!h || !n_renders || !raygen_ms || !mlp_ms || !march_ms) return ngf_set_error(NGF_EINVAL, "NULL argument");
+  Guard g(h->device);
+  double s[3] = {0, 0, 0};
+  for (int i = 0; i + 3 < h->ev_used; i += 4) {
+    CUN(cudaEventSynchronize(h->ev[i + 3]));
+    for (int k = 0; k < 3; ++k) {
+      float ms = 0.f;
+      CUN(cudaEventElapsedTime(&ms, h->ev[i + k], h->ev[i + k + 1]));
+      s[k] += ms;
+    }
+  }
+  *n_renders = h->ev_used / 4;
+  *raygen_ms = s[0]; *mlp_ms = s[1]; *march_ms = s[2];
+  h->ev_used = 0;
+  return NGF_OK;
+}
+
+}  // extern "C"

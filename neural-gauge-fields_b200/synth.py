@@ -203,3 +203,81 @@ def load_into(field, state: Dict[str, torch.Tensor], occupancy: torch.Tensor | N
         dev = field.device
         field.alphaMask = mask_cls(dev, field.aabb.to(dev), occupancy.to(dev))
     return field
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# UV-Mapping (NeuTex) synthetic inputs — BASELINE configs[3]
+# ---------------------------------------------------------------------------------------------------------------
+NEUTEX_H, NEUTEX_W = 600, 800                 # DTU test render, UV-Mapping/data/dtu.py (no_crop)
+NEUTEX_FOCAL = (1446.2, 1441.6)               # scan83 intrinsics (in_camFocal.npy / in_camPrincpt.npy, rounded)
+NEUTEX_PRINCPT = (411.6, 309.5)
+NEUTEX_SAMPLES = 64                           # dtu_test.sh: --sample_num 64
+
+# layer shapes (out, in) in the reference's module order
+NEUTEX_LAYERS = {
+    "net_geometry_decoder.block": [(256, 63)] + [(256, 256)] * 10 + [(1, 256)],          # decoder.py:201-217
+    "net_texture.block1": [(256, 42)] + [(256, 256)] * 5,                                # decoder.py:20-26
+    "net_texture.block2": [(256, 295)] + [(256, 256)] * 3 + [(3, 256)],                  # decoder.py:29-36
+}
+
+
+def neutex_state(seed: int = 0, gain: float = 1.0) -> Dict[str, torch.Tensor]:
+    """state_dict (reference NeuTex parameter names, primitive_type='square') with xavier-uniform weights like the
+    reference's init_seq / init_weights (util.py:390-425) and small random biases."""
+    g = torch.Generator().manual_seed(seed)
+    st: Dict[str, torch.Tensor] = {}
+
+    def lin(name, o, i, act_gain):
+        bound = gain * act_gain * math.sqrt(6.0 / (i + o))
+        st[name + ".weight"] = (torch.rand((o, i), generator=g) * 2 - 1) * bound
+        st[name + ".bias"] = (torch.rand((o,), generator=g) * 2 - 1) * 0.05
+
+    relu, leaky = math.sqrt(2.0), math.sqrt(2.0 / (1 + 0.2 ** 2))
+    for prefix, shapes in NEUTEX_LAYERS.items():
+        ag = relu if "geometry" in prefix else leaky
+        for n, (o, i) in enumerate(shapes):
+            lin(f"{prefix}.{2 * n}", o, i, ag if o > 3 else 1.0)
+    lin("net_texture.color1", 3, 256, 1.0)
+    enc = "gauge_transform.encoder"
+    lin(f"{enc}.linear1", 64, 63, 1.0)
+    lin(f"{enc}.linear2", 128, 64, 1.0)
+    lin(f"{enc}.linear_list.0", 128, 128, 1.0)
+    lin(f"{enc}.linear_list.1", 128, 128, 1.0)
+    lin(f"{enc}.last_linear", 2, 128, 1.0)
+    # a denser object in the middle of the cube so rays see structure: bias the density head
+    st["net_geometry_decoder.block.22.bias"] = torch.tensor([1.5])
+    return {k: v.float().contiguous() for k, v in st.items()}
+
+
+def neutex_camera(pose: int = 0, H: int = NEUTEX_H, W: int = NEUTEX_W, radius: float = 2.6, max_rays: int = 0):
+    """-> campos [1,3], raydir [1,R,3] (unit), like DtuDataset.get_item (data/dtu.py:119-182): pixel-centre rays
+    through a pinhole with the scan83 intrinsics, camera on a sphere looking at the unit cube."""
+    az, el = pose_angles(pose, seed=3)
+    c2w = look_at_c2w(az, el, radius)
+    j, i = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    fx, fy = NEUTEX_FOCAL[0] * W / NEUTEX_W, NEUTEX_FOCAL[1] * H / NEUTEX_H
+    # keep the object framed whatever the crop: principal point scaled with the image
+    cx, cy = NEUTEX_PRINCPT[0] * W / NEUTEX_W, NEUTEX_PRINCPT[1] * H / NEUTEX_H
+    d = torch.stack([(i + 0.5 - cx) / fx * 3.0, (j + 0.5 - cy) / fy * 3.0, torch.ones_like(i)], -1)   # x3: wider view
+    d = d @ c2w[:, :3].T
+    d = d / (d.norm(dim=-1, keepdim=True) + 1e-5)                                                       # dtu.py:35
+    d = d.reshape(1, -1, 3)
+    if max_rays and d.shape[1] > max_rays:
+        d = d[:, :: d.shape[1] // max_rays][:, :max_rays]
+    return c2w[:, 3].reshape(1, 3).contiguous(), d.contiguous()
+
+
+def neutex_noise(n_rays: int, samples: int = NEUTEX_SAMPLES, seed: int = 11) -> torch.Tensor:
+    """The U[0,1) jitter tensor cube_ray_generation draws with torch.rand (renderer.py:113-118), made explicit so
+    both implementations consume the same numbers."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand((1, n_rays, samples), generator=g)
+
+
+def neutex_texture(h: int = 96, w: int = 128, channels: int = 3, seed: int = 5) -> torch.Tensor:
+    """A synthetic edited texture [h, w, channels] in [0,1] (stands in for UV-Mapping/data/texture*.png after
+    load_square: flipped vertically, /255; util.py:270-274)."""
+    g = torch.Generator().manual_seed(seed)
+    v, u = torch.meshgrid(torch.linspace(0, 1, h), torch.linspace(0, 1, w), indexing="ij")
+    base = torch.stack([0.5 + 0.5 * torch.sin(12 * u + 3 * c) * torch.cos(9 * v - c) for c in range(channels)], -1)
+    return (0.8 * base + 0.2 * torch.rand((h, w, channels), generator=g)).clamp(0, 1).float().contiguous()

@@ -114,7 +114,9 @@ def fingerprint(state, rays, occ) -> str:
         h.update(np.ascontiguousarray(state[k].numpy()).tobytes())
     h.update(np.ascontiguousarray(rays.numpy()).tobytes())
     if occ is not None:
-        h.update(np.packbits(occ.numpy() > 0).tobytes())
+        # {0,1} occupancy volumes hash as bits (the same digest as before); other tensors (textures) as raw bytes
+        binary = bool(((occ == 0) | (occ == 1)).all())
+        h.update(np.packbits(occ.numpy() > 0).tobytes() if binary else np.ascontiguousarray(occ.numpy()).tobytes())
     return h.hexdigest()
 
 
@@ -133,3 +135,43 @@ def pointwise_inputs(n: int = 2048, seed: int = 7):
     lattice = torch.linspace(-1.5, 1.5, 256)
     world[:64] = lattice[torch.randint(0, 256, (64, 3), generator=g)]                      # exact voxel centres
     return xyz.contiguous(), dirs.contiguous(), world.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# UV-Mapping (NeuTex) cases
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class NeutexCase:
+    name: str
+    pose: int = 0
+    max_rays: int = 2048
+    background: Optional[Tuple[float, float, float]] = (1.0, 1.0, 1.0)
+    texture_channels: int = 0            # 0: learned texture; 3 / 4: synthetic edited texture (target_texture branch)
+    seed: int = 0
+    gain: float = 1.0
+    noise_seed: int = 11
+
+
+NEUTEX_CASES = [
+    NeutexCase("neutex_white"),
+    NeutexCase("neutex_black", pose=5, background=(0.0, 0.0, 0.0), seed=2, max_rays=1024),
+    NeutexCase("neutex_nobg", pose=9, background=None, max_rays=777, noise_seed=4),
+    NeutexCase("neutex_texture_rgb", pose=3, texture_channels=3, max_rays=1024),
+    NeutexCase("neutex_texture_rgba", pose=7, texture_channels=4, max_rays=1024, background=(0.2, 0.4, 0.6)),
+]
+NEUTEX_BY_NAME = {c.name: c for c in NEUTEX_CASES}
+
+
+@functools.lru_cache(maxsize=4)
+def _neutex_state(seed, gain):
+    return synth.neutex_state(seed, gain)
+
+
+def build_neutex_inputs(case: NeutexCase):
+    """-> (state_dict, texture or None, campos [1,3], raydir [1,R,3], background [1,3] or None, noise [1,R,64])."""
+    state = _neutex_state(case.seed, case.gain)
+    tex = synth.neutex_texture(channels=case.texture_channels) if case.texture_channels else None
+    campos, raydir = synth.neutex_camera(case.pose, max_rays=case.max_rays)
+    bg = None if case.background is None else torch.tensor([case.background], dtype=torch.float32)
+    noise = synth.neutex_noise(raydir.shape[1], seed=case.noise_seed)
+    return state, tex, campos, raydir, bg, noise

@@ -88,12 +88,65 @@ def make_pointwise(variant: str) -> str:
     return path
 
 
+def build_reference_neutex(case: K.NeutexCase):
+    """The reference's UV-Mapping sub-modules (decoder.py, gauge_fields.py) with the synthetic state loaded.
+    NeuTex.forward itself cannot run as shipped, so the modules are wired exactly as
+    model/model.py:30-50 does, minus the loss-only inverse-gauge lines."""
+    pkg = ref_loader.uvmapping_model()
+    state, tex, campos, raydir, bg, noise = K.build_neutex_inputs(case)
+    geo = ref_loader.quiet(pkg.decoder.GeometryMlpDecoder, pos_freqs=10, hidden_size=256, num_layers=10)
+    gt = pkg.gauge_fields.GaugeTransform("square")
+    texnet = ref_loader.quiet(pkg.decoder.TextureMlpDecoder, 3, 10, 6, uv_dim=2, layers=[5, 3], width=256, clamp=False,
+                              primitive_type="square", target_texture="None")
+    for mod, prefix in ((geo, "net_geometry_decoder"), (gt, "gauge_transform"), (texnet, "net_texture")):
+        mod.load_state_dict({k[len(prefix) + 1:]: v for k, v in state.items() if k.startswith(prefix + ".")}, strict=True)
+    if tex is not None:
+        texnet.cubemap_ = tex.clone()                       # what __init__ does with load_square(target_texture)
+    return pkg, geo, gt, texnet, (state, tex, campos, raydir, bg, noise)
+
+
+@torch.no_grad()
+def make_neutex(case: K.NeutexCase) -> str:
+    pkg, geo, gt, texnet, (state, tex, campos, raydir, bg, noise) = build_reference_neutex(case)
+    ren = pkg.renderer
+    cols, trs, dens, uvs = [], [], [], []
+    for s in range(0, raydir.shape[1], 1024):               # test.py:108-114 chunking
+        rd, nz = raydir[:, s:s + 1024], noise[:, s:s + 1024]
+        # cube_ray_generation draws its jitter with torch.rand((N, R, S)); feed it the case's numbers
+        real_rand = torch.rand
+        torch.rand = lambda *a, **k: nz.clone()
+        try:
+            pos, seg, valid, _ = ren.cube_ray_generation(campos, rd, 64, jitter=0.05)
+        finally:
+            torch.rand = real_rand
+        density = geo(pos)["density"][..., None]
+        uv = gt(pos)
+        feat = texnet(uv, rd[:, :, None, :])
+        bsdf = torch.cat([density, feat[..., :3]], dim=-1)
+        out = ren.ray_march(rd, pos, seg, valid, bsdf, None, None, ren.radiance_render, ren.alpha_blend)
+        color, bg_w = out[0], out[6]
+        if bg is not None:
+            color = color + bg[:, None, :] * bg_w[:, :, None]
+        cols.append(ren.simple_tone_map(color))
+        trs.append(bg_w)
+        dens.append(density[..., 0])
+        uvs.append(uv)
+    path = K.golden_path(case.name)
+    np.savez_compressed(path, color=torch.cat(cols, 1).numpy(), transmittance=torch.cat(trs, 1).numpy(),
+                        density_head=torch.cat(dens, 1)[0, :8].numpy(), uv_head=torch.cat(uvs, 1)[0, :8].numpy(),
+                        fingerprint=K.fingerprint(state, torch.cat([raydir[0], noise[0]], 1), tex),
+                        torch_version=torch.__version__)
+    return path
+
+
 def main(argv):
     if not ref_loader.available():
         raise SystemExit("reference tree not found: golden vectors can only be generated in the build container")
-    names = argv or [c.name for c in K.CASES] + ["pointwise_triplane", "pointwise_infoinv"]
+    names = argv or [c.name for c in K.CASES] + ["pointwise_triplane", "pointwise_infoinv"] + [c.name for c in K.NEUTEX_CASES]
     for n in names:
-        if n.startswith("pointwise_"):
+        if n in K.NEUTEX_BY_NAME:
+            p = make_neutex(K.NEUTEX_BY_NAME[n])
+        elif n.startswith("pointwise_"):
             p = make_pointwise(n.split("_", 1)[1])
         else:
             p = make_case(K.CASE_BY_NAME[n])
