@@ -376,8 +376,10 @@ static int pack_params(NgfField_* h, const NgfFieldDesc* d, bool allocate) {
       for (int k = 0; k < 64; ++k) put_kmajor(w2p, 64, j, k, W2[(size_t)j * 64 + k]);
     }
     std::vector<float> tail(kTailFloats, 0.f);
-    memcpy(tail.data(), W3.data(), 192 * 4);
-    memcpy(tail.data() + 192, b2.data(), 64 * 4);
+    for (int c = 0; c < 64; ++c) {          // one float4 per hidden unit: (b2, w3[0], w3[1], w3[2])
+      tail[4 * c] = b2[c];
+      for (int o = 0; o < 3; ++o) tail[4 * c + 1 + o] = W3[(size_t)o * 64 + c];
+    }
     memcpy(tail.data() + 256, b3.data(), 3 * 4);
     if (allocate) {
       CU(dev_alloc(&h->w1p, w1p.size()));

@@ -60,7 +60,7 @@ struct FieldDev {
   float db;
   // InfoInv density MLP 72->32->32->1, fp32: [w1t 72x32 (input-major)][b1 32][w2 32x32][b2 32][w3 32][b3 1]
   const float* dmlp;
-  // colour MLP, packed: w1p/w2p fp16 in tcgen05 K-major core-matrix order, tail fp32 [w3 3x64][b2 64][b3 3][pad]
+  // colour MLP, packed: w1p/w2p fp16 in tcgen05 K-major core-matrix order, tail fp32 [64 x (b2, w3_r, w3_g, w3_b)][b3 3][pad]
   const __half* w1p;
   const __half* w2p;
   const float* tail;

@@ -91,8 +91,9 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread t of the warp = lane base + t)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread t of the warp = lane base + t).
+// tmem_ld32_issue + tmem_ld_wait let several loads be in flight before the wait.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float v[32]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -104,7 +105,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+  tmem_ld32_issue(taddr, v);
+  tmem_ld_wait();
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -116,7 +121,10 @@ struct MlpSmem {
   static constexpr int NKC = K1 / 8;                       // 8-wide K chunks in layer 1
   static constexpr uint32_t kW1Bytes = NKC * kMid * 16;    // 20480 | 30720
   static constexpr uint32_t kW2Bytes = (kMid / 8) * kMid * 16;     // 8192
-  static constexpr uint32_t kABytes = NKC * kTileM * 16;   // 40960 | 61440
+  // K-group stride (LBO) of the layer-1 A operand: one 16-byte slot of padding per group rotates the shared-memory
+  // banks so that the six lanes that write the six K groups of one row do not collide
+  static constexpr uint32_t kLboA = kTileM * 16 + 16;
+  static constexpr uint32_t kABytes = NKC * kLboA;         // 41280 | 61920
   static constexpr uint32_t kHBytes = (kMid / 8) * kTileM * 16;    // 16384
   // InfoInv aliases the hidden tile onto the (dead by then) A tile to stay within two CTAs per SM.
   static constexpr bool kAliasH = (V == 1);
@@ -187,7 +195,34 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// Blend 8 fp16 channels from 4 taps in fp32 and return them packed as 8 halves.
+// Blend 8 fp16 channels from 4 taps with packed half2 FMAs (texels are stored in fp16 and the result is an fp16 MMA
+// operand anyway; the fp16 accumulation adds about one more rounding of 2^-11 relative to the fp32 blend).
+struct __align__(16) TapsH {
+  int off[4];
+  __half2 w[4];
+};
+__device__ __forceinline__ TapsH to_half_taps(const Taps& t) {
+  TapsH h;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { h.off[k] = t.off[k]; h.w[k] = __float2half2_rn(t.w[k]); }
+  return h;
+}
+__device__ __forceinline__ uint4 blend8h(const __half* __restrict__ base, int chan_off, int AC, const TapsH& t) {
+  __half2 acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + (size_t)t.off[k] * AC + chan_off));
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] = k == 0 ? __hmul2(t.w[0], h[e]) : __hfma2(t.w[k], h[e], acc[e]);
+  }
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&acc[0]); o.y = *reinterpret_cast<uint32_t*>(&acc[1]);
+  o.z = *reinterpret_cast<uint32_t*>(&acc[2]); o.w = *reinterpret_cast<uint32_t*>(&acc[3]);
+  return o;
+}
+
+// fp32 variant (InfoInv multiplies the blended feature by the phase code before rounding)
 __device__ __forceinline__ void blend8(const __half* __restrict__ base, int chan_off, int AC, const Taps& t,
                                        float out[8]) {
 #pragma unroll
@@ -218,20 +253,27 @@ __device__ __forceinline__ void mlp_gather(const FieldDev& f, uint8_t* smem, uin
   uint8_t* A = smem + L::offA;
   const int tid = threadIdx.x;
   if (V == 0) {
-    // items (row m, plane, half): 3 chunks of 8 channels each; lanes of a warp = consecutive rows
-    for (int it = tid; it < kTileM * 6; it += kThreads) {
-      const int m = it & (kTileM - 1), ph = it >> 7, pl = ph >> 1, half = ph & 1;
+    // Phase 1: bilinear tap sets of the 128 x 3 (row, plane) pairs -> shared memory (aliases the layer-2 operand, which is
+    // only written after this tile's layer-1 MMA).
+    TapsH* tapbuf = reinterpret_cast<TapsH*>(smem + L::offH);
+    for (int it = tid; it < kTileM * 3; it += kThreads) {
+      const int m = it & (kTileM - 1), pl = it >> 7;
       const QEntry& e = q[(head + m) & (kQueueCap - 1)];
       const PlaneDev& P = f.plane[pl];
-      Taps t = make_taps(e.c[2 * pl], e.c[2 * pl + 1], P.W, P.H, P.wm1, P.hm1);
+      tapbuf[it] = to_half_taps(make_taps(e.c[2 * pl], e.c[2 * pl + 1], P.W, P.H, P.wm1, P.hm1));
+    }
+    __syncthreads();
+    // Phase 2: consecutive lanes take consecutive 16-byte chunks of the SAME texel (6 chunks = 96 contiguous bytes per
+    // tap), so a warp-wide load touches ~8 cache lines instead of 32.
 #pragma unroll
-      for (int cg = 0; cg < 3; ++cg) {
-        float v[8];
-        const int chunk = half * 3 + cg;
-        blend8(P.app, chunk * 8, AC, t, v);
-        uint4 o = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
-                             pack_half2(v[6], v[7]));
-        *reinterpret_cast<uint4*>(A + (size_t)(pl * 6 + chunk) * (kTileM * 16) + m * 16) = o;
+    for (int pl = 0; pl < 3; ++pl) {
+      const PlaneDev& P = f.plane[pl];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int it = tid + kThreads * j;                 // < 768 = 128 rows x 6 chunks
+        const int chunk = it % 6, m = it / 6;
+        const TapsH t = tapbuf[pl * kTileM + m];
+        *reinterpret_cast<uint4*>(A + (size_t)(pl * 6 + chunk) * L::kLboA + m * 16) = blend8h(P.app, chunk * 8, AC, t);
       }
     }
   } else {
@@ -253,7 +295,7 @@ __device__ __forceinline__ void mlp_gather(const FieldDev& f, uint8_t* smem, uin
         for (int k = 0; k < 8; ++k) v[k] *= pe[k];
         uint4 o = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
                              pack_half2(v[6], v[7]));
-        *reinterpret_cast<uint4*>(A + (size_t)(pl * 9 + chunk) * (kTileM * 16) + m * 16) = o;
+        *reinterpret_cast<uint4*>(A + (size_t)(pl * 9 + chunk) * L::kLboA + m * 16) = o;
       }
     }
   }
@@ -269,8 +311,13 @@ __device__ __forceinline__ void mlp_gather(const FieldDev& f, uint8_t* smem, uin
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         float a1 = d[k], a2 = d[k] * 2.f;
-        v[3 + 2 * k] = sinf(a1); v[4 + 2 * k] = sinf(a2);
-        v[9 + 2 * k] = cosf(a1); v[10 + 2 * k] = cosf(a2);
+        if (fabsf(a1) <= 4.f) {   // unit view directions: the fast intrinsics err by ~4e-7 there (far below fp16 rounding)
+          v[3 + 2 * k] = __sinf(a1); v[4 + 2 * k] = __sinf(a2);
+          v[9 + 2 * k] = __cosf(a1); v[10 + 2 * k] = __cosf(a2);
+        } else {
+          v[3 + 2 * k] = sinf(a1); v[4 + 2 * k] = sinf(a2);
+          v[9 + 2 * k] = cosf(a1); v[10 + 2 * k] = cosf(a2);
+        }
       }
       v[15] = 1.f;
     } else {
@@ -281,8 +328,8 @@ __device__ __forceinline__ void mlp_gather(const FieldDev& f, uint8_t* smem, uin
                           pack_half2(v[6], v[7]));
     uint4 o1 = make_uint4(pack_half2(v[8], v[9]), pack_half2(v[10], v[11]), pack_half2(v[12], v[13]),
                           pack_half2(v[14], v[15]));
-    *reinterpret_cast<uint4*>(A + (size_t)(F / 8) * (kTileM * 16) + m * 16) = o0;
-    *reinterpret_cast<uint4*>(A + (size_t)(F / 8 + 1) * (kTileM * 16) + m * 16) = o1;
+    *reinterpret_cast<uint4*>(A + (size_t)(F / 8) * L::kLboA + m * 16) = o0;
+    *reinterpret_cast<uint4*>(A + (size_t)(F / 8 + 1) * L::kLboA + m * 16) = o1;
   }
 }
 
@@ -311,7 +358,7 @@ __device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint3
     fence_async_smem();
     __syncthreads();
     const uint32_t tmem = ctl->tmem_base;
-    constexpr uint32_t lboA = kTileM * 16u, sboA = 128u, lboB = kMid * 16u, sboB = 128u;
+    constexpr uint32_t lboA = L::kLboA, sboA = 128u, lboB = kMid * 16u, sboB = 128u;
     constexpr uint32_t idesc = umma_idesc(kTileM, kMid);
     // ---- layer 1: [128 x K1] x [K1 x 64] -> TMEM columns [0,64)
     if (tid == 0) {
@@ -319,7 +366,7 @@ __device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint3
       const uint32_t a0 = smem_u32(smem + L::offA), b0 = smem_u32(smem + L::offW1);
 #pragma unroll 1
       for (int j = 0; j < NKC / 2; ++j)
-        umma_f16(tmem, umma_desc(a0 + j * 2 * kTileM * 16, lboA, sboA), umma_desc(b0 + j * 2 * kMid * 16, lboB, sboB),
+        umma_f16(tmem, umma_desc(a0 + j * 2 * lboA, lboA, sboA), umma_desc(b0 + j * 2 * kMid * 16, lboB, sboB),
                  idesc, j > 0);
       umma_commit(&ctl->bar);
     }
@@ -335,7 +382,7 @@ __device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint3
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = 0.f;
     for (int kc = 0; kc < NKC; ++kc) {
-      uint4 araw = *reinterpret_cast<const uint4*>(A + (size_t)kc * (kTileM * 16) + row * 16);
+      uint4 araw = *reinterpret_cast<const uint4*>(A + (size_t)kc * L::kLboA + row * 16);
       const __half2* ah = reinterpret_cast<const __half2*>(&araw);
       float a[8];
 #pragma unroll
@@ -412,15 +459,14 @@ __device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint3
   // ---- epilogue 2: + b2, ReLU, layer 3 (64 -> 3) partial sums over this thread's 32 hidden units
   float p0 = 0.f, p1 = 0.f, p2 = 0.f;
   {
-    const float* w3 = tail;                // [3][64]
-    const float* b2 = tail + 192;
+    const float4* t4 = reinterpret_cast<const float4*>(tail);      // per hidden unit: (b2, w3_r, w3_g, w3_b)
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const int col = chalf * 32 + j;
-      float h = fmaxf(acc[j] + b2[col], 0.f);
-      p0 += h * w3[col];
-      p1 += h * w3[64 + col];
-      p2 += h * w3[128 + col];
+      const float4 c = t4[chalf * 32 + j];
+      float h = fmaxf(acc[j] + c.x, 0.f);
+      p0 += h * c.y;
+      p1 += h * c.z;
+      p2 += h * c.w;
     }
   }
   float4* part = reinterpret_cast<float4*>(smem + L::offPart);

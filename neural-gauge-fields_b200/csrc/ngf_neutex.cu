@@ -44,12 +44,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 constexpr uint32_t kKGroupBytes = kRows * 16;            // one 8-wide K group of the 256-row A operand
 constexpr uint32_t offA = 0;                             // [32 K groups][256 rows][8 halves]  (split: lo half at +64 KiB)
 constexpr uint32_t kABytes = 32 * kKGroupBytes;          // 131072
-constexpr uint32_t offA2 = offA + kABytes;               // view-direction operand, K = 48
-constexpr uint32_t kA2Bytes = 6 * kKGroupBytes;          // 24576
+constexpr uint32_t offA2 = offA + kABytes;               // view-direction operand, K = 48: 39 encoding columns, two
+constexpr uint32_t kA2Bytes = 6 * kKGroupBytes;          //   constant-one columns (39, 40) that carry the biases, 7 zeros
 constexpr uint32_t offRing = offA2 + kA2Bytes;
-constexpr uint32_t offBar = offRing + kStages * kStageBytes;
+constexpr uint32_t offHx = offRing + kStages * kStageBytes;   // head partial sums exchanged between a row's two threads
+constexpr uint32_t kHxBytes = 2 * kRows * 16;
+constexpr uint32_t offBar = offHx + kHxBytes;
 constexpr uint32_t kSmemBytes = offBar + 256;
 constexpr uint32_t kALoOff = 16 * kKGroupBytes;          // lo operand of split layers (K <= 128)
+constexpr int kOnesCol = 39;                             // A2 columns 39 and 40 are 1.0
 
 struct Bars {
   uint64_t full[kStages];
@@ -60,82 +63,139 @@ struct Bars {
 };
 
 __device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkerThreads) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------
 // A-operand writers.  Element (row r, column k) lives at (k / 8) * kKGroupBytes + r * 16 + (k % 8) * 2.
 // ---------------------------------------------------------------------------------------------------------
-template <int NG, bool SPLIT>
-__device__ __forceinline__ void store_groups(uint8_t* A, int row, const float* v) {
+template <bool SPLIT>
+__device__ __forceinline__ void store_group(uint8_t* A, int group, int row, const float* v) {
+  uint32_t hi[4], lo[4];
 #pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float a = v[8 * g + 2 * e], b = v[8 * g + 2 * e + 1];
-      __half2 h = __floats2half2_rn(a, b);
-      hi[e] = *reinterpret_cast<uint32_t*>(&h);
-      if (SPLIT) {
-        float2 back = __half22float2(h);
-        __half2 l = __floats2half2_rn(a - back.x, b - back.y);
-        lo[e] = *reinterpret_cast<uint32_t*>(&l);
-      }
+  for (int e = 0; e < 4; ++e) {
+    const float a = v[2 * e], b = v[2 * e + 1];
+    __half2 h = __floats2half2_rn(a, b);
+    hi[e] = *reinterpret_cast<uint32_t*>(&h);
+    if (SPLIT) {
+      float2 back = __half22float2(h);
+      __half2 l = __floats2half2_rn(a - back.x, b - back.y);
+      lo[e] = *reinterpret_cast<uint32_t*>(&l);
     }
-    *reinterpret_cast<uint4*>(A + g * kKGroupBytes + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    if (SPLIT) *reinterpret_cast<uint4*>(A + kALoOff + g * kKGroupBytes + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
+  *reinterpret_cast<uint4*>(A + group * kKGroupBytes + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (SPLIT) *reinterpret_cast<uint4*>(A + kALoOff + group * kKGroupBytes + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-// [x, sin(x_d * 2^f), cos(x_d * 2^f)] with column order of util.py:427-438 (d-major, then f), zero padded to 8*NG
-template <int D, int F, int NG, bool SPLIT>
-__device__ __forceinline__ void write_encoding(uint8_t* A, int row, const float* x) {
-  float v[8 * NG];
+// Encoding [x, sin(x_d * 2^f), cos(x_d * 2^f)] (column order of util.py:427-438: d-major, then f), zero padded to
+// 8*NG columns; with ONES, columns kOnesCol and kOnesCol+1 are 1.0.  The row's two threads each write half of the K
+// groups (CH = 0 / 1).  ACCURATE: every value from sinf / cosf (gauge network, 1e-6 budget); otherwise one sincosf per
+// coordinate and the double-angle recurrence (error grows ~2x per octave to <= 3e-5 at 2^9, far below the fp16
+// rounding of the operand it feeds).
+template <int D, int F, int NG, bool SPLIT, bool ACCURATE, bool ONES, int CH>
+__device__ __forceinline__ void write_encoding_half(uint8_t* A, int row, const float* x) {
+  float sn[D * F], cs[D * F];
+  if (!ACCURATE) {
 #pragma unroll
-  for (int i = 0; i < 8 * NG; ++i) v[i] = 0.f;
-#pragma unroll
-  for (int d = 0; d < D; ++d) {
-    v[d] = x[d];
-#pragma unroll
-    for (int f = 0; f < F; ++f) {
+    for (int d = 0; d < D; ++d) {
       float s, c;
-      sincosf(x[d] * (float)(1 << f), &s, &c);
-      v[D + d * F + f] = s;
-      v[D + D * F + d * F + f] = c;
+      sincosf(x[d], &s, &c);
+      sn[d * F] = s; cs[d * F] = c;
+#pragma unroll
+      for (int f = 1; f < F; ++f) {
+        const float s2 = 2.f * s * c, c2 = 1.f - 2.f * s * s;
+        s = s2; c = c2;
+        sn[d * F + f] = s; cs[d * F + f] = c;
+      }
     }
   }
-  store_groups<NG, SPLIT>(A, row, v);
+  constexpr int G0 = CH * (NG / 2), G1 = G0 + NG / 2;
+#pragma unroll
+  for (int g = G0; g < G1; ++g) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = 8 * g + e;
+      float val = 0.f;
+      if (col < D) val = x[col];
+      else if (col < D + D * F) {
+        const int i = col - D;
+        val = ACCURATE ? sinf(x[i / F] * (float)(1 << (i % F))) : sn[i];
+      } else if (col < D + 2 * D * F) {
+        const int i = col - D - D * F;
+        val = ACCURATE ? cosf(x[i / F] * (float)(1 << (i % F))) : cs[i];
+      } else if (ONES && (col == kOnesCol || col == kOnesCol + 1)) val = 1.f;
+      v[e] = val;
+    }
+    store_group<SPLIT>(A, g, row, v);
+  }
+}
+template <int D, int F, int NG, bool SPLIT, bool ACCURATE, bool ONES>
+__device__ __forceinline__ void write_encoding(uint8_t* A, int row, int ch, const float* x) {
+  if (ch == 0) write_encoding_half<D, F, NG, SPLIT, ACCURATE, ONES, 0>(A, row, x);
+  else write_encoding_half<D, F, NG, SPLIT, ACCURATE, ONES, 1>(A, row, x);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Epilogue of one layer for one row: TMEM -> + bias -> activation -> (fp16 A operand of the next layer) and/or
-// fp32 dot products with up to 3 head weight rows.
+// Epilogue of one layer for one (row, column half): TMEM (bias already accumulated by the bias slice) -> activation ->
+// fp16 A operand of the next layer and/or fp32 partial dot products with up to 3 head weight rows.
+//   MODE 0: activation on packed halves, write   MODE 1: fp32 activation, split hi/lo write   MODE 2: no write
 // ---------------------------------------------------------------------------------------------------------
-template <int N, int ACT, bool WRITE, bool SPLIT, int NH>
-__device__ __forceinline__ void epilogue(uint32_t taddr, const float* __restrict__ bias, uint8_t* A, int row,
-                                         const float* __restrict__ headw, float* hacc) {
+template <int ACT>
+__device__ __forceinline__ uint32_t act_pack(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  if (ACT == 0) h = __hmax2(h, __float2half2_rn(0.f));
+  else h = __hmax2(h, __hmul2(h, __float2half2_rn(0.2f)));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int N, int ACT, int MODE, int NH>
+__device__ __forceinline__ void epilogue(uint32_t taddr, uint8_t* A, int row, int ch, const float* __restrict__ headw,
+                                         float* hacc) {
+  constexpr int NC = N / 2;                     // columns of this thread
+  const int col0 = ch * NC;
+  if (MODE == 0 && NH == 0) {
+    static_assert(NC % 64 == 0 || NC == 32, "column count");
+    constexpr int STEP = NC >= 64 ? 64 : 32;
 #pragma unroll 1
-  for (int c0 = 0; c0 < N; c0 += 32) {
-    float v[32];
-    tmem_ld32(taddr + c0, v);
+    for (int c0 = 0; c0 < NC; c0 += STEP) {
+      float v[STEP];
+      tmem_ld32_issue(taddr + col0 + c0, v);
+      if (STEP == 64) tmem_ld32_issue(taddr + col0 + c0 + 32, v + 32);
+      tmem_ld_wait();
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + q);
-      v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = ACT == 0 ? fmaxf(v[j], 0.f) : fmaxf(v[j], 0.2f * v[j]);
-    if (NH > 0) {
-#pragma unroll
-      for (int h = 0; h < NH; ++h) {
-        float s = hacc[h];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 w = __ldg(reinterpret_cast<const float4*>(headw + h * N + c0) + q);
-          s += v[4 * q] * w.x + v[4 * q + 1] * w.y + v[4 * q + 2] * w.z + v[4 * q + 3] * w.w;
-        }
-        hacc[h] = s;
+      for (int g = 0; g < STEP / 8; ++g) {
+        const uint4 o = make_uint4(act_pack<ACT>(v[8 * g], v[8 * g + 1]), act_pack<ACT>(v[8 * g + 2], v[8 * g + 3]),
+                                   act_pack<ACT>(v[8 * g + 4], v[8 * g + 5]), act_pack<ACT>(v[8 * g + 6], v[8 * g + 7]));
+        *reinterpret_cast<uint4*>(A + ((col0 + c0) / 8 + g) * kKGroupBytes + row * 16) = o;
       }
     }
-    if (WRITE) store_groups<4, SPLIT>(A + (c0 / 8) * kKGroupBytes, row, v);
+  } else {
+#pragma unroll 1
+    for (int c0 = 0; c0 < NC; c0 += 32) {
+      float v[32];
+      tmem_ld32(taddr + col0 + c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = ACT == 0 ? fmaxf(v[j], 0.f) : fmaxf(v[j], 0.2f * v[j]);
+      if (NH > 0) {
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          float s = hacc[h];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(headw + h * N + col0 + c0) + q);
+            s += v[4 * q] * w.x + v[4 * q + 1] * w.y + v[4 * q + 2] * w.z + v[4 * q + 3] * w.w;
+          }
+          hacc[h] = s;
+        }
+      }
+      if (MODE != 2) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (MODE == 1) store_group<true>(A, (col0 + c0) / 8 + g, row, v + 8 * g);
+          else store_group<false>(A, (col0 + c0) / 8 + g, row, v + 8 * g);
+        }
+      }
+    }
   }
 }
 
@@ -172,24 +232,24 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
     mbar_init(&bars->acc_ready, 1);
-    mbar_init(&bars->a_ready, kWorkerThreads / 32);
+    mbar_init(&bars->a_ready, kWorkerWarps);
     fence_mbar_init();
   }
   __syncthreads();
-  if (warp == 8) tmem_alloc(&bars->tmem_base, 512);
+  if (warp == kWorkerWarps) tmem_alloc(&bars->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 9) {
+  if (warp == kWorkerWarps + 1) {
     // ------------------------------------------------------------------ weight producer
     if (lane == 0) {
       uint32_t it = 0;
       for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int l = 0; l < kNumLayers; ++l) {
           const LayerDesc& L = net.layer[l];
-          const int nk = (L.K + L.Kext) / 16;
+          const int nk = (L.K + L.Kext) / 16 + L.bias_slice;
           for (int kk = 0; kk < nk; ++kk, ++it) {
             const uint32_t s = it % kStages;
             mbar_wait(&bars->empty[s], ((it / kStages) & 1u) ^ 1u);
@@ -200,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kWorkerWarps) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       uint32_t it = 0, par_a = 0;
@@ -208,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
       for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int l = 0; l < kNumLayers; ++l) {
           const LayerDesc& L = net.layer[l];
-          const int nk_main = L.K / 16, nk = (L.K + L.Kext) / 16;
+          const int nk_main = L.K / 16, nk_ext = L.Kext / 16, nk = nk_main + nk_ext + L.bias_slice;
           const uint32_t idesc = umma_idesc(128, L.N);
           const uint32_t lboB = (uint32_t)L.N * 16u;
           mbar_wait(&bars->a_ready, par_a);
@@ -218,7 +278,9 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
             const uint32_t s = it % kStages;
             mbar_wait(&bars->full[s], (it / kStages) & 1u);
             tc_fence_after();
+            const bool bias_only = kk >= nk_main + nk_ext;           // A = the constant-one columns, weights = bias
             const uint32_t abase = kk < nk_main ? a0 + (uint32_t)kk * 2u * kKGroupBytes
+                                   : bias_only  ? a2 + 4u * kKGroupBytes
                                                 : a2 + (uint32_t)(kk - nk_main) * 2u * kKGroupBytes;
             const uint32_t bbase = r0 + s * kStageBytes;
 #pragma unroll
@@ -228,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
               const uint64_t da_hi = umma_desc(ah, kKGroupBytes, 128u);
               const uint64_t db_hi = umma_desc(bbase, lboB, 128u);
               umma_f16(d, da_hi, db_hi, idesc, kk > 0);
-              if (L.split) {
+              if (L.split && !bias_only) {
                 const uint64_t da_lo = umma_desc(ah + kALoOff, kKGroupBytes, 128u);
                 const uint64_t db_lo = umma_desc(bbase + (uint32_t)L.N * 32u, lboB, 128u);
                 umma_f16(d, da_lo, db_hi, idesc, 1u);
@@ -242,11 +304,12 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
       }
     }
   } else {
-    // ------------------------------------------------------------------ row workers (warps 0..7)
-    const int half = warp >> 2;
+    // ------------------------------------------------------------------ row workers (warps 0..15)
+    const int half = (warp >> 2) & 1, ch = warp >> 3;
     const int row = half * 128 + (warp & 3) * 32 + lane;
     const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)half * 256u;
     uint8_t* A = smem + offA;
+    float4* hx = reinterpret_cast<float4*>(smem + offHx);      // [2 column halves][256 rows]
     uint32_t par_acc = 0;
     auto signal_a = [&]() {
       fence_async_smem();
@@ -259,7 +322,20 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
       par_acc ^= 1u;
       tc_fence_after();
     };
+    // add the partial head sums of the row's other column half
+    auto combine = [&](float* v, int n) {
+      hx[ch * kRows + row] = make_float4(v[0], n > 1 ? v[1] : 0.f, n > 2 ? v[2] : 0.f, 0.f);
+      worker_bar();
+      const float4 o = hx[(ch ^ 1) * kRows + row];
+      v[0] += o.x;
+      if (n > 1) v[1] += o.y;
+      if (n > 2) v[2] += o.z;
+    };
     const float* heads = net.heads;
+    {   // the constant-one columns must exist before the first bias slice is multiplied
+      const float zero[3] = {0.f, 0.f, 0.f};
+      write_encoding<3, 6, 6, false, false, true>(smem + offA2, row, ch, zero);
+    }
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const uint32_t item = tile * kRows + row;
       int id = -1;
@@ -271,84 +347,85 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
         const float* rd = a.raydir + (size_t)(id >> 6) * 3;
         dir[0] = __ldg(rd); dir[1] = __ldg(rd + 1); dir[2] = __ldg(rd + 2);
       }
-      int l = 0;
       // ---- geometry: [p, PE(p,10)] -> 256 -> 10 x 256 (ReLU) -> 1 -> softplus          (decoder.py:201-237)
-      write_encoding<3, 10, 8, false>(A, row, p);
+      write_encoding<3, 10, 8, false, false, false>(A, row, ch, p);
       signal_a();
-      for (; l < 10; ++l) {
+      for (int l = 0; l < 10; ++l) {
         wait_acc();
-        epilogue<256, 0, true, false, 0>(taddr, net.bias + net.layer[l].b_off, A, row, nullptr, nullptr);
+        epilogue<256, 0, 0, 0>(taddr, A, row, ch, nullptr, nullptr);
         signal_a();
       }
       float raw = 0.f;
       wait_acc();
-      epilogue<256, 0, false, false, 1>(taddr, net.bias + net.layer[l].b_off, A, row, heads + kHeadGeo, &raw);
-      ++l;
+      epilogue<256, 0, 2, 1>(taddr, A, row, ch, heads + kHeadGeo, &raw);
+      combine(&raw, 1);
       const float sigma = softplus_t(raw + __ldg(heads + kHeadGeoB));
       // ---- gauge: [p, PE(p,10)] -> 64 -> 128 -> 128 -> 128 (ReLU) -> 2 -> tanh, split fp16   (gauge_fields.py:8-74)
-      write_encoding<3, 10, 8, true>(A, row, p);
+      write_encoding<3, 10, 8, true, true, false>(A, row, ch, p);
       signal_a();
       wait_acc();
-      epilogue<64, 0, true, true, 0>(taddr, net.bias + net.layer[l].b_off, A, row, nullptr, nullptr);
-      ++l;
+      epilogue<64, 0, 1, 0>(taddr, A, row, ch, nullptr, nullptr);
       signal_a();
-      for (int r = 0; r < 2; ++r, ++l) {
+      for (int r = 0; r < 2; ++r) {
         wait_acc();
-        epilogue<128, 0, true, true, 0>(taddr, net.bias + net.layer[l].b_off, A, row, nullptr, nullptr);
+        epilogue<128, 0, 1, 0>(taddr, A, row, ch, nullptr, nullptr);
         signal_a();
       }
       float uvr[2] = {0.f, 0.f};
       wait_acc();
-      epilogue<128, 0, false, true, 2>(taddr, net.bias + net.layer[l].b_off, A, row, heads + kHeadGauge, uvr);
-      ++l;
+      epilogue<128, 0, 2, 2>(taddr, A, row, ch, heads + kHeadGauge, uvr);
+      combine(uvr, 2);
       float uv[2] = {tanhf(uvr[0] + __ldg(heads + kHeadGaugeB)), tanhf(uvr[1] + __ldg(heads + kHeadGaugeB + 1))};
       // ---- texture block1: [uv, PE(uv,10)] -> 256 -> 5 x 256 (LeakyReLU 0.2); color1 256 -> 3 softplus   (decoder.py:56-78)
-      write_encoding<2, 10, 6, false>(A, row, uv);
-      write_encoding<3, 6, 6, false>(smem + offA2, row, dir);
+      write_encoding<2, 10, 6, false, false, false>(A, row, ch, uv);
+      write_encoding<3, 6, 6, false, false, true>(smem + offA2, row, ch, dir);
       signal_a();
-      for (int r = 0; r < 5; ++r, ++l) {
+      for (int r = 0; r < 5; ++r) {
         wait_acc();
-        epilogue<256, 1, true, false, 0>(taddr, net.bias + net.layer[l].b_off, A, row, nullptr, nullptr);
+        epilogue<256, 1, 0, 0>(taddr, A, row, ch, nullptr, nullptr);
         signal_a();
       }
       float c1[3] = {0.f, 0.f, 0.f};
       wait_acc();
-      epilogue<256, 1, true, false, 3>(taddr, net.bias + net.layer[l].b_off, A, row, heads + kHeadC1, c1);
-      ++l;
+      epilogue<256, 1, 0, 3>(taddr, A, row, ch, heads + kHeadC1, c1);
       signal_a();
+      combine(c1, 3);
 #pragma unroll
       for (int k = 0; k < 3; ++k) c1[k] = softplus_t(c1[k] + __ldg(heads + kHeadC1B + k));
       // ---- texture block2: [h, d, PE(d,6)] -> 256 -> 3 x 256 (LeakyReLU) -> 3
-      for (int r = 0; r < 3; ++r, ++l) {
+      for (int r = 0; r < 3; ++r) {
         wait_acc();
-        epilogue<256, 1, true, false, 0>(taddr, net.bias + net.layer[l].b_off, A, row, nullptr, nullptr);
+        epilogue<256, 1, 0, 0>(taddr, A, row, ch, nullptr, nullptr);
         signal_a();
       }
       float c2[3] = {0.f, 0.f, 0.f};
       wait_acc();
-      epilogue<256, 1, false, false, 3>(taddr, net.bias + net.layer[l].b_off, A, row, heads + kHeadB2, c2);
-      float rgb[3];
+      epilogue<256, 1, 2, 3>(taddr, A, row, ch, heads + kHeadB2, c2);
+      combine(c2, 3);
+      if (ch == 0 && id >= 0) {
+        float rgb[3];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) rgb[k] = c1[k] + c2[k] + __ldg(heads + kHeadB2B + k);
-      if (net.texture == nullptr) {
+        for (int k = 0; k < 3; ++k) rgb[k] = c1[k] + c2[k] + __ldg(heads + kHeadB2B + k);
+        if (net.texture == nullptr) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) rgb[k] = fmaxf(rgb[k], 0.f);                       // (c1 + c2).clamp(min=0)
-      } else {                                                                         // decoder.py:91-103, mode 0
-        float m = 0.f;
+          for (int k = 0; k < 3; ++k) rgb[k] = fmaxf(rgb[k], 0.f);                     // (c1 + c2).clamp(min=0)
+        } else {                                                                       // decoder.py:91-103, mode 0
+          float m = 0.f;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) m += fminf(fmaxf(rgb[k] * 8.f, 0.f), 1.f);
-        m = m / 3.f;
-        float tx[3];
-        sample_texture(net, uv[0], uv[1], tx);
+          for (int k = 0; k < 3; ++k) m += fminf(fmaxf(rgb[k] * 8.f, 0.f), 1.f);
+          m = m / 3.f;
+          float tx[3];
+          sample_texture(net, uv[0], uv[1], tx);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) rgb[k] = tx[k] * m;
+          for (int k = 0; k < 3; ++k) rgb[k] = tx[k] * m;
+        }
+        a.sample_out[id] = make_float4(sigma, rgb[0], rgb[1], rgb[2]);
       }
-      if (id >= 0) a.sample_out[id] = make_float4(sigma, rgb[0], rgb[1], rgb[2]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == kWorkerWarps) tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------

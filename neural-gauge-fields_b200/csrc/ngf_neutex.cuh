@@ -17,8 +17,9 @@ namespace ntx {
 
 constexpr int kS = 64;                 // samples per ray (dtu_test.sh: --sample_num 64); the kernels are built for it
 constexpr int kRows = 256;             // work items per MLP tile: two M=128 tcgen05 tiles sharing every weight chunk
-constexpr int kWorkerThreads = 256;    // one thread per tile row (TMEM lane)
-constexpr int kThreads = 320;          // + 1 MMA-issue warp + 1 weight-producer warp
+constexpr int kWorkerThreads = 512;    // two threads per tile row (TMEM lane): each owns half of the layer's columns
+constexpr int kWorkerWarps = kWorkerThreads / 32;
+constexpr int kThreads = kWorkerThreads + 64;   // + 1 MMA-issue warp + 1 weight-producer warp
 constexpr int kStages = 8;             // weight ring
 constexpr uint32_t kStageBytes = 8192; // one K=16 slice of a 256-wide layer (or hi+lo slices of a <=128-wide one)
 constexpr int kNumLayers = 25;         // MMA layers per tile: geometry 11, gauge 4, texture block1 6, block2 4
@@ -28,15 +29,15 @@ struct LayerDesc {
   int Kext;             // extra K taken from the view-direction operand (block2 layer 0: 48), else 0
   int N;                // output width (64 / 128 / 256)
   int split;            // 1: hi/lo split-fp16 operands, 3 MMAs per K step (gauge network)
+  int bias_slice;       // 1: one more K=16 slice whose A operand is the constant-one columns of the view operand and
+                        //    whose weights are (bias_hi, bias_lo); 0: the bias rides in the Kext slices (block2 layer 0)
   uint32_t w_off;       // byte offset of the layer's first weight chunk in the packed weight stream
   uint32_t chunk_bytes; // bytes per K=16 chunk (N*32, doubled when split)
-  uint32_t b_off;       // float offset of the layer's bias in the bias array
 };
 
 struct NetDev {
   LayerDesc layer[kNumLayers];
   const uint8_t* wpack;   // all weight chunks, tcgen05 K-major core-matrix order, in execution order
-  const float* bias;      // concatenated biases of the 25 MMA layers
   const float* heads;     // fp32 head weights (16-byte aligned rows first, then the biases), offsets kHead* below
   const float* texture;   // [h][w][c] edited texture or nullptr
   int tex_h, tex_w, tex_c;

@@ -35,7 +35,6 @@ struct NgfNeutex_ {
   int num_sms = 0;
   NetDev net{};
   uint8_t* wpack = nullptr;
-  float* bias = nullptr;
   float* heads = nullptr;
   float* texture = nullptr;
   // workspace for up to cap_rays rays
@@ -68,7 +67,7 @@ static void ntx_free_all(NgfNeutex_* h) {
   ntx_free_ws(h);
   ntx_free_chunks(h);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
-  cudaFree(h->wpack); cudaFree(h->bias); cudaFree(h->heads); cudaFree(h->texture); cudaFree(h->counters); cudaFree(h->cam_bg);
+  cudaFree(h->wpack); cudaFree(h->heads); cudaFree(h->texture); cudaFree(h->counters); cudaFree(h->cam_bg);
 }
 
 struct Guard {
@@ -145,18 +144,30 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
 
   std::vector<uint8_t> wp;
-  std::vector<float> bias, heads(kHeadFloats, 0.f), W, B;
+  std::vector<float> heads(kHeadFloats, 0.f), W, B, Wb;
   int li = 0;
+  // The bias is accumulated by the tensor core: the view-direction operand carries two constant-one columns
+  // (kOnesCol, kOnesCol + 1 = columns 7 and 8 of its third K=16 slice) and the weights hold (bias_hi, bias_lo) there.
+  // Layers without view inputs get one extra K=16 slice for it; block2 layer 0 has it inside its 48 view columns.
   auto add = [&](const NgfLinear& l, int K, int Kext, bool split) -> int {
     if (fetch(W, l.w, (size_t)l.out_dim * l.in_dim) != cudaSuccess || fetch(B, l.b, l.out_dim) != cudaSuccess)
       return ngf_set_error(NGF_ECUDA, "cannot read layer %d parameters: %s", li, cudaGetErrorString(cudaGetLastError()));
     LayerDesc& L = h->net.layer[li++];
-    L.K = K; L.Kext = Kext; L.N = l.out_dim; L.split = split ? 1 : 0;
+    const int N = l.out_dim;
+    const bool merged = Kext > 0;
+    const int K_total = merged ? K + Kext : K + 16;
+    const int bias_col = merged ? K + 39 : K + 7;
+    L.K = K; L.Kext = Kext; L.N = N; L.split = split ? 1 : 0; L.bias_slice = merged ? 0 : 1;
     L.w_off = (uint32_t)wp.size();
-    L.chunk_bytes = (uint32_t)l.out_dim * 32u * (split ? 2u : 1u);
-    L.b_off = (uint32_t)bias.size();
-    pack_layer(wp, W, l.out_dim, l.in_dim, K + Kext, split);
-    bias.insert(bias.end(), B.begin(), B.end());
+    L.chunk_bytes = (uint32_t)N * 32u * (split ? 2u : 1u);
+    Wb.assign((size_t)N * K_total, 0.f);
+    for (int r = 0; r < N; ++r) {
+      for (int k = 0; k < l.in_dim; ++k) Wb[(size_t)r * K_total + k] = W[(size_t)r * l.in_dim + k];
+      const float bh = __half2float(__float2half_rn(B[r]));
+      Wb[(size_t)r * K_total + bias_col] = bh;
+      Wb[(size_t)r * K_total + bias_col + 1] = B[r] - bh;
+    }
+    pack_layer(wp, Wb, N, K_total, K_total, split);
     return NGF_OK;
   };
   auto head = [&](const NgfLinear& l, int w_off, int b_off) -> int {
@@ -179,8 +190,6 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
 
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->wpack), wp.size());
   if (e == cudaSuccess) e = cudaMemcpy(h->wpack, wp.data(), wp.size(), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->bias), bias.size() * sizeof(float));
-  if (e == cudaSuccess) e = cudaMemcpy(h->bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->heads), heads.size() * sizeof(float));
   if (e == cudaSuccess) e = cudaMemcpy(h->heads, heads.data(), heads.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->counters), 64);
@@ -194,7 +203,7 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
     ntx_free_all(h); delete h;
     return ngf_set_error(NGF_ECUDA, "ngf_neutex_pack: %s", cudaGetErrorString(e));
   }
-  h->net.wpack = h->wpack; h->net.bias = h->bias; h->net.heads = h->heads;
+  h->net.wpack = h->wpack; h->net.heads = h->heads;
   h->net.texture = h->texture; h->net.tex_h = d->tex_h; h->net.tex_w = d->tex_w; h->net.tex_c = d->tex_c;
   h->net.jitter = d->jitter;
   *out = h;
