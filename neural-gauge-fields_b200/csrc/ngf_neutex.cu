@@ -246,16 +246,18 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
     // ------------------------------------------------------------------ weight producer
     if (lane == 0) {
       uint32_t it = 0;
+      const uint8_t* wsrc = net.wpack + (size_t)(blockIdx.x % (unsigned)net.w_copies) * net.wpack_stride;
       for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int l = 0; l < kNumLayers; ++l) {
           const LayerDesc& L = net.layer[l];
           const int nk = (L.K + L.Kext) / 16 + L.bias_slice;
-          for (int kk = 0; kk < nk; ++kk, ++it) {
+          for (int kk = 0; kk < nk; kk += kSlicesPerStage, ++it) {
             const uint32_t s = it % kStages;
+            const int n = nk - kk < kSlicesPerStage ? nk - kk : kSlicesPerStage;
+            const uint32_t bytes = (uint32_t)n * L.chunk_bytes;          // consecutive slices are contiguous
             mbar_wait(&bars->empty[s], ((it / kStages) & 1u) ^ 1u);
-            mbar_expect_tx(&bars->full[s], L.chunk_bytes);
-            bulk_g2s(smem + offRing + s * kStageBytes, net.wpack + L.w_off + (size_t)kk * L.chunk_bytes, L.chunk_bytes,
-                     &bars->full[s]);
+            mbar_expect_tx(&bars->full[s], bytes);
+            bulk_g2s(smem + offRing + s * kStageBytes, wsrc + L.w_off + (size_t)kk * L.chunk_bytes, bytes, &bars->full[s]);
           }
         }
       }
@@ -274,27 +276,31 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
           mbar_wait(&bars->a_ready, par_a);
           par_a ^= 1u;
           tc_fence_after();
-          for (int kk = 0; kk < nk; ++kk, ++it) {
+          for (int k0 = 0; k0 < nk; k0 += kSlicesPerStage, ++it) {
             const uint32_t s = it % kStages;
+            const int n = nk - k0 < kSlicesPerStage ? nk - k0 : kSlicesPerStage;
             mbar_wait(&bars->full[s], (it / kStages) & 1u);
-            tc_fence_after();
-            const bool bias_only = kk >= nk_main + nk_ext;           // A = the constant-one columns, weights = bias
-            const uint32_t abase = kk < nk_main ? a0 + (uint32_t)kk * 2u * kKGroupBytes
-                                   : bias_only  ? a2 + 4u * kKGroupBytes
-                                                : a2 + (uint32_t)(kk - nk_main) * 2u * kKGroupBytes;
-            const uint32_t bbase = r0 + s * kStageBytes;
+            for (int j = 0; j < n; ++j) {
+              const int kk = k0 + j;
+              const bool bias_only = kk >= nk_main + nk_ext;         // A = the constant-one columns, weights = bias
+              const uint32_t abase = kk < nk_main ? a0 + (uint32_t)kk * 2u * kKGroupBytes
+                                     : bias_only  ? a2 + 4u * kKGroupBytes
+                                                  : a2 + (uint32_t)(kk - nk_main) * 2u * kKGroupBytes;
+              const uint32_t bbase = r0 + s * kStageBytes + (uint32_t)j * L.chunk_bytes;
+              if (net.dbg & 2) continue;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const uint32_t d = tmem + (uint32_t)half * 256u;
-              const uint32_t ah = abase + (uint32_t)half * 128u * 16u;
-              const uint64_t da_hi = umma_desc(ah, kKGroupBytes, 128u);
-              const uint64_t db_hi = umma_desc(bbase, lboB, 128u);
-              umma_f16(d, da_hi, db_hi, idesc, kk > 0);
-              if (L.split && !bias_only) {
-                const uint64_t da_lo = umma_desc(ah + kALoOff, kKGroupBytes, 128u);
-                const uint64_t db_lo = umma_desc(bbase + (uint32_t)L.N * 32u, lboB, 128u);
-                umma_f16(d, da_lo, db_hi, idesc, 1u);
-                umma_f16(d, da_hi, db_lo, idesc, 1u);
+              for (int half = 0; half < 2; ++half) {
+                const uint32_t d = tmem + (uint32_t)half * 256u;
+                const uint32_t ah = abase + (uint32_t)half * 128u * 16u;
+                const uint64_t da_hi = umma_desc(ah, kKGroupBytes, 128u);
+                const uint64_t db_hi = umma_desc(bbase, lboB, 128u);
+                umma_f16(d, da_hi, db_hi, idesc, kk > 0);
+                if (L.split && !bias_only) {
+                  const uint64_t da_lo = umma_desc(ah + kALoOff, kKGroupBytes, 128u);
+                  const uint64_t db_lo = umma_desc(bbase + (uint32_t)L.N * 32u, lboB, 128u);
+                  umma_f16(d, da_lo, db_hi, idesc, 1u);
+                  umma_f16(d, da_hi, db_lo, idesc, 1u);
+                }
               }
             }
             umma_commit(&bars->empty[s]);
@@ -318,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
       if (lane == 0) mbar_arrive(&bars->a_ready);
     };
     auto wait_acc = [&]() {
-      mbar_wait(&bars->acc_ready, par_acc);
+      mbar_wait_backoff(&bars->acc_ready, par_acc);
       par_acc ^= 1u;
       tc_fence_after();
     };

@@ -20,8 +20,10 @@ constexpr int kRows = 256;             // work items per MLP tile: two M=128 tcg
 constexpr int kWorkerThreads = 512;    // two threads per tile row (TMEM lane): each owns half of the layer's columns
 constexpr int kWorkerWarps = kWorkerThreads / 32;
 constexpr int kThreads = kWorkerThreads + 64;   // + 1 MMA-issue warp + 1 weight-producer warp
-constexpr int kStages = 8;             // weight ring
-constexpr uint32_t kStageBytes = 8192; // one K=16 slice of a 256-wide layer (or hi+lo slices of a <=128-wide one)
+constexpr int kStages = 4;             // weight ring
+constexpr int kSlicesPerStage = 2;     // K=16 weight slices per ring stage: one wait / copy / commit per stage
+constexpr uint32_t kSliceBytes = 8192; // one K=16 slice of a 256-wide layer (or hi+lo slices of a <=128-wide one)
+constexpr uint32_t kStageBytes = kSlicesPerStage * kSliceBytes;
 constexpr int kNumLayers = 25;         // MMA layers per tile: geometry 11, gauge 4, texture block1 6, block2 4
 
 struct LayerDesc {
@@ -38,10 +40,13 @@ struct LayerDesc {
 struct NetDev {
   LayerDesc layer[kNumLayers];
   const uint8_t* wpack;   // all weight chunks, tcgen05 K-major core-matrix order, in execution order
+  uint32_t wpack_stride;  // optional replicas of the stream (NGF_NTX_COPIES, default 1): CTA b reads copy b % w_copies
+  int w_copies;
   const float* heads;     // fp32 head weights (16-byte aligned rows first, then the biases), offsets kHead* below
   const float* texture;   // [h][w][c] edited texture or nullptr
   int tex_h, tex_w, tex_c;
   float jitter;
+  int dbg;                // NGF_NTX_DBG (profiling experiments only): 1 = skip epilogue bodies, 2 = skip MMA issue
 };
 
 // geometry head [256] | gauge head [2][128] | color1 [3][256] | block2 head [3][256] | biases 1 + 2 + 3 + 3

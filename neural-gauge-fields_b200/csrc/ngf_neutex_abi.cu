@@ -188,8 +188,16 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
   if (!rc) rc = head(d->tex_block2[4], kHeadB2, kHeadB2B);
   if (rc) { ntx_free_all(h); delete h; return rc; }
 
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->wpack), wp.size());
-  if (e == cudaSuccess) e = cudaMemcpy(h->wpack, wp.data(), wp.size(), cudaMemcpyHostToDevice);
+  // Replicate the weight stream: all CTAs walk it in lock step, so a single copy is read by 148 SMs at the same
+  // addresses at the same time and serialises on a few L2 slices.
+  int copies = 1;
+  { const char* ce = getenv("NGF_NTX_COPIES"); if (ce && atoi(ce) >= 1 && atoi(ce) <= 64) copies = atoi(ce); }
+  const size_t stride = (wp.size() + 4095) / 4096 * 4096 + 4096 * 3;     // odd number of 4 KiB pages apart
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->wpack), stride * copies);
+  for (int c = 0; c < copies && e == cudaSuccess; ++c)
+    e = cudaMemcpy(h->wpack + stride * c, wp.data(), wp.size(), cudaMemcpyHostToDevice);
+  h->net.wpack_stride = (uint32_t)stride;
+  h->net.w_copies = copies;
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->heads), heads.size() * sizeof(float));
   if (e == cudaSuccess) e = cudaMemcpy(h->heads, heads.data(), heads.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->counters), 64);
@@ -206,6 +214,7 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
   h->net.wpack = h->wpack; h->net.heads = h->heads;
   h->net.texture = h->texture; h->net.tex_h = d->tex_h; h->net.tex_w = d->tex_w; h->net.tex_c = d->tex_c;
   h->net.jitter = d->jitter;
+  { const char* e = getenv("NGF_NTX_DBG"); h->net.dbg = e ? atoi(e) : 0; }
   *out = h;
   return NGF_OK;
 }
