@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--field", default="hull", choices=["hull", "fog"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-regime (tensor-bound) side measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the InfoInv / UV-Mapping side measurements (BASELINE configs[2], [3])")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -247,11 +248,21 @@ def main():
     value = n_batch * args.steps / (ms * 1e-3)
 
     # ---- end-to-end timed region: pinned host rays -> H2D -> render (+ all-gather) -> D2H of the results
+    e2e_drain = lambda: None
     if world == 1:
-        rgb_h = torch.empty((n_local, 3)).pin_memory()
-        dep_h = torch.empty((n_local,)).pin_memory()
+        # the repo's public call for a sequence of frames: ngf_b200.render_frames = ngf_field_render_host_async per frame,
+        # frame k+1 uploading while frame k renders and frame k-1 downloads (3 result buffers in rotation)
+        outs = [(torch.empty((n_local, 3)).pin_memory(), torch.empty((n_local,)).pin_memory()) for _ in range(3)]
+        pend = []
         def step_e2e(i):
-            field.render_host(host[i % N_POSES], rgb_h, dep_h, white_bg=True, N_samples=S, image_width=W, iteration=30001)
+            r, d = outs[i % 3]
+            pend.append(field.render_host_async(host[i % N_POSES], r, d, white_bg=True, N_samples=S, image_width=W,
+                                                iteration=30001))
+            if len(pend) > 2:
+                field.host_wait(pend.pop(0))
+        def e2e_drain():
+            while pend:
+                field.host_wait(pend.pop(0))
         d2h = n_local * 16
     else:
         stage = torch.empty_like(dev_rays[0])
@@ -266,10 +277,12 @@ def main():
         d2h = n_local * 16
     for i in range(3):
         step_e2e(i)
+    e2e_drain()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         step_e2e(i)
+    e2e_drain()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = n_batch * args.steps / e2e_s
@@ -312,7 +325,7 @@ def main():
                    "rays_per_step": n_batch, "l2": f"inputs rotate over {N_POSES} poses ({N_POSES * n_local * 24 / 1e6:.0f} MB of rays per rank > 126 MB L2)",
                    "parallelism": "single GPU" if world == 1 else f"ray-sharded dp{world}, {BLOCK}-ray interleaved blocks"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_local * 24, "d2h_bytes_per_step": d2h,
-                "api": "ngf_field_render_host (C ABI, host buffers)" if world == 1 else "H2D + ngf_field_render + all-gather + D2H"},
+                "api": "ngf_b200.render_frames: ngf_field_render_host_async per frame (C ABI, pinned host buffers, 3 frames in flight)" if world == 1 else "H2D + ngf_field_render + all-gather + D2H"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": roofline,
@@ -322,15 +335,20 @@ def main():
     if world == 1 and not args.no_dense:
         line["dense_regime"] = dense_regime(ngf_b200, synth, dev, pk, dev_rays)
 
+    # ---- the other single-GPU configurations of BASELINE.json, as side measurements
+    if world == 1 and not args.no_extra:
+        line["other_configs"] = {"infoinv": infoinv_config(ngf_b200, synth, dev, pk, dev_rays),
+                                 "neutex": neutex_config(ngf_b200, synth, dev, pk)}
+
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample of the same workload
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import restate_field as R
         spec = R.spec_from_state("triplane", state, alpha_volume=occ, gauge_on=True, **kw)
         threads = os.cpu_count() or 1
-        sample = host[0][::2].contiguous()
+        sample = torch.cat([host[0], host[1]])
         v, done, dt = cpu_port_rate(spec, R, sample, args.cpu_seconds, threads)
         line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
-                                "sample": f"{done} rays (every 2nd ray of frame 0, 4096-ray chunks) in {dt:.1f} s"}
+                                "sample": f"first {done} rays of frames 0-1 (4096-ray chunks, torch CPU fp32, {threads} threads) in {dt:.1f} s"}
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
@@ -370,6 +388,71 @@ def dense_regime(ngf_b200, synth, dev, pk, dev_rays):
                          "executed_tflops": executed / c_s / 1e12,
                          "note": "achieved counts the reference's arithmetic (70 400 FLOP/colour sample incl. the 144x144 "
                                  "basis); executed counts what the kernel runs after folding the basis into layer 1"}}
+
+
+def infoinv_config(ngf_b200, synth, dev, pk, dev_rays):
+    """BASELINE configs[2]: InfoInv (sinusoidal phase product, 72->32->32->1 density MLP, 216-wide colour input),
+    800x800 rays x 192 samples, hull field + alpha mask."""
+    kw = synth.field_kwargs("C2")
+    f = ngf_b200.InfoInvTriPlane(kw["aabb"], kw["gridSize"], dev, near_far=kw["near_far"], step_ratio=kw["step_ratio"],
+                                 distance_scale=kw["distance_scale"], rayMarch_weight_thres=kw["rayMarch_weight_thres"])
+    synth.load_into(f, synth.field_state("infoinv", "hull"), synth.occupancy_volume("hull"), ngf_b200.AlphaGridMask)
+    n = dev_rays[0].shape[0]
+    for i in range(3):
+        f(dev_rays[i], white_bg=True, N_samples=S, infoinv=True, image_width=W)
+    torch.cuda.synchronize()
+    st = f.last_stats()
+    steps = 10
+    f.kernel_timing(steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        f(dev_rays[i % N_POSES], white_bg=True, N_samples=S, infoinv=True, image_width=W)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    n_k, m_ms, c_ms = f.kernel_timing_read()
+    nV, nA = st["samples_density"] / n, st["samples_colour"] / n
+    flops = n * (nV * 6720 + nA * 131456)                        # SURVEY.md §8(d): InfoInv MLP FLOPs per sample
+    return {"workload": "InfoInv hull field, 800x800 rays x 192 samples/ray, infoinv=True, 256^3 alpha mask (BASELINE configs[2])",
+            "rays_per_s": n / (ms * 1e-3), "ms_per_frame": ms, "march_kernel_ms": m_ms / n_k, "colour_kernel_ms": c_ms / n_k,
+            "density_samples_per_ray": nV, "colour_samples_per_ray": nA,
+            "mlp_flop_roofline_frac": flops / (ms * 1e-3) / 1e12 / pk["tensor"]}
+
+
+def neutex_config(ngf_b200, synth, dev, pk):
+    """BASELINE configs[3]: UV-Mapping NeuTex render, 600x800 rays x 64 samples, random-init networks of the reference's
+    shapes, synthetic DTU-like camera, explicit jitter noise."""
+    m = ngf_b200.NeuTex(device=dev)
+    m.load_state_dict(synth.neutex_state(0))
+    campos, raydir = synth.neutex_camera(0)
+    R = raydir.shape[1]
+    noise = synth.neutex_noise(R)
+    bg = torch.ones(1, 3)
+    d_cam, d_rd, d_nz, d_bg = campos.to(dev), raydir.to(dev), noise.to(dev), bg.to(dev)
+    m(d_cam, d_rd, d_bg, noise=d_nz)
+    steps = 3
+    m.kernel_timing(steps)
+    for i in range(steps):
+        m(d_cam, d_rd, d_bg, noise=d_nz)
+    k, a_ms, b_ms, c_ms = m.kernel_timing_read()
+    nv = m.last_valid_samples()
+    per_sample = 2 * (63 * 256 + 10 * 256 * 256 + 256 + 63 * 64 + 64 * 128 + 2 * 128 * 128 + 256 + 42 * 256 + 5 * 256 * 256
+                      + 768 + 295 * 256 + 3 * 256 * 256 + 768)      # geometry + gauge + texture, reference arithmetic
+    total_ms = (a_ms + b_ms + c_ms) / k
+    h_rd, h_nz = raydir.pin_memory(), noise.pin_memory()
+    m.render_host(campos, h_rd, bg, h_nz)
+    t0 = time.perf_counter()
+    m.render_host(campos, h_rd, bg, h_nz)
+    e2e_s = time.perf_counter() - t0
+    return {"workload": "UV-Mapping NeuTex, 600x800 rays x 64 samples/ray, square primitive, jitter 0.05 (BASELINE configs[3])",
+            "rays_per_s": R / (total_ms * 1e-3), "ms_per_frame": total_ms, "raygen_ms": a_ms / k, "mlp_kernel_ms": b_ms / k,
+            "march_ms": c_ms / k, "in_cube_samples_per_ray": nv / R,
+            "e2e_rays_per_s": R / e2e_s, "e2e_h2d_bytes": R * (3 + 64) * 4, "e2e_d2h_bytes": R * 16,
+            "roofline": {"bound": "tensor", "kernel": "ntx_mlp_kernel", "achieved": nv * per_sample / (b_ms / k * 1e-3) / 1e12,
+                         "peak": pk["tensor"], "unit": "TFLOP/s", "frac": nv * per_sample / (b_ms / k * 1e-3) / 1e12 / pk["tensor"],
+                         "note": "reference arithmetic (2.66 MFLOP) of the in-cube samples only; the reference itself pushes all "
+                                 "64 samples/ray through the MLPs"}}
 
 
 if __name__ == "__main__":

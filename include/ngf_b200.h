@@ -164,6 +164,17 @@ int ngf_field_render_host(NgfField f, const float* rays_host, int64_t n_rays, in
                           int32_t n_samples, int32_t white_bg, int32_t tile_w, float* rgb_host,
                           float* depth_host, int32_t mlp_impl);
 
+/*
+ * Asynchronous variant for loops over many frames (the reference's evaluation() renders 200 test frames one after the
+ * other, main.py:89-100): enqueues the frame and returns a ticket at once; consecutive frames pipeline on the device
+ * (frame k+1's H2D overlaps frame k's compute and D2H).  The host buffers of a frame must stay untouched until
+ * ngf_field_host_wait(ticket) returns.  At most 8 frames may be in flight (older tickets are waited for implicitly).
+ */
+int ngf_field_render_host_async(NgfField f, const float* rays_host, int64_t n_rays, int32_t ray_stride,
+                                int32_t n_samples, int32_t white_bg, int32_t tile_w, float* rgb_host,
+                                float* depth_host, int32_t mlp_impl, uint64_t* ticket);
+int ngf_field_host_wait(NgfField f, uint64_t ticket);
+
 /* Per-call switches of forward(): TriPlane `iteration >= gauge_start` (TriPlane/models/Field.py:58) and InfoInv
  * `infoinv=` (InfoInv/models/FieldBase.py:228).  They only flip a flag in the handle; no repack. */
 int ngf_field_set_gauge(NgfField f, int32_t on);

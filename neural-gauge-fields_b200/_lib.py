@@ -64,6 +64,9 @@ SIGNATURES = {
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "ngf_field_render_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
+    "ngf_field_render_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                              C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]),
+    "ngf_field_host_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
     "ngf_field_set_gauge": (C.c_int, [C.c_void_p, C.c_int32]),
     "ngf_field_set_infoinv": (C.c_int, [C.c_void_p, C.c_int32]),
     "ngf_field_stats": (C.c_int, [C.c_void_p, C.POINTER(NgfStats), C.c_void_p]),

@@ -60,7 +60,8 @@ struct DeviceGuard {
 // handle
 // ---------------------------------------------------------------------------------------------------------
 struct HostChunk {            // one in-flight chunk of the host-buffer render path
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // compute stream (slots 0..kHostComp-1 own one; the others borrow slot % kHostComp)
+  cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;   // upload done | kernels done | download done
   float* rays = nullptr;
   float* rgb = nullptr;
   float* depth = nullptr;
@@ -98,20 +99,51 @@ struct NgfField_ {
   // kernel timing (ngf_field_timing_*)
   std::vector<cudaEvent_t> ev;        // 3 per timed march+colour pair
   int ev_used = 0;
-  // host path
-  HostChunk chunk[2];
+  // host path: kHostSlots chunks in flight, each on its own stream; whole-frame pipelines are replayed as CUDA graphs
+  HostChunk chunk[6];
+  cudaStream_t s_in = nullptr, s_out = nullptr;       // dedicated upload / download streams
+  int next_slot = 0;                                  // round robin over the chunk slots, across frames
   long long chunk_cap = 0;
   int chunk_stride = 0;
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  struct HostGraph {
+    const void *rays, *rgb, *depth;
+    long long n_rays;
+    int stride, n_samples, white_bg, tile_w, impl;
+    unsigned long long epoch;
+    cudaGraphExec_t exec;            // nullptr: capture failed once, stay eager for this key
+  };
+  std::vector<HostGraph> graphs;
+  unsigned long long epoch = 0;       // bumped whenever anything a captured kernel argument depends on changes
+  cudaEvent_t frame_done[8] = {};     // completion of the last 8 asynchronous host frames (ticket % 8)
+  unsigned long long next_ticket = 1;
 };
+static const int kHostSlots = 6;    // chunk buffers in flight
+static const int kHostComp = 3;     // compute streams
 
 static const int kCounterBytes = 64;
 
+static void drop_graphs(NgfField_* h) {
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+}
+
 static void free_chunks(NgfField_* h) {
-  for (auto& c : h->chunk) {
-    if (c.stream) cudaStreamDestroy(c.stream);
+  drop_graphs(h);
+  if (h->ev_fork) { cudaEventDestroy(h->ev_fork); h->ev_fork = nullptr; }
+  for (auto& e : h->ev_join) if (e) { cudaEventDestroy(e); e = nullptr; }
+  for (auto& e : h->frame_done) if (e) { cudaEventDestroy(e); e = nullptr; }
+  for (int i = 0; i < kHostSlots; ++i) {
+    HostChunk& c = h->chunk[i];
+    if (c.stream && i < kHostComp) cudaStreamDestroy(c.stream);
+    if (c.ev_in) cudaEventDestroy(c.ev_in);
+    if (c.ev_comp) cudaEventDestroy(c.ev_comp);
+    if (c.ev_out) cudaEventDestroy(c.ev_out);
     cudaFree(c.rays); cudaFree(c.rgb); cudaFree(c.depth); cudaFree(c.acc); cudaFree(c.counters); cudaFree(c.queue);
     c = HostChunk{};
   }
+  if (h->s_in) { cudaStreamDestroy(h->s_in); h->s_in = nullptr; }
+  if (h->s_out) { cudaStreamDestroy(h->s_out); h->s_out = nullptr; }
   h->chunk_cap = 0;
 }
 
@@ -437,6 +469,8 @@ int ngf_field_repack(NgfField h, const NgfFieldDesc* desc) {
   if (desc->variant != h->dev.variant) return fail(NGF_EINVAL, "repack: variant changed");
   DeviceGuard g(h->device);
   if (!g.ok) return fail(NGF_ECUDA, "cannot select device %d", h->device);
+  ++h->epoch;
+  drop_graphs(h);
   return pack_params(h, desc, false);
 }
 
@@ -489,7 +523,6 @@ static int render_dev(NgfField h, const float* rays, long long n_rays, int ray_s
   if (want > 0xfffffff0ll) { per = 0xfffffff0ll / S / unit * unit; want = per * S; }
   int rc = ensure_queue(queue, queue_cap, want, st);
   if (rc) return rc;
-  CU(cudaMemsetAsync(counters + 2, 0, kCounterBytes - 8, st));
   for (long long s0 = 0; s0 < n_rays; s0 += per) {
     const long long n = (n_rays - s0) < per ? (n_rays - s0) : per;
     RenderArgs a{};
@@ -509,7 +542,7 @@ static int render_dev(NgfField h, const float* rays, long long n_rays, int ray_s
     a.queue = *queue;
     a.queue_cap = (unsigned int)(n * S < want ? n * S : want);
     a.stats = reinterpret_cast<unsigned long long*>(counters + 2);
-    CU(cudaMemsetAsync(counters, 0, 8, st));
+    CU(cudaMemsetAsync(counters, 0, s0 == 0 ? kCounterBytes : 8, st));   // first batch also clears the statistics
     const bool timed = h->ev_used + 3 <= (int)h->ev.size();
     if (timed) CU(cudaEventRecord(h->ev[h->ev_used], st));
     CU(launch_march(h->dev, a, h->num_sms, st));
@@ -551,21 +584,71 @@ int ngf_field_render(NgfField h, const float* rays_dev, int64_t n_rays, int32_t 
                     h->counters, &h->queue, &h->queue_cap, mlp_impl, st);
 }
 
-int ngf_field_render_host(NgfField h, const float* rays_host, int64_t n_rays, int32_t ray_stride,
-                          int32_t n_samples, int32_t white_bg, int32_t tile_w, float* rgb_host,
-                          float* depth_host, int32_t mlp_impl) {
-  if (!h) return fail(NGF_EINVAL, "field is NULL");
+// Enqueue one whole frame as a three-stage pipeline over chunks: uploads back to back on s_in, kernels on kHostComp
+// compute streams, downloads back to back on s_out, chained by events; a chunk buffer (slot) is reused every kHostSlots
+// chunks.  The frame is complete when s_out has drained (origin of the fork/join is s_in, so the same code runs under
+// stream capture).
+static int host_enqueue(NgfField h, const float* rays_host, long long n_rays, int ray_stride, int n_samples, int white_bg,
+                        int tile_w, float* rgb_host, float* depth_host, int mlp_impl, long long chunk, bool img,
+                        bool join) {
+  CU(cudaEventRecord(h->ev_fork, h->s_in));
+  CU(cudaStreamWaitEvent(h->s_out, h->ev_fork, 0));
+  for (int i = 0; i < kHostComp; ++i) CU(cudaStreamWaitEvent(h->chunk[i].stream, h->ev_fork, 0));
+  int ci = h->next_slot;
+  for (long long s = 0; s < n_rays; s += chunk, ci = (ci + 1) % kHostSlots) {
+    const long long n = (n_rays - s) < chunk ? (n_rays - s) : chunk;
+    HostChunk& c = h->chunk[ci];
+    // upload: the slot's ray buffer is free once the kernels of its previous chunk are done
+    CU(cudaStreamWaitEvent(h->s_in, c.ev_comp, 0));
+    CU(cudaMemcpyAsync(c.rays, rays_host + s * ray_stride, (size_t)n * ray_stride * sizeof(float),
+                       cudaMemcpyHostToDevice, h->s_in));
+    CU(cudaEventRecord(c.ev_in, h->s_in));
+    // kernels: need the rays, and the slot's result buffers must have been downloaded
+    CU(cudaStreamWaitEvent(c.stream, c.ev_in, 0));
+    CU(cudaStreamWaitEvent(c.stream, c.ev_out, 0));
+    int rc = render_dev(h, c.rays, n, ray_stride, n_samples, white_bg, img ? tile_w : 0, c.rgb, c.depth, c.acc,
+                        c.counters, &c.queue, &c.queue_cap, mlp_impl, c.stream);
+    if (rc) return rc;
+    CU(cudaEventRecord(c.ev_comp, c.stream));
+    // download
+    CU(cudaStreamWaitEvent(h->s_out, c.ev_comp, 0));
+    CU(cudaMemcpyAsync(rgb_host + s * 3, c.rgb, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+    CU(cudaMemcpyAsync(depth_host + s, c.depth, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+    CU(cudaEventRecord(c.ev_out, h->s_out));
+  }
+  h->next_slot = ci;
+  if (!join) return NGF_OK;               // eager callers wait on s_out; joining would stall the next frame's uploads
+  // stream capture needs every forked stream to flow back into the origin (s_in)
+  for (int i = 0; i < kHostComp; ++i) {
+    CU(cudaEventRecord(h->ev_join[i], h->chunk[i].stream));
+    CU(cudaStreamWaitEvent(h->s_in, h->ev_join[i], 0));
+  }
+  CU(cudaEventRecord(h->ev_join[kHostComp], h->s_out));
+  CU(cudaStreamWaitEvent(h->s_in, h->ev_join[kHostComp], 0));
+  return NGF_OK;
+}
+
+// Validate, pick the chunk size and make sure the slot buffers exist.
+static int host_prepare(NgfField h, const float* rays_host, int64_t n_rays, int32_t ray_stride, int32_t tile_w,
+                        float* rgb_host, float* depth_host, int32_t mlp_impl, bool pipelined, long long* chunk_out,
+                        bool* img_out) {
   if (n_rays < 0 || n_rays > 0x7fffffffll) return fail(NGF_EINVAL, "n_rays=%lld", (long long)n_rays);
-  if (n_rays == 0) return NGF_OK;
   if (!rays_host || !rgb_host || !depth_host) return fail(NGF_EINVAL, "NULL ray/output pointer");
   if (ray_stride < 6) return fail(NGF_EINVAL, "ray_stride=%d (< 6)", ray_stride);
   if (mlp_impl != NGF_MLP_TCGEN05 && mlp_impl != NGF_MLP_SIMT) return fail(NGF_EINVAL, "mlp_impl=%d", mlp_impl);
-  DeviceGuard g(h->device);
-  if (!g.ok) return fail(NGF_ECUDA, "cannot select device %d", h->device);
-
-  // chunking: ~128 Ki rays per chunk, whole groups of 4 image rows when the image width is known
+  // Chunking (whole groups of 4 image rows when the image width is known).  A single synchronous frame overlaps its own
+  // copies and kernels best with ~128 Ki-ray chunks; when frames are pipelined (async API) the overlap comes from the
+  // neighbouring frames and larger chunks keep the kernels efficient.  [B200: 0.72 ms sync, 0.38 ms pipelined per
+  // 640 000-ray frame]
   const bool img = tile_w > 0 && n_rays % tile_w == 0;
-  long long chunk = 128 * 1024;
+  static long long chunk_sync = 0, chunk_async = 0;
+  if (chunk_sync == 0) {
+    const char* e = getenv("NGF_HOST_CHUNK");
+    chunk_sync = e && atoll(e) > 0 ? atoll(e) : 128 * 1024;
+    const char* ea = getenv("NGF_HOST_CHUNK_ASYNC");
+    chunk_async = ea && atoll(ea) > 0 ? atoll(ea) : (e && atoll(e) > 0 ? atoll(e) : 320 * 1000);
+  }
+  long long chunk = pipelined ? chunk_async : chunk_sync;
   if (img) {
     long long rows = chunk / tile_w;
     rows = rows < 4 ? 4 : rows - rows % 4;
@@ -573,9 +656,20 @@ int ngf_field_render_host(NgfField h, const float* rays_host, int64_t n_rays, in
   }
   if (chunk > n_rays) chunk = n_rays;
   if (h->chunk_cap < chunk || h->chunk_stride != ray_stride) {
+    if (h->s_in) { CU(cudaStreamSynchronize(h->s_in)); CU(cudaStreamSynchronize(h->s_out)); }
     free_chunks(h);
-    for (auto& c : h->chunk) {
-      CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (auto& e : h->ev_join) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : h->frame_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < kHostSlots; ++i) {
+      HostChunk& c = h->chunk[i];
+      if (i < kHostComp) CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+      else c.stream = h->chunk[i % kHostComp].stream;
+      CU(cudaEventCreateWithFlags(&c.ev_in, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&c.ev_comp, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&c.ev_out, cudaEventDisableTiming));
       CU(dev_alloc(&c.rays, (size_t)chunk * ray_stride));
       CU(dev_alloc(&c.rgb, (size_t)chunk * 3));
       CU(dev_alloc(&c.depth, (size_t)chunk));
@@ -585,32 +679,112 @@ int ngf_field_render_host(NgfField h, const float* rays_host, int64_t n_rays, in
     h->chunk_cap = chunk;
     h->chunk_stride = ray_stride;
   }
-  int ci = 0;
-  for (long long s = 0; s < n_rays; s += chunk, ci ^= 1) {
-    const long long n = (n_rays - s) < chunk ? (n_rays - s) : chunk;
-    HostChunk& c = h->chunk[ci];
-    CU(cudaMemcpyAsync(c.rays, rays_host + s * ray_stride, (size_t)n * ray_stride * sizeof(float),
-                       cudaMemcpyHostToDevice, c.stream));
-    int rc = render_dev(h, c.rays, n, ray_stride, n_samples, white_bg, img ? tile_w : 0, c.rgb, c.depth, c.acc,
-                        c.counters, &c.queue, &c.queue_cap, mlp_impl, c.stream);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(rgb_host + s * 3, c.rgb, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
-    CU(cudaMemcpyAsync(depth_host + s, c.depth, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+  *chunk_out = chunk;
+  *img_out = img;
+  return NGF_OK;
+}
+
+int ngf_field_render_host(NgfField h, const float* rays_host, int64_t n_rays, int32_t ray_stride,
+                          int32_t n_samples, int32_t white_bg, int32_t tile_w, float* rgb_host,
+                          float* depth_host, int32_t mlp_impl) {
+  if (!h) return fail(NGF_EINVAL, "field is NULL");
+  if (n_rays == 0) return NGF_OK;
+  DeviceGuard g(h->device);
+  if (!g.ok) return fail(NGF_ECUDA, "cannot select device %d", h->device);
+  long long chunk = 0;
+  bool img = false;
+  int rc = host_prepare(h, rays_host, n_rays, ray_stride, tile_w, rgb_host, depth_host, mlp_impl, false, &chunk, &img);
+  if (rc) return rc;
+  static int use_graphs = -1;
+  if (use_graphs < 0) {
+    const char* ge = getenv("NGF_HOST_GRAPH");
+    use_graphs = ge && ge[0] == '0' ? 0 : 1;
   }
-  CU(cudaStreamSynchronize(h->chunk[0].stream));
-  CU(cudaStreamSynchronize(h->chunk[1].stream));
+  cudaStream_t s0 = h->s_in;
+
+  // A frame that was already rendered once from the same host buffers is replayed as one CUDA-graph launch instead of
+  // ~50 stream calls.
+  const bool graph_ok = use_graphs == 1 && h->ev.empty();
+  NgfField_::HostGraph* hit = nullptr;
+  if (graph_ok)
+    for (auto& e : h->graphs)
+      if (e.rays == rays_host && e.rgb == rgb_host && e.depth == depth_host && e.n_rays == n_rays &&
+          e.stride == ray_stride && e.n_samples == n_samples && e.white_bg == white_bg && e.tile_w == tile_w &&
+          e.impl == mlp_impl && e.epoch == h->epoch) { hit = &e; break; }
+  if (hit && hit->exec) {
+    CU(cudaGraphLaunch(hit->exec, s0));
+    CU(cudaStreamSynchronize(s0));
+    return NGF_OK;
+  }
+  rc = host_enqueue(h, rays_host, n_rays, ray_stride, n_samples, white_bg, tile_w, rgb_host, depth_host, mlp_impl,
+                    chunk, img, false);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->s_out));
+  if (graph_ok && !hit) {                 // every buffer now has its final size: record the same pipeline for next time
+    if (h->graphs.size() >= 64) drop_graphs(h);
+    NgfField_::HostGraph e{rays_host, rgb_host, depth_host, (long long)n_rays, ray_stride, n_samples, white_bg, tile_w,
+                           mlp_impl, h->epoch, nullptr};
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const int crc = host_enqueue(h, rays_host, n_rays, ray_stride, n_samples, white_bg, tile_w, rgb_host, depth_host,
+                                   mlp_impl, chunk, img, true);
+      const cudaError_t ce = cudaStreamEndCapture(s0, &graph);
+      if (crc == NGF_OK && ce == cudaSuccess && graph) {
+        if (cudaGraphInstantiate(&e.exec, graph, 0) != cudaSuccess) e.exec = nullptr;
+      }
+      if (graph) cudaGraphDestroy(graph);
+    }
+    cudaGetLastError();                   // a failed capture only means this key stays on the eager path
+    g_err[0] = 0;
+    h->graphs.push_back(e);
+  }
+  return NGF_OK;
+}
+
+int ngf_field_render_host_async(NgfField h, const float* rays_host, int64_t n_rays, int32_t ray_stride,
+                                int32_t n_samples, int32_t white_bg, int32_t tile_w, float* rgb_host,
+                                float* depth_host, int32_t mlp_impl, uint64_t* ticket) {
+  if (!h || !ticket) return fail(NGF_EINVAL, "NULL argument");
+  DeviceGuard g(h->device);
+  if (!g.ok) return fail(NGF_ECUDA, "cannot select device %d", h->device);
+  long long chunk = 0;
+  bool img = false;
+  int rc = host_prepare(h, rays_host, n_rays, ray_stride, tile_w, rgb_host, depth_host, mlp_impl, true, &chunk, &img);
+  if (rc) return rc;
+  const unsigned long long t = h->next_ticket;
+  cudaEvent_t done = h->frame_done[t % 8];
+  CU(cudaEventSynchronize(done));         // at most 8 frames in flight: the slot's previous frame must be finished
+  if (n_rays > 0) {
+    rc = host_enqueue(h, rays_host, n_rays, ray_stride, n_samples, white_bg, tile_w, rgb_host, depth_host, mlp_impl,
+                      chunk, img, false);
+    if (rc) return rc;
+  }
+  CU(cudaEventRecord(done, h->s_out));
+  *ticket = t;
+  ++h->next_ticket;
+  return NGF_OK;
+}
+
+int ngf_field_host_wait(NgfField h, uint64_t ticket) {
+  if (!h) return fail(NGF_EINVAL, "field is NULL");
+  if (ticket == 0 || ticket >= h->next_ticket) return fail(NGF_EINVAL, "unknown ticket %llu", (unsigned long long)ticket);
+  if (ticket + 8 < h->next_ticket) return NGF_OK;     // its event slot was recycled by ticket + 8, which waited for it
+  DeviceGuard g(h->device);
+  CU(cudaEventSynchronize(h->frame_done[ticket % 8]));
   return NGF_OK;
 }
 
 int ngf_field_set_gauge(NgfField h, int32_t on) {
   if (!h) return fail(NGF_EINVAL, "field is NULL");
   if (on && !h->has_gauge) return fail(NGF_EINVAL, "field was packed without gauge planes");
+  if (h->dev.gauge_on != (on ? 1 : 0)) ++h->epoch;
   h->dev.gauge_on = on ? 1 : 0;
   return NGF_OK;
 }
 
 int ngf_field_set_infoinv(NgfField h, int32_t on) {
   if (!h) return fail(NGF_EINVAL, "field is NULL");
+  if (h->dev.infoinv != (on ? 1 : 0)) ++h->epoch;
   h->dev.infoinv = on ? 1 : 0;
   return NGF_OK;
 }

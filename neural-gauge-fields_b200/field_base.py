@@ -301,6 +301,26 @@ class Base(torch.nn.Module):
                                              depth_host.data_ptr(), self._mlp_impl), "ngf_field_render_host")
         return rgb_host, depth_host
 
+    @torch.no_grad()
+    def render_host_async(self, rays_host, rgb_host, depth_host, white_bg=True, N_samples=-1, image_width=0, **fwd_kw):
+        """Enqueue a whole-frame host-buffer render and return a ticket (ngf_field_render_host_async).  The three
+        pinned CPU tensors must stay untouched until ``host_wait(ticket)``; consecutive frames overlap on the device."""
+        h = self._ensure_handle()
+        lib = _lib.load()
+        self._set_switches(lib, h, **fwd_kw)
+        for t in (rays_host, rgb_host, depth_host):
+            if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("render_host_async takes contiguous fp32 CPU tensors")
+        ticket = C.c_uint64()
+        _lib.check(lib.ngf_field_render_host_async(h, rays_host.data_ptr(), rays_host.shape[0], rays_host.shape[1],
+                                                   int(N_samples), int(bool(white_bg)), int(image_width),
+                                                   rgb_host.data_ptr(), depth_host.data_ptr(), self._mlp_impl,
+                                                   C.byref(ticket)), "ngf_field_render_host_async")
+        return int(ticket.value)
+
+    def host_wait(self, ticket: int):
+        _lib.check(_lib.load().ngf_field_host_wait(self._ensure_handle(), int(ticket)), "ngf_field_host_wait")
+
     def last_stats(self) -> dict:
         """Counters of the last device-side render (forces a stream sync)."""
         st = _lib.NgfStats()

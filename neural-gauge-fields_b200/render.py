@@ -22,6 +22,35 @@ def renderer(rays, field, chunk=4096, N_samples=-1, white_bg=True, is_train=Fals
     return out['rgb_map'], out['depth_map']
 
 
+@torch.no_grad()
+def render_frames(frames, field, N_samples=-1, white_bg=True, image_width=0, depth=2, **fwd_kw):
+    """Render a sequence of frames whose rays live in pinned CPU memory, as the reference's ``evaluation`` loop does
+    (TriPlane/main.py:89-100: ``renderer`` per frame, then ``.cpu()``), but pipelined: while frame k is on the device,
+    frame k+1 is being uploaded and frame k-1 downloaded (ngf_field_render_host_async).  ``frames`` yields [R, C] fp32
+    CPU tensors (pinned for full copy bandwidth); yields (rgb [R,3], depth [R]) pinned CPU tensors in order.  A yielded
+    pair is reused ``depth + 1`` frames later, so consume (or copy) it before advancing that far."""
+    if not fwd_kw and hasattr(field, "gauge_start"):
+        fwd_kw = {"iteration": 30001}
+    bufs, pending = [], []
+    for k, rays in enumerate(frames):
+        if len(bufs) <= k % (depth + 1):
+            bufs.append((torch.empty((rays.shape[0], 3)).pin_memory(), torch.empty((rays.shape[0],)).pin_memory()))
+        rgb, dep = bufs[k % (depth + 1)]
+        if rgb.shape[0] != rays.shape[0]:
+            rgb, dep = torch.empty((rays.shape[0], 3)).pin_memory(), torch.empty((rays.shape[0],)).pin_memory()
+            bufs[k % (depth + 1)] = (rgb, dep)
+        t = field.render_host_async(rays, rgb, dep, white_bg=white_bg, N_samples=N_samples, image_width=image_width,
+                                    **fwd_kw)
+        pending.append((t, rgb, dep))
+        if len(pending) > depth - 1:
+            t0, r0, d0 = pending.pop(0)
+            field.host_wait(t0)
+            yield r0, d0
+    for t0, r0, d0 in pending:
+        field.host_wait(t0)
+        yield r0, d0
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # ray sharding: global ray g belongs to rank (g // block) % world; local index (g // (block*world))*block + g % block
 # ---------------------------------------------------------------------------------------------------------------

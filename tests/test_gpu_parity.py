@@ -66,10 +66,18 @@ def test_image_tiling_and_host_path_do_not_change_results(name):
     # atomics change the summation order of weight*rgb within a ray: a few ulp
     assert (out["rgb_map"].cpu() - rgb0).abs().max() < 1e-5
     assert torch.equal(out["depth_map"].cpu(), depth0)
-    rgb_h, depth_h = f.render_host(rays.pin_memory(), white_bg=case.white_bg, N_samples=case.n_samples,
+    pinned = rays.pin_memory()
+    rgb_h, depth_h = f.render_host(pinned, white_bg=case.white_bg, N_samples=case.n_samples,
                                    image_width=64, **forward_kwargs(case))
     assert (rgb_h - rgb0).abs().max() < 1e-5
     assert torch.equal(depth_h, depth0)
+    # the same host buffers again: replayed as a CUDA graph (ngf_field_render_host) — must give the same frame
+    rgb_keep, depth_keep = rgb_h.clone(), depth_h.clone()
+    rgb_h.zero_(); depth_h.zero_()
+    for _ in range(2):
+        f.render_host(pinned, rgb_h, depth_h, white_bg=case.white_bg, N_samples=case.n_samples, image_width=64,
+                      **forward_kwargs(case))
+        assert (rgb_h - rgb_keep).abs().max() < 1e-5 and torch.equal(depth_h, depth_keep)
 
 
 @pytest.mark.parametrize("variant", ["triplane", "infoinv"])
@@ -166,3 +174,21 @@ def test_repack_after_parameter_update():
     spec = oracle_spec(case, state2, kw, occ)
     o_rgb, _ = R.render(spec, rays, N_samples=64)
     assert (out["rgb_map"].cpu() - o_rgb).abs().max() < RGB_TOL
+
+
+def test_pipelined_frames_equal_single_frames():
+    """render_frames (ngf_field_render_host_async, frames overlapping on the device) returns the same frames as one
+    synchronous render each, in order, also when more frames are submitted than the 8 the library keeps in flight."""
+    import ngf_b200
+    case = K.CASE_BY_NAME["tp_fog_c1"]
+    state, kw, occ, _ = K.build_inputs(case)
+    f = build_cuda_field(case, state, kw, occ)
+    frames = [K.synth.config_rays("C1", p).pin_memory() for p in range(11)]
+    want = []
+    for r in frames:
+        out = f(r.cuda(), white_bg=True, N_samples=64, image_width=64, iteration=30001)
+        want.append((out["rgb_map"].cpu(), out["depth_map"].cpu()))
+    got = [(a.clone(), b.clone()) for a, b in ngf_b200.render_frames(frames, f, N_samples=64, image_width=64, depth=3)]
+    assert len(got) == len(want)
+    for (a, b), (c, d) in zip(got, want):
+        assert (a - c).abs().max() < 1e-5 and torch.equal(b, d)
