@@ -5,7 +5,7 @@
 
 A "step" is one pass of the hot path over one batch of synthetic rays:
   N = 1   one 800x800 TriPlane frame (640 000 rays, 192 samples/ray, gauge on, alpha mask) = BASELINE configs[1];
-  N > 1   a batch of N such frames whose rays are dealt to the ranks in interleaved 2000-ray blocks (each rank renders
+  N > 1   a batch of N such frames whose rays are dealt to the ranks in interleaved 3200-ray blocks (4 image rows) (each rank renders
           640 000 rays per step = weak scaling) followed by ONE NCCL all-gather of the rendered frames (configs[4]).
 Inputs rotate over 16 different camera poses (16 x 15.4 MB of rays per rank > 126 MB L2), so every step reads its rays
 from HBM.  The field (25 MB of packed planes) is model state and stays wherever the hardware keeps it.
@@ -29,7 +29,7 @@ if ROOT not in sys.path:
 import torch
 
 N_POSES = 16
-BLOCK = 2000
+BLOCK = 3200                      # 4 image rows: shards keep whole 8x4-pixel warp tiles
 H = W = 800
 S = 192
 RAYS_PER_FRAME = H * W
@@ -207,15 +207,18 @@ def main():
     img_w = W if world == 1 else 0
     n_batch = world * RAYS_PER_FRAME
 
+    sharded = ngf_b200.ShardedFrameRenderer(field, n_batch, BLOCK) if world > 1 else None
+
     def step_device(rays):
-        out = field(rays, white_bg=True, N_samples=S, iteration=30001, image_width=img_w)
         if world == 1:
+            out = field(rays, white_bg=True, N_samples=S, iteration=30001, image_width=img_w)
             return out["rgb_map"], out["depth_map"]
-        local_res = torch.cat([out["rgb_map"], out["depth_map"][:, None]], 1)
-        return frame_allgather(local_res, n_batch, BLOCK), None
+        # render my shard; the all-gather of this batch overlaps the kernels of the next one (double-buffered)
+        return sharded.submit(rays, N_samples=S, white_bg=True, iteration=30001, image_width=W), None
 
     def barrier():
         if world > 1:
+            torch.cuda.synchronize()          # includes the side stream of the overlapped all-gathers
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -269,10 +272,9 @@ def main():
         res_h = torch.empty((n_local, 4)).pin_memory()
         def step_e2e(i):
             stage.copy_(host[i % N_POSES], non_blocking=True)
-            out = field(stage, white_bg=True, N_samples=S, iteration=30001)
-            loc = torch.cat([out["rgb_map"], out["depth_map"][:, None]], 1)
-            frame_allgather(loc, n_batch, BLOCK)
-            res_h.copy_(loc, non_blocking=True)
+            t = sharded.submit(stage, N_samples=S, white_bg=True, iteration=30001, image_width=W)
+            frame = sharded.result(t)
+            res_h.copy_(frame[:n_local], non_blocking=True)      # read back one shard's worth of the gathered batch
             torch.cuda.synchronize()
         d2h = n_local * 16
     for i in range(3):

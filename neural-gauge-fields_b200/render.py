@@ -128,3 +128,59 @@ def render_frame_sharded(rays, field, block=2048, N_samples=-1, white_bg=True, g
     rgb, depth = renderer(mine, field, N_samples=N_samples, white_bg=white_bg, **fwd_kw)
     local = torch.cat([rgb, depth[:, None]], 1)
     return frame_allgather(local, R, block, group)
+
+
+class ShardedFrameRenderer:
+    """Ray-sharded multi-GPU rendering with the frame all-gather overlapped with the next frame's kernels.
+
+    Every rank renders its interleaved shard of a ray batch; the all-gather of the [rays, 4] (rgb, depth)
+    results and the re-ordering into frame order run on a side stream, double-buffered, so the collective of batch k
+    overlaps the march / colour kernels of batch k+1.  One NCCL all-gather per batch, no other collective.
+
+        r = ShardedFrameRenderer(field, n_rays_total, block)
+        t = r.submit(my_shard_of_rays)          # returns at once
+        frame = r.result(t)                      # [n_rays_total, 4] on this rank's device, ordered as the input batch
+    """
+
+    def __init__(self, field, n_rays_total: int, block: int = 2000, group=None):
+        import torch.distributed as dist
+        self.field, self.n, self.block, self.group = field, int(n_rays_total), int(block), group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = field.device
+        self.max_shard = -(-(-(-self.n // block)) // self.world) * block
+        self.comm = torch.cuda.Stream(device=dev)
+        self.local = [torch.zeros((self.max_shard, 4), device=dev) for _ in range(2)]
+        self.gathered = [torch.empty((self.world, self.max_shard, 4), device=dev) for _ in range(2)]
+        self.frame = [torch.empty((self.n, 4), device=dev) for _ in range(2)]
+        self.rendered = [torch.cuda.Event() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        self.count = 0
+
+    @torch.no_grad()
+    def submit(self, rays_local, N_samples=-1, white_bg=True, **fwd_kw):
+        import torch.distributed as dist
+        b = self.count % 2
+        cur = torch.cuda.current_stream(self.field.device)
+        cur.wait_event(self.done[b])                       # buffers of this parity are free again
+        rgb, depth = renderer(rays_local, self.field, N_samples=N_samples, white_bg=white_bg, **fwd_kw)
+        n = rgb.shape[0]
+        torch.cat([rgb, depth[:, None]], 1, out=self.local[b][:n])
+        self.rendered[b].record(cur)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.rendered[b])
+            dist.all_gather_into_tensor(self.gathered[b].view(self.world * self.max_shard, 4), self.local[b],
+                                        group=self.group)
+            src = self.gathered[b]
+            _lib.check(_lib.load().ngf_shard_scatter(src.data_ptr(), self.n, 4, self.block, self.world, self.max_shard,
+                                                     self.frame[b].data_ptr(), int(self.comm.cuda_stream)))
+            self.done[b].record(self.comm)
+        self.count += 1
+        return self.count - 1
+
+    def result(self, ticket: int):
+        """Make the current stream wait for batch ``ticket`` (it must be one of the last two submitted) and return its
+        frame buffer; the buffer is overwritten two submissions later."""
+        if ticket < self.count - 2 or ticket >= self.count:
+            raise ValueError("only the last two submitted batches are still buffered")
+        torch.cuda.current_stream(self.field.device).wait_event(self.done[ticket % 2])
+        return self.frame[ticket % 2]

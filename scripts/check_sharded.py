@@ -28,6 +28,17 @@ gold = load_golden("tp_fog_c1")
 e_rgb = float(np.abs(frame[:, :3].cpu().numpy() - gold["rgb"]).max())
 e_dep = float(np.abs(frame[:, 3].cpu().numpy() - gold["depth"]).max())
 ok = e_rgb < 1e-3 and e_dep < 2e-3
+# the overlapped, double-buffered variant: three batches in a row, each must equal the same golden frame
+from ngf_b200.render import shard_rays
+sr = ngf_b200.ShardedFrameRenderer(f, rays.shape[0], block=96)
+mine = shard_rays(rays.to(dev), 96, dist.get_rank(), dist.get_world_size())
+tickets = []
+for k in range(3):
+    tickets.append(sr.submit(mine, N_samples=case.n_samples, white_bg=True, iteration=30001))
+    fr = sr.result(tickets[-1]).clone()
+    torch.cuda.synchronize()
+    ok = ok and float(np.abs(fr[:, :3].cpu().numpy() - gold["rgb"]).max()) < 1e-3 and \
+        float(np.abs(fr[:, 3].cpu().numpy() - gold["depth"]).max()) < 2e-3
 print(f"rank {dist.get_rank()}/{dist.get_world_size()}: rgb {e_rgb:.2e} depth {e_dep:.2e} {'OK' if ok else 'MISMATCH'}", flush=True)
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
