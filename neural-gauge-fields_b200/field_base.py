@@ -414,66 +414,71 @@ class Base(torch.nn.Module):
                                                          out.data_ptr(), _cuda_stream_ptr(self.device)))
         return out
 
-    # ------------------------------------------------------------------ occupancy maintenance (FieldBase.py:140-215)
+    # ------------------------------------------------------------------ occupancy maintenance (FieldBase.py:140-246)
+    # These run on the same point-wise kernels as the renderer (ngf_field_sigma_world / sample_ray / alpha_keep); the whole
+    # lattice or ray set goes to the device in one call instead of the reference's per-slice / per-chunk Python loops.
     @torch.no_grad()
     def compute_alpha(self, xyz_locs, length=1, **kw):
-        """Reference: Base.compute_alpha (FieldBase.py:140-159): alpha = 1 - exp(-sigma * length) with the gauge off."""
+        """Reference: Base.compute_alpha (FieldBase.py:140-159): alpha = 1 - exp(-sigma * length), field evaluated with
+        the gauge off and the current alpha mask applied."""
         self._apply_alpha_kw(**kw)
-        sigma = self._sigma_world(xyz_locs.view(-1, 3), use_gauge=False)
+        sigma = self._sigma_world(xyz_locs.reshape(-1, 3), use_gauge=False)
         return (1 - torch.exp(-sigma * length)).view(xyz_locs.shape[:-1])
 
     def _apply_alpha_kw(self, **kw):
         pass
 
+    def _lattice(self, gs):
+        """World positions of the gs[0] x gs[1] x gs[2] lattice spanning the box, [gx, gy, gz, 3] on the device.  The
+        per-axis blend aabb0*(1-s) + aabb1*s with s = torch.linspace(0, 1, g) is evaluated on the CPU exactly as
+        FieldBase.py:165-171 does, then broadcast."""
+        lo, hi = self.aabb[0].detach().float().cpu(), self.aabb[1].detach().float().cpu()
+        axes = []
+        for k in range(3):
+            t = torch.linspace(0, 1, gs[k])
+            axes.append((lo[k] * (1 - t) + hi[k] * t).to(self.device))
+        gx, gy, gz = torch.meshgrid(axes[0], axes[1], axes[2], indexing="ij")
+        return torch.stack((gx, gy, gz), -1)
+
     @torch.no_grad()
     def getDenseAlpha(self, gridSize=None, **kw):
-        """Reference: Base.getDenseAlpha (FieldBase.py:161-177)."""
-        gridSize = self.gridSize if gridSize is None else gridSize
-        gs = [int(g) for g in gridSize]
-        samples = torch.stack(torch.meshgrid(torch.linspace(0, 1, gs[0]), torch.linspace(0, 1, gs[1]),
-                                             torch.linspace(0, 1, gs[2]), indexing="ij"), -1).to(self.device)
-        dense_xyz = self.aabb[0] * (1 - samples) + self.aabb[1] * samples
-        alpha = torch.zeros_like(dense_xyz[..., 0])
-        for i in range(gs[0]):
-            alpha[i] = self.compute_alpha(dense_xyz[i].view(-1, 3), self.stepSize, **kw).view((gs[1], gs[2]))
+        """Reference: Base.getDenseAlpha (FieldBase.py:161-177) -> (alpha [gx,gy,gz], dense_xyz [gx,gy,gz,3])."""
+        gs = [int(g) for g in (self.gridSize if gridSize is None else gridSize)]
+        dense_xyz = self._lattice(gs)
+        alpha = self.compute_alpha(dense_xyz.view(-1, 3), self.stepSize, **kw).view(gs)
         return alpha, dense_xyz
 
     @torch.no_grad()
     def updateAlphaMask(self, gridSize=(200, 200, 200), **kw):
-        """Reference: Base.updateAlphaMask (FieldBase.py:179-215): dense alpha -> 3x3x3 max-pool -> threshold ->
-        new AlphaGridMask; returns the tight box of the occupied voxels."""
+        """Reference: Base.updateAlphaMask (FieldBase.py:179-215): dense alpha, 3x3x3 dilation, threshold at
+        alphaMask_thres -> new AlphaGridMask over the current box; returns the tight box of the occupied lattice points."""
         gs = [int(g) for g in gridSize]
         alpha, dense_xyz = self.getDenseAlpha(gs, **kw)
-        dense_xyz = dense_xyz.transpose(0, 2).contiguous()
-        alpha = alpha.clamp(0, 1).transpose(0, 2).contiguous()[None, None]
-        alpha = F.max_pool3d(alpha, kernel_size=3, padding=1, stride=1).view(gs[::-1])
-        alpha[alpha >= self.alphaMask_thres] = 1
-        alpha[alpha < self.alphaMask_thres] = 0
-        self.alphaMask = AlphaGridMask(self.device, self.aabb, alpha)
-        valid_xyz = dense_xyz[alpha > 0.5]
-        new_aabb = torch.stack((valid_xyz.amin(0), valid_xyz.amax(0)))
-        return new_aabb
+        # the mask volume is indexed [z, y, x] (FieldBase.py:183-184)
+        vol = alpha.clamp(0, 1).permute(2, 1, 0).contiguous()
+        vol = F.max_pool3d(vol[None, None], kernel_size=3, padding=1, stride=1)[0, 0]
+        occupied = vol >= self.alphaMask_thres
+        self.alphaMask = AlphaGridMask(self.device, self.aabb, occupied.float())
+        pts = dense_xyz.permute(2, 1, 0, 3)[occupied]
+        return torch.stack((pts.amin(0), pts.amax(0)))
 
     @torch.no_grad()
     def filtering_rays(self, all_rays, all_rgbs, N_samples=256, chunk=10240 * 5, bbox_only=False):
-        """Reference: Base.filtering_rays (FieldBase.py:217-246).  Keeps rays that hit the box (bbox_only) or pass
-        through an occupied cell."""
-        N = int(torch.tensor(all_rays.shape[:-1]).prod())
-        flat = all_rays.reshape(N, all_rays.shape[-1])
-        keep = []
-        for s in range(0, N, chunk):
-            rays_chunk = flat[s:s + chunk].to(self.device)
-            rays_o, rays_d = rays_chunk[..., :3], rays_chunk[..., 3:6]
+        """Reference: Base.filtering_rays (FieldBase.py:217-246): keep the rays that cross the box (bbox_only) or that
+        have at least one sample the alpha mask keeps."""
+        flat = all_rays.reshape(-1, all_rays.shape[-1])
+        keep = torch.empty(flat.shape[0], dtype=torch.bool)
+        step = int(chunk) * 8                                  # the device takes far larger pieces than the reference's
+        for s in range(0, flat.shape[0], step):
+            r = flat[s:s + step].to(self.device)
+            o, d = r[:, :3], r[:, 3:6]
             if bbox_only:
-                vec = torch.where(rays_d == 0, torch.full_like(rays_d, 1e-6), rays_d)
-                rate_a = (self.aabb[1] - rays_o) / vec
-                rate_b = (self.aabb[0] - rays_o) / vec
-                t_min = torch.minimum(rate_a, rate_b).amax(-1)
-                t_max = torch.maximum(rate_a, rate_b).amin(-1)
-                mask = t_max > t_min
+                safe = torch.where(d == 0, torch.full_like(d, 1e-6), d)
+                ta, tb = (self.aabb[1] - o) / safe, (self.aabb[0] - o) / safe
+                hit = torch.maximum(ta, tb).amin(-1) > torch.minimum(ta, tb).amax(-1)
             else:
-                pts, _, _ = self.sample_ray(rays_o, rays_d, N_samples=N_samples, is_train=False)
-                mask = self._alpha_keep(pts.view(-1, 3)).view(pts.shape[:-1]).any(-1)
-            keep.append(mask.cpu())
-        mask_filtered = torch.cat(keep).view(all_rgbs.shape[:-1])
-        return all_rays[mask_filtered], all_rgbs[mask_filtered]
+                pts, _, _ = self.sample_ray(o, d, N_samples=N_samples, is_train=False)
+                hit = self._alpha_keep(pts.view(-1, 3)).view(pts.shape[:-1]).any(-1)
+            keep[s:s + step] = hit.cpu()
+        keep = keep.view(all_rgbs.shape[:-1])
+        return all_rays[keep], all_rgbs[keep]

@@ -88,6 +88,25 @@ def make_pointwise(variant: str) -> str:
     return path
 
 
+@torch.no_grad()
+def make_alphamask() -> str:
+    """Reference occupancy maintenance on a 48^3 lattice: updateAlphaMask (FieldBase.py:179-215), then filtering_rays
+    (FieldBase.py:217-246) with and without the mask."""
+    case = K.Case("alphamask_triplane", kind="hull", mask=False)
+    field, state, kw, occ, rays = build_reference_field(case)
+    new_aabb = ref_loader.quiet(field.updateAlphaMask, (48, 48, 48))
+    vol = field.alphaMask.alpha_volume[0, 0]
+    rgbs = torch.zeros(rays.shape[0], 3)
+    kept_mask = ref_loader.quiet(field.filtering_rays, rays, rgbs, N_samples=64)[0]
+    kept_bbox = ref_loader.quiet(field.filtering_rays, rays, rgbs, bbox_only=True)[0]
+    path = K.golden_path(case.name)
+    np.savez_compressed(path, volume_bits=np.packbits(vol.numpy() > 0), volume_shape=np.array(vol.shape),
+                        new_aabb=new_aabb.numpy(), n_kept_mask=np.int64(kept_mask.shape[0]),
+                        n_kept_bbox=np.int64(kept_bbox.shape[0]), kept_mask_first=kept_mask[:16].numpy(),
+                        fingerprint=K.fingerprint(state, rays, None), torch_version=torch.__version__)
+    return path
+
+
 def build_reference_neutex(case: K.NeutexCase):
     """The reference's UV-Mapping sub-modules (decoder.py, gauge_fields.py) with the synthetic state loaded.
     NeuTex.forward itself cannot run as shipped, so the modules are wired exactly as
@@ -142,9 +161,12 @@ def make_neutex(case: K.NeutexCase) -> str:
 def main(argv):
     if not ref_loader.available():
         raise SystemExit("reference tree not found: golden vectors can only be generated in the build container")
-    names = argv or [c.name for c in K.CASES] + ["pointwise_triplane", "pointwise_infoinv"] + [c.name for c in K.NEUTEX_CASES]
+    names = argv or [c.name for c in K.CASES] + ["pointwise_triplane", "pointwise_infoinv", "alphamask_triplane"] + \
+        [c.name for c in K.NEUTEX_CASES]
     for n in names:
-        if n in K.NEUTEX_BY_NAME:
+        if n == "alphamask_triplane":
+            p = make_alphamask()
+        elif n in K.NEUTEX_BY_NAME:
             p = make_neutex(K.NEUTEX_BY_NAME[n])
         elif n.startswith("pointwise_"):
             p = make_pointwise(n.split("_", 1)[1])
