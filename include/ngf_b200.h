@@ -175,6 +175,24 @@ int ngf_field_render_host_async(NgfField f, const float* rays_host, int64_t n_ra
                                 float* depth_host, int32_t mlp_impl, uint64_t* ticket);
 int ngf_field_host_wait(NgfField f, uint64_t ticket);
 
+/*
+ * On-device ray generation: the rays of a pinhole camera are produced inside the march kernel,
+ * so a frame needs 18 numbers instead of a 15 MB ray tensor.  Replaces get_ray_directions + the unit normalisation of
+ * blender.py:52 + get_rays (TriPlane/dataLoader/ray_utils.py:24-42,66-87; blender.py:46-52) as evaluation_path uses
+ * them per frame (TriPlane/main.py:155-161): pixel (i, j) -> ((i+0.5-cx)/fx, (j+0.5-cy)/fy, 1) / |.| rotated by
+ * c2w[:3,:3], origin c2w[:3,3]; rays are the row-major pixels, results as in ngf_field_render with tile_w = width.
+ */
+typedef struct NgfCamera {
+  float c2w[12];          /* row-major [3][4] camera-to-world */
+  float fx, fy, cx, cy;   /* focal lengths and principal point in pixels (blender.py: fx = fy = focal, cx = W/2, cy = H/2) */
+  int32_t width, height;
+} NgfCamera;
+int ngf_field_render_camera(NgfField f, const NgfCamera* camera, int32_t n_samples, int32_t white_bg, float* rgb_dev,
+                            float* depth_dev, float* acc_dev, int32_t mlp_impl, void* stream);
+/* Same into HOST buffers, pipelined like ngf_field_render_host_async (wait with ngf_field_host_wait). */
+int ngf_field_render_camera_host_async(NgfField f, const NgfCamera* camera, int32_t n_samples, int32_t white_bg,
+                                       float* rgb_host, float* depth_host, int32_t mlp_impl, uint64_t* ticket);
+
 /* Per-call switches of forward(): TriPlane `iteration >= gauge_start` (TriPlane/models/Field.py:58) and InfoInv
  * `infoinv=` (InfoInv/models/FieldBase.py:228).  They only flip a flag in the handle; no repack. */
 int ngf_field_set_gauge(NgfField f, int32_t on);

@@ -47,6 +47,11 @@ class NgfNeutexDesc(C.Structure):
                 ("tex_c", C.c_int32)]
 
 
+class NgfCamera(C.Structure):
+    _fields_ = [("c2w", C.c_float * 12), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("width", C.c_int32), ("height", C.c_int32)]
+
+
 class NgfStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("samples_in_box", C.c_uint64), ("samples_density", C.c_uint64),
                 ("samples_colour", C.c_uint64), ("mlp_tiles", C.c_uint64)]
@@ -66,6 +71,10 @@ SIGNATURES = {
                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
     "ngf_field_render_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                               C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]),
+    "ngf_field_render_camera": (C.c_int, [C.c_void_p, C.POINTER(NgfCamera), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int32, C.c_void_p]),
+    "ngf_field_render_camera_host_async": (C.c_int, [C.c_void_p, C.POINTER(NgfCamera), C.c_int32, C.c_int32, C.c_void_p,
+                                                     C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]),
     "ngf_field_host_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
     "ngf_field_set_gauge": (C.c_int, [C.c_void_p, C.c_int32]),
     "ngf_field_set_infoinv": (C.c_int, [C.c_void_p, C.c_int32]),

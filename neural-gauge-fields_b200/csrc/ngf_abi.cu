@@ -508,7 +508,7 @@ static int ensure_queue(QEntry** q, long long* cap, long long want, cudaStream_t
 
 static int render_dev(NgfField h, const float* rays, long long n_rays, int ray_stride, int n_samples, int white_bg,
                       int tile_w, float* rgb, float* depth, float* acc, unsigned int* counters, QEntry** queue,
-                      long long* queue_cap, int mlp_impl, cudaStream_t st) {
+                      long long* queue_cap, int mlp_impl, cudaStream_t st, const CamDev* cam = nullptr) {
   if (n_rays == 0) return NGF_OK;
   const int S = n_samples > 0 ? n_samples : h->n_samples_default;
   if (S < 1) return fail(NGF_EINVAL, "n_samples resolves to %d", S);
@@ -526,7 +526,9 @@ static int render_dev(NgfField h, const float* rays, long long n_rays, int ray_s
   for (long long s0 = 0; s0 < n_rays; s0 += per) {
     const long long n = (n_rays - s0) < per ? (n_rays - s0) : per;
     RenderArgs a{};
-    a.rays = rays + s0 * ray_stride; a.n_rays = n; a.ray_stride = ray_stride;
+    a.rays = rays ? rays + s0 * ray_stride : nullptr; a.n_rays = n; a.ray_stride = ray_stride;
+    a.cam_on = cam ? 1 : 0;
+    if (cam) { a.cam = *cam; a.cam.base = cam->base + s0; }
     a.S = S;
     a.white_bg = white_bg ? 1 : 0;
     if (img) {
@@ -590,7 +592,7 @@ int ngf_field_render(NgfField h, const float* rays_dev, int64_t n_rays, int32_t 
 // stream capture).
 static int host_enqueue(NgfField h, const float* rays_host, long long n_rays, int ray_stride, int n_samples, int white_bg,
                         int tile_w, float* rgb_host, float* depth_host, int mlp_impl, long long chunk, bool img,
-                        bool join) {
+                        bool join, const CamDev* cam = nullptr) {
   CU(cudaEventRecord(h->ev_fork, h->s_in));
   CU(cudaStreamWaitEvent(h->s_out, h->ev_fork, 0));
   for (int i = 0; i < kHostComp; ++i) CU(cudaStreamWaitEvent(h->chunk[i].stream, h->ev_fork, 0));
@@ -599,15 +601,18 @@ static int host_enqueue(NgfField h, const float* rays_host, long long n_rays, in
     const long long n = (n_rays - s) < chunk ? (n_rays - s) : chunk;
     HostChunk& c = h->chunk[ci];
     // upload: the slot's ray buffer is free once the kernels of its previous chunk are done
-    CU(cudaStreamWaitEvent(h->s_in, c.ev_comp, 0));
-    CU(cudaMemcpyAsync(c.rays, rays_host + s * ray_stride, (size_t)n * ray_stride * sizeof(float),
-                       cudaMemcpyHostToDevice, h->s_in));
-    CU(cudaEventRecord(c.ev_in, h->s_in));
-    // kernels: need the rays, and the slot's result buffers must have been downloaded
-    CU(cudaStreamWaitEvent(c.stream, c.ev_in, 0));
-    CU(cudaStreamWaitEvent(c.stream, c.ev_out, 0));
-    int rc = render_dev(h, c.rays, n, ray_stride, n_samples, white_bg, img ? tile_w : 0, c.rgb, c.depth, c.acc,
-                        c.counters, &c.queue, &c.queue_cap, mlp_impl, c.stream);
+    if (!cam) {
+      CU(cudaStreamWaitEvent(h->s_in, c.ev_comp, 0));
+      CU(cudaMemcpyAsync(c.rays, rays_host + s * ray_stride, (size_t)n * ray_stride * sizeof(float),
+                         cudaMemcpyHostToDevice, h->s_in));
+      CU(cudaEventRecord(c.ev_in, h->s_in));
+      CU(cudaStreamWaitEvent(c.stream, c.ev_in, 0));     // kernels need the rays ...
+    }
+    CU(cudaStreamWaitEvent(c.stream, c.ev_out, 0));      // ... and the slot's result buffers must have been downloaded
+    CamDev cam_chunk{};
+    if (cam) { cam_chunk = *cam; cam_chunk.base = s; }
+    int rc = render_dev(h, cam ? nullptr : c.rays, n, ray_stride, n_samples, white_bg, img ? tile_w : 0, c.rgb, c.depth,
+                        c.acc, c.counters, &c.queue, &c.queue_cap, mlp_impl, c.stream, cam ? &cam_chunk : nullptr);
     if (rc) return rc;
     CU(cudaEventRecord(c.ev_comp, c.stream));
     // download
@@ -631,9 +636,9 @@ static int host_enqueue(NgfField h, const float* rays_host, long long n_rays, in
 // Validate, pick the chunk size and make sure the slot buffers exist.
 static int host_prepare(NgfField h, const float* rays_host, int64_t n_rays, int32_t ray_stride, int32_t tile_w,
                         float* rgb_host, float* depth_host, int32_t mlp_impl, bool pipelined, long long* chunk_out,
-                        bool* img_out) {
+                        bool* img_out, bool camera = false) {
   if (n_rays < 0 || n_rays > 0x7fffffffll) return fail(NGF_EINVAL, "n_rays=%lld", (long long)n_rays);
-  if (!rays_host || !rgb_host || !depth_host) return fail(NGF_EINVAL, "NULL ray/output pointer");
+  if ((!rays_host && !camera) || !rgb_host || !depth_host) return fail(NGF_EINVAL, "NULL ray/output pointer");
   if (ray_stride < 6) return fail(NGF_EINVAL, "ray_stride=%d (< 6)", ray_stride);
   if (mlp_impl != NGF_MLP_TCGEN05 && mlp_impl != NGF_MLP_SIMT) return fail(NGF_EINVAL, "mlp_impl=%d", mlp_impl);
   // Chunking (whole groups of 4 image rows when the image width is known).  A single synchronous frame overlaps its own
@@ -759,6 +764,68 @@ int ngf_field_render_host_async(NgfField h, const float* rays_host, int64_t n_ra
                       chunk, img, false);
     if (rc) return rc;
   }
+  CU(cudaEventRecord(done, h->s_out));
+  *ticket = t;
+  ++h->next_ticket;
+  return NGF_OK;
+}
+
+static int check_camera(const NgfCamera* c, CamDev* out) {
+  if (!c) return fail(NGF_EINVAL, "camera is NULL");
+  if (c->width < 1 || c->height < 1 || (long long)c->width * c->height > 0x7fffffffll) return fail(NGF_EINVAL, "camera image %dx%d", c->width, c->height);
+  if (!(c->fx != 0.f) || !(c->fy != 0.f)) return fail(NGF_EINVAL, "camera focal length is zero");
+  memcpy(out->c2w, c->c2w, sizeof(out->c2w));
+  out->fx = c->fx; out->fy = c->fy; out->cx = c->cx; out->cy = c->cy;
+  out->W = c->width; out->H = c->height;
+  out->base = 0;
+  return NGF_OK;
+}
+
+int ngf_field_render_camera(NgfField h, const NgfCamera* camera, int32_t n_samples, int32_t white_bg, float* rgb_dev,
+                            float* depth_dev, float* acc_dev, int32_t mlp_impl, void* stream) {
+  if (!h) return fail(NGF_EINVAL, "field is NULL");
+  CamDev cam{};
+  int rc = check_camera(camera, &cam);
+  if (rc) return rc;
+  if (!rgb_dev || !depth_dev) return fail(NGF_EINVAL, "NULL output pointer");
+  if (mlp_impl != NGF_MLP_TCGEN05 && mlp_impl != NGF_MLP_SIMT) return fail(NGF_EINVAL, "mlp_impl=%d", mlp_impl);
+  DeviceGuard g(h->device);
+  if (!g.ok) return fail(NGF_ECUDA, "cannot select device %d", h->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long n_rays = (long long)cam.W * cam.H;
+  float* acc = acc_dev;
+  if (!acc) {
+    if (h->acc_cap < n_rays) {
+      CU(cudaStreamSynchronize(st));
+      cudaFree(h->acc_ws);
+      h->acc_ws = nullptr; h->acc_cap = 0;
+      CU(dev_alloc(&h->acc_ws, (size_t)n_rays));
+      h->acc_cap = n_rays;
+    }
+    acc = h->acc_ws;
+  }
+  return render_dev(h, nullptr, n_rays, 6, n_samples, white_bg, cam.W, rgb_dev, depth_dev, acc, h->counters, &h->queue,
+                    &h->queue_cap, mlp_impl, st, &cam);
+}
+
+int ngf_field_render_camera_host_async(NgfField h, const NgfCamera* camera, int32_t n_samples, int32_t white_bg,
+                                       float* rgb_host, float* depth_host, int32_t mlp_impl, uint64_t* ticket) {
+  if (!h || !ticket) return fail(NGF_EINVAL, "NULL argument");
+  CamDev cam{};
+  int rc = check_camera(camera, &cam);
+  if (rc) return rc;
+  DeviceGuard g(h->device);
+  if (!g.ok) return fail(NGF_ECUDA, "cannot select device %d", h->device);
+  const long long n_rays = (long long)cam.W * cam.H;
+  long long chunk = 0;
+  bool img = false;
+  rc = host_prepare(h, nullptr, n_rays, 6, cam.W, rgb_host, depth_host, mlp_impl, true, &chunk, &img, true);
+  if (rc) return rc;
+  const unsigned long long t = h->next_ticket;
+  cudaEvent_t done = h->frame_done[t % 8];
+  CU(cudaEventSynchronize(done));
+  rc = host_enqueue(h, nullptr, n_rays, 6, n_samples, white_bg, cam.W, rgb_host, depth_host, mlp_impl, chunk, img, false, &cam);
+  if (rc) return rc;
   CU(cudaEventRecord(done, h->s_out));
   *ticket = t;
   ++h->next_ticket;

@@ -66,6 +66,30 @@ struct FieldDev {
   const float* tail;
 };
 
+// Pinhole camera for on-device ray generation (TriPlane/dataLoader/ray_utils.py:24-42,66-87 + blender.py:46-52)
+struct CamDev {
+  float c2w[12];                  // row-major [3][4] camera-to-world
+  float fx, fy, cx, cy;
+  int W, H;
+  long long base;                 // pixel index of local ray 0 (frames rendered in row blocks)
+};
+
+// Ray of pixel `ray` (row-major): camera-space direction ((i+0.5-cx)/fx, (j+0.5-cy)/fy, 1), normalised
+// (blender.py:52), rotated by c2w[:3,:3] (get_rays: directions @ c2w[:3,:3].T); origin = c2w[:3,3].
+__device__ __forceinline__ void camera_ray(const CamDev& c, long long ray, float o[3], float d[3]) {
+  ray += c.base;
+  const int j = (int)(ray / c.W), i = (int)(ray - (long long)j * c.W);
+  const float x = __fdiv_rn(__fsub_rn(__fadd_rn((float)i, 0.5f), c.cx), c.fx);
+  const float y = __fdiv_rn(__fsub_rn(__fadd_rn((float)j, 0.5f), c.cy), c.fy);
+  const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), 1.f));
+  const float dx = __fdiv_rn(x, nrm), dy = __fdiv_rn(y, nrm), dz = __fdiv_rn(1.f, nrm);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    d[k] = __fadd_rn(__fadd_rn(__fmul_rn(dx, c.c2w[4 * k]), __fmul_rn(dy, c.c2w[4 * k + 1])), __fmul_rn(dz, c.c2w[4 * k + 2]));
+    o[k] = c.c2w[4 * k + 3];
+  }
+}
+
 constexpr int kDmlpFloats = 32 * 72 + 32 + 32 * 32 + 32 + 32 + 1;   // 3457
 constexpr int kTailFloats = 3 * 64 + 64 + 4;                        // 260
 

@@ -9,6 +9,8 @@
 namespace ngf {
 
 struct RenderArgs {
+  CamDev cam;                  // cam_on: rays are generated from this camera (pixel = ray index), `rays` is unused
+  int cam_on;
   const float* rays;
   long long n_rays;
   int ray_stride;

@@ -91,10 +91,15 @@ __global__ void __launch_bounds__(kMarchThreads, V == 0 ? 3 : 2) ngf_march_kerne
         if (ray >= a.n_rays) ray = -1;
       }
       if (ray >= 0) {
-        const float* rp = a.rays + ray * a.ray_stride;
+        if (a.cam_on) {
+          camera_ray(a.cam, ray, o, d);
+          last_col = d[2];                               // a 6-column ray's last column (FieldBase.py:306)
+        } else {
+          const float* rp = a.rays + ray * a.ray_stride;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { o[k] = __ldg(rp + k); d[k] = __ldg(rp + 3 + k); }
-        last_col = __ldg(rp + a.ray_stride - 1);
+          for (int k = 0; k < 3; ++k) { o[k] = __ldg(rp + k); d[k] = __ldg(rp + 3 + k); }
+          last_col = __ldg(rp + a.ray_stride - 1);
+        }
         t0 = ray_t0(f, o, d);
         int lo_i, hi_i;
         ray_index_range(f, o, d, t0, S, lo_i, hi_i);
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, 2) ngf_colour_kernel(const __grid_co
       q[threadIdx.x] = v;
     }
     __syncthreads();
-    mlp_tile<V, IMPL, true>(f, smem, 0u, phase, a.rays + 3, a.ray_stride, a.rgb);
+    mlp_tile<V, IMPL, true>(f, smem, 0u, phase, a.rays + 3, a.ray_stride, a.rgb, a.cam_on ? &a.cam : nullptr);
   }
   mlp_teardown<IMPL>(smem, L::offCtl);
   if (threadIdx.x == 0) atomicAdd(a.stats + 3, (unsigned long long)done);

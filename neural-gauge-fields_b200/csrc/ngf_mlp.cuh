@@ -270,11 +270,12 @@ __device__ __forceinline__ void blend8(const __half* __restrict__ base, int chan
 
 // ----------------------------------------------------------------------------------------------------------
 // Fill the A tile rows [0,128) from queue slots head .. head+127.
-//   dir / dir_stride : view direction of entry id is dir[id*dir_stride + 0..2]
+//   dir / dir_stride : view direction of entry id is dir[id*dir_stride + 0..2]; with a camera (cam != nullptr) it is
+//                      regenerated from the pixel index instead
 // ----------------------------------------------------------------------------------------------------------
 template <int V>
 __device__ __forceinline__ void mlp_gather(const FieldDev& f, uint8_t* smem, uint32_t head,
-                                           const float* __restrict__ dir, int dir_stride) {
+                                           const float* __restrict__ dir, int dir_stride, const CamDev* cam) {
   using L = MlpSmem<V>;
   constexpr int AC = Cfg<V>::AC, F = Cfg<V>::F;
   const QEntry* q = reinterpret_cast<const QEntry*>(smem + L::offQueue);
@@ -333,8 +334,14 @@ __device__ __forceinline__ void mlp_gather(const FieldDev& f, uint8_t* smem, uin
     const QEntry& e = q[(head + m) & (kQueueCap - 1)];
     float v[16];
     if (e.id >= 0) {
-      const float* dp = dir + (size_t)e.id * dir_stride;
-      float d[3] = {__ldg(dp), __ldg(dp + 1), __ldg(dp + 2)};
+      float d[3];
+      if (cam) {
+        float o_unused[3];
+        camera_ray(*cam, e.id, o_unused, d);
+      } else {
+        const float* dp = dir + (size_t)e.id * dir_stride;
+        d[0] = __ldg(dp); d[1] = __ldg(dp + 1); d[2] = __ldg(dp + 2);
+      }
       v[0] = d[0]; v[1] = d[1]; v[2] = d[2];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -369,7 +376,8 @@ __device__ __forceinline__ void mlp_gather(const FieldDev& f, uint8_t* smem, uin
 // ----------------------------------------------------------------------------------------------------------
 template <int V, int IMPL, bool ATOMIC>
 __device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint32_t head, uint32_t& phase,
-                                         const float* __restrict__ dir, int dir_stride, float* __restrict__ out) {
+                                         const float* __restrict__ dir, int dir_stride, float* __restrict__ out,
+                                         const CamDev* cam = nullptr) {
   using L = MlpSmem<V>;
   constexpr int NKC = L::NKC;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -380,7 +388,7 @@ __device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint3
   uint8_t* H = smem + L::offH;
   float acc[32];
 
-  mlp_gather<V>(f, smem, head, dir, dir_stride);
+  mlp_gather<V>(f, smem, head, dir, dir_stride, cam);
 
   if (IMPL == 0) {
     fence_async_smem();

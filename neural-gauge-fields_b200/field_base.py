@@ -318,6 +318,49 @@ class Base(torch.nn.Module):
                                                    C.byref(ticket)), "ngf_field_render_host_async")
         return int(ticket.value)
 
+    @staticmethod
+    def _camera(c2w, H, W, focal, center=None):
+        cam = _lib.NgfCamera()
+        m = torch.as_tensor(c2w, dtype=torch.float32).cpu().reshape(-1)[:12]
+        for k in range(12):
+            cam.c2w[k] = float(m[k])
+        fx, fy = (focal if isinstance(focal, (tuple, list)) else (focal, focal))
+        cx, cy = center if center is not None else (W / 2, H / 2)           # ray_utils.py:38
+        cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height = float(fx), float(fy), float(cx), float(cy), int(W), int(H)
+        return cam
+
+    @torch.no_grad()
+    def render_camera(self, c2w, H, W, focal, center=None, white_bg=True, N_samples=-1, **fwd_kw):
+        """Render the H x W frame of a pinhole camera with its rays generated on the device (ngf_field_render_camera):
+        what evaluation_path does with get_rays(directions, c2w) + renderer (TriPlane/main.py:155-161).
+        -> {'rgb_map': [H*W,3], 'depth_map': [H*W]} on the field's device."""
+        h = self._ensure_handle()
+        lib = _lib.load()
+        self._set_switches(lib, h, **fwd_kw)
+        cam = self._camera(c2w, H, W, focal, center)
+        R = H * W
+        rgb = torch.empty((R, 3), dtype=torch.float32, device=self.device)
+        depth = torch.empty((R,), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.ngf_field_render_camera(h, C.byref(cam), int(N_samples), int(bool(white_bg)), rgb.data_ptr(),
+                                                   depth.data_ptr(), None, self._mlp_impl,
+                                                   _cuda_stream_ptr(self.device)), "ngf_field_render_camera")
+        return {'rgb_map': rgb, 'depth_map': depth}
+
+    @torch.no_grad()
+    def render_camera_host_async(self, c2w, H, W, focal, rgb_host, depth_host, center=None, white_bg=True, N_samples=-1,
+                                 **fwd_kw):
+        """As render_camera but into pinned CPU tensors, pipelined across frames; returns a ticket for host_wait."""
+        h = self._ensure_handle()
+        lib = _lib.load()
+        self._set_switches(lib, h, **fwd_kw)
+        cam = self._camera(c2w, H, W, focal, center)
+        ticket = C.c_uint64()
+        _lib.check(lib.ngf_field_render_camera_host_async(h, C.byref(cam), int(N_samples), int(bool(white_bg)),
+                                                          rgb_host.data_ptr(), depth_host.data_ptr(), self._mlp_impl,
+                                                          C.byref(ticket)), "ngf_field_render_camera_host_async")
+        return int(ticket.value)
+
     def host_wait(self, ticket: int):
         _lib.check(_lib.load().ngf_field_host_wait(self._ensure_handle(), int(ticket)), "ngf_field_host_wait")
 

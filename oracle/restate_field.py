@@ -140,6 +140,25 @@ def spec_from_state(variant: str, state: dict, *, aabb, gridSize, step_ratio=2.0
 
 
 # --------------------------------------------------------------------------------------------------------------
+# §8f rank 1  camera rays (TriPlane/dataLoader/ray_utils.py:24-42,66-87; blender.py:46-52; main.py:155-159)
+# --------------------------------------------------------------------------------------------------------------
+def reference_rays(H: int, W: int, focal, c2w: torch.Tensor, center=None) -> torch.Tensor:
+    """-> rays [H*W, 6]: get_ray_directions (pixel-centre directions; kornia.create_meshgrid restated as index grids
+    with x fastest) / their norm (blender.py:52), get_rays (directions @ c2w[:3,:3].T, origin c2w[:3,3]).
+    kornia is absent offline, so this function is pinned by reading, not by running the reference."""
+    ys, xs = torch.meshgrid(torch.linspace(0, H - 1, H), torch.linspace(0, W - 1, W), indexing="ij")
+    i, j = xs + 0.5, ys + 0.5
+    fx, fy = focal if isinstance(focal, (tuple, list)) else (focal, focal)
+    cent = center if center is not None else [W / 2, H / 2]
+    dirs = torch.stack([(i - cent[0]) / fx, (j - cent[1]) / fy, torch.ones_like(i)], -1)
+    dirs = dirs / torch.norm(dirs, dim=-1, keepdim=True)
+    c2w = torch.as_tensor(c2w, dtype=torch.float32)
+    rays_d = dirs @ c2w[:3, :3].T
+    rays_o = c2w[:3, 3].expand(rays_d.shape)
+    return torch.cat([rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)], 1).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------------------
 # a2  ray march (FieldBase.py:118-137)
 # --------------------------------------------------------------------------------------------------------------
 def march(spec: FieldSpec, o: torch.Tensor, d: torch.Tensor, S: int):

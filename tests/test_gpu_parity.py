@@ -213,3 +213,29 @@ def test_occupancy_maintenance_matches_reference_golden():
     kept_b, _ = f.filtering_rays(rays, rgbs, bbox_only=True)
     assert kept_b.shape[0] == int(gold["n_kept_bbox"])                     # pure fp32 slab test: exact
     assert abs(kept.shape[0] - int(gold["n_kept_mask"])) <= max(2, int(gold["n_kept_mask"]) // 200)
+
+
+def test_camera_rays_on_device():
+    """ngf_field_render_camera (rays generated in the march kernel) vs the oracle rendering the rays the reference's
+    get_ray_directions / get_rays produce for the same camera, and vs the CUDA path fed with those rays."""
+    import ngf_b200
+    case = K.CASE_BY_NAME["tp_fog_c1"]
+    state, kw, occ, _ = K.build_inputs(case)
+    f = build_cuda_field(case, state, kw, occ)
+    H, W = 48, 80                                                   # not square, not a multiple of the 8x4 warp tile rows
+    focal = K.synth.FOCAL_800 * 64 / 800
+    c2w = K.synth.look_at_c2w(*K.synth.pose_angles(4))
+    rays = R.reference_rays(H, W, focal, c2w)
+    out_cam = f.render_camera(c2w, H, W, focal, white_bg=True, N_samples=64, iteration=30001)
+    out_rays = f(rays.cuda(), white_bg=True, N_samples=64, image_width=W, iteration=30001)
+    torch.cuda.synchronize()
+    # the directions differ from torch's in the last bit (matmul summation order), which moves samples by ~1e-7
+    assert (out_cam["rgb_map"] - out_rays["rgb_map"]).abs().max() < 2e-4
+    assert (out_cam["depth_map"] - out_rays["depth_map"]).abs().max() < 1e-3
+    spec = oracle_spec(case, state, kw, occ)
+    o_rgb, o_depth = R.render(spec, rays, white_bg=True, N_samples=64)
+    assert (out_cam["rgb_map"].cpu() - o_rgb).abs().max() < RGB_TOL
+    assert (out_cam["depth_map"].cpu() - o_depth).abs().max() < DEPTH_TOL
+    rgb_h, dep_h = torch.empty((H * W, 3)).pin_memory(), torch.empty((H * W,)).pin_memory()
+    f.host_wait(f.render_camera_host_async(c2w, H, W, focal, rgb_h, dep_h, white_bg=True, N_samples=64, iteration=30001))
+    assert (rgb_h - out_cam["rgb_map"].cpu()).abs().max() < 1e-5 and torch.equal(dep_h, out_cam["depth_map"].cpu())
