@@ -236,6 +236,15 @@ int ngf_field_sigma_world(NgfField f, const float* pts_dev, int64_t n, int32_t u
                           void* stream);
 
 /*
+ * Frame post-processing on the device, replacing what evaluation() does on the CPU after
+ * `.cpu()` (TriPlane/main.py:99-116): u8 = (rgb * 255).astype('uint8') for the PNG / video writers and
+ * sse = sum((rgb - gt)^2), from which PSNR = -10 ln(sse / n_values) / ln 10 (main.py:105-106).  Either output may be
+ * NULL.  Arrays are device pointers on the current device; sse_dev is one double, zeroed by the call.
+ */
+int ngf_frame_post(const float* rgb_dev, const float* gt_dev, int64_t n_values, uint8_t* u8_dev, double* sse_dev,
+                   void* stream);
+
+/*
  * Multi-GPU helpers (the reference has no distributed code).  Rays of a frame are dealt to
  * ranks in interleaved blocks of `block` rays: global ray g belongs to rank (g / block) % world.
  *  ngf_shard_count   : number of rays rank owns.

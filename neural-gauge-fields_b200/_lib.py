@@ -103,6 +103,7 @@ SIGNATURES = {
     "ngf_neutex_timing_begin": (C.c_int, [C.c_void_p, C.c_int32]),
     "ngf_neutex_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          C.POINTER(C.c_double)]),
+    "ngf_frame_post": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ngf_shard_count": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "ngf_shard_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_void_p]),

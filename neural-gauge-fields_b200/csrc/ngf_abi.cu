@@ -957,6 +957,21 @@ int ngf_field_sigma_world(NgfField h, const float* pts_dev, int64_t n, int32_t u
   return NGF_OK;
 }
 
+int ngf_frame_post(const float* rgb_dev, const float* gt_dev, int64_t n_values, uint8_t* u8_dev, double* sse_dev,
+                   void* stream) {
+  if (!rgb_dev) return fail(NGF_EINVAL, "rgb is NULL");
+  if (n_values < 0) return fail(NGF_EINVAL, "negative count");
+  if (gt_dev && !sse_dev) return fail(NGF_EINVAL, "gt given but sse is NULL");
+  if (!gt_dev && !u8_dev) return fail(NGF_EINVAL, "nothing to do: neither u8 nor gt given");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 148;
+  CU(cudaGetDevice(&dev));
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (gt_dev) CU(cudaMemsetAsync(sse_dev, 0, sizeof(double), st));
+  CU(launch_frame_post(rgb_dev, gt_dev, n_values, u8_dev, sse_dev, sms, st));
+  return NGF_OK;
+}
+
 int64_t ngf_shard_count(int64_t n_rays, int32_t block, int32_t rank, int32_t world) {
   if (n_rays < 0 || block < 1 || world < 1 || rank < 0 || rank >= world) return -1;
   const long long per_cycle = (long long)block * world;

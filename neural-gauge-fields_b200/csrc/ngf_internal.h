@@ -55,6 +55,9 @@ cudaError_t launch_pack_occ2(const uint32_t* bits, int W, int H, int D, uint32_t
 // TriPlane: dsum[t] = <dens[t][0..DC), w[0..DC)>
 cudaError_t launch_pack_dsum(const float* dens, long long hw, int DC, const float* w_dev, float* dsum, cudaStream_t st);
 
+cudaError_t launch_frame_post(const float* rgb, const float* gt, long long n, uint8_t* u8, double* sse, int num_sms,
+                              cudaStream_t st);
+
 // ray sharding
 cudaError_t launch_shard_gather(const float* src, long long n_rays, int width, int block, int rank, int world,
                                 float* dst, cudaStream_t st);

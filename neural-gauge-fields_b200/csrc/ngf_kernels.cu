@@ -583,6 +583,45 @@ cudaError_t launch_pack_dsum(const float* dens, long long hw, int DC, const floa
 }
 
 // ==========================================================================================================
+// Frame post-processing: what evaluation() does on the CPU after .cpu() (TriPlane/main.py:99-116)
+//   u8  = (rgb * 255).astype('uint8')      (fp32 multiply, truncation)
+//   sse = sum((rgb - gt)^2)                 (PSNR = -10 ln(sse / n) / ln 10 on the host)
+// ==========================================================================================================
+__global__ void ngf_frame_post_kernel(const float* __restrict__ rgb, const float* __restrict__ gt, long long n,
+                                      uint8_t* __restrict__ u8, double* __restrict__ sse) {
+  double local = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = rgb[i];
+    if (u8) u8[i] = (uint8_t)__fmul_rn(v, 255.f);
+    if (gt) {
+      const float d = __fsub_rn(v, gt[i]);
+      local += (double)__fmul_rn(d, d);
+    }
+  }
+  if (!gt) return;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) local += __shfl_xor_sync(0xffffffffu, local, s);
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+    atomicAdd(sse, t);
+  }
+}
+
+cudaError_t launch_frame_post(const float* rgb, const float* gt, long long n, uint8_t* u8, double* sse, int num_sms,
+                              cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  long long blocks = (n + 255) / 256;
+  if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+  ngf_frame_post_kernel<<<(unsigned)blocks, 256, 0, st>>>(rgb, gt, n, u8, sse);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// ==========================================================================================================
 // Ray sharding: ray g belongs to rank (g / block) % world, local index
 // (g / (block*world)) * block + g % block.
 // ==========================================================================================================

@@ -51,6 +51,26 @@ def render_frames(frames, field, N_samples=-1, white_bg=True, image_width=0, dep
         yield r0, d0
 
 
+@torch.no_grad()
+def frame_post(rgb_map, gt_rgb=None, want_u8=True):
+    """Device-side tail of the reference's ``evaluation`` (TriPlane/main.py:99-116): -> (uint8 image or None, PSNR or
+    None).  ``rgb_map`` / ``gt_rgb``: CUDA fp32 tensors of equal shape."""
+    import math
+    rgb = rgb_map.contiguous()
+    n = rgb.numel()
+    u8 = torch.empty(rgb.shape, dtype=torch.uint8, device=rgb.device) if want_u8 else None
+    sse = torch.zeros(1, dtype=torch.float64, device=rgb.device) if gt_rgb is not None else None
+    gt = None if gt_rgb is None else gt_rgb.to(rgb.device).float().contiguous()
+    with torch.cuda.device(rgb.device):
+        _lib.check(_lib.load().ngf_frame_post(rgb.data_ptr(), None if gt is None else gt.data_ptr(), n,
+                                              None if u8 is None else u8.data_ptr(),
+                                              None if sse is None else sse.data_ptr(), _cuda_stream_ptr(rgb.device)))
+    psnr = None
+    if sse is not None:
+        psnr = -10.0 * math.log(float(sse.item()) / n) / math.log(10.0)
+    return u8, psnr
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # ray sharding: global ray g belongs to rank (g // block) % world; local index (g // (block*world))*block + g % block
 # ---------------------------------------------------------------------------------------------------------------

@@ -239,3 +239,17 @@ def test_camera_rays_on_device():
     rgb_h, dep_h = torch.empty((H * W, 3)).pin_memory(), torch.empty((H * W,)).pin_memory()
     f.host_wait(f.render_camera_host_async(c2w, H, W, focal, rgb_h, dep_h, white_bg=True, N_samples=64, iteration=30001))
     assert (rgb_h - out_cam["rgb_map"].cpu()).abs().max() < 1e-5 and torch.equal(dep_h, out_cam["depth_map"].cpu())
+
+
+def test_frame_post_matches_reference_arithmetic():
+    """uint8 conversion and PSNR of TriPlane/main.py:99-116 done on the device."""
+    import ngf_b200
+    g = torch.Generator().manual_seed(5)
+    rgb = torch.rand((4096, 3), generator=g)
+    rgb[:8] = torch.tensor([0.0, 1.0, 0.5])
+    gt = (rgb + 0.03 * torch.randn(rgb.shape, generator=g)).clamp(0, 1)
+    want_u8 = (rgb.numpy() * 255).astype("uint8")
+    want_psnr = -10.0 * np.log(torch.mean((rgb - gt) ** 2).item()) / np.log(10.0)
+    u8, ps = ngf_b200.frame_post(rgb.cuda(), gt.cuda())
+    assert np.array_equal(u8.cpu().numpy(), want_u8)                  # byte work: bit-exact
+    assert abs(ps - want_psnr) < 1e-4
