@@ -336,6 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
       v[0] += o.x;
       if (n > 1) v[1] += o.y;
       if (n > 2) v[2] += o.z;
+      worker_bar();              // the buffer may be rewritten by the next head layer only after every read
     };
     const float* heads = net.heads;
     {   // the constant-one columns must exist before the first bias slice is multiplied
