@@ -309,15 +309,34 @@ __device__ __forceinline__ float phase_value(const float xyz[3], int ch) {
 // compute_density, InfoInv (InfoInv/models/Field.py:52-70 + networks.py:34-54): 3 x bilinear over channels
 // [0,24) (x phase code of xyz with 4 bands when infoinv), MLP 72->32->32->1 (ReLU), softplus(.-10).
 // `w` points at the fp32 density MLP (shared memory in the render kernel, global in the point-wise kernel).
+// fp32 throughout; the two hidden layers use the packed fma.rn.f32x2 of sm_100 (two exact fp32 FMAs per instruction).
 __device__ __forceinline__ float sigma_infoinv(const FieldDev& f, const float c[6], const float* __restrict__ w) {
   const float xyz[3] = {c[0], c[1], c[3]};
-  float h1[kDensMid];
+  // phase code PE(xyz, 4): sin / cos of x * 2^k, k < 4 — one sincosf per coordinate, then the exact double-angle identities
+  // (arguments <= 8 rad; the recurrence error stays below 1e-6)
+  float sn[12], cs[12];
+  if (f.infoinv) {
 #pragma unroll
-  for (int j = 0; j < kDensMid; ++j) h1[j] = w[32 * 72 + j];
-  const float* w1t = w;                              // [72][32] input-major
+    for (int a = 0; a < 3; ++a) {
+      float s_, c_;
+      sincosf(xyz[a], &s_, &c_);
+      sn[4 * a] = s_; cs[4 * a] = c_;
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        const float s2 = 2.f * s_ * c_, c2 = 1.f - 2.f * s_ * s_;
+        s_ = s2; c_ = c2;
+        sn[4 * a + k] = s_; cs[4 * a + k] = c_;
+      }
+    }
+  }
+  float2 h1[kDensMid / 2];
+  const float2* b1 = reinterpret_cast<const float2*>(w + 32 * 72);
+#pragma unroll
+  for (int j = 0; j < kDensMid / 2; ++j) h1[j] = b1[j];
   for (int pl = 0; pl < 3; ++pl) {
     const PlaneDev& P = f.plane[pl];
     Taps t = make_taps(c[2 * pl], c[2 * pl + 1], P.W, P.H, P.wm1, P.hm1);
+#pragma unroll
     for (int q = 0; q < 6; ++q) {                    // 6 x float4 = 24 channels
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -328,25 +347,28 @@ __device__ __forceinline__ float sigma_infoinv(const FieldDev& f, const float c[
       float fe[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        int ch = 4 * q + e;
+        const int ch = 4 * q + e;                    // channel of PE(xyz,4): [sin x(4) sin y(4) sin z(4) cos x(4) cos y(4) cos z(4)]
         float x = fe[e];
-        if (f.infoinv) x *= phase_value<4>(xyz, ch);
-        const int col = pl * 24 + ch;
+        if (f.infoinv) x *= ch < 12 ? sn[ch] : cs[ch - 12];
+        const float2 xx = make_float2(x, x);
+        const float2* wrow = reinterpret_cast<const float2*>(w + (pl * 24 + ch) * 32);   // [72][32] input-major
 #pragma unroll
-        for (int j = 0; j < kDensMid; ++j) h1[j] += w1t[col * 32 + j] * x;
+        for (int j = 0; j < kDensMid / 2; ++j) h1[j] = __ffma2_rn(wrow[j], xx, h1[j]);
       }
     }
   }
+#pragma unroll
+  for (int j = 0; j < kDensMid / 2; ++j) { h1[j].x = fmaxf(h1[j].x, 0.f); h1[j].y = fmaxf(h1[j].y, 0.f); }
   const float* b2 = w + 32 * 72 + 32 + 32 * 32;
-  const float* w2 = w + 32 * 72 + 32;
+  const float2* w2 = reinterpret_cast<const float2*>(w + 32 * 72 + 32);
   const float* w3 = b2 + 32;
   float out = w3[32];
 #pragma unroll 4
   for (int j = 0; j < kDensMid; ++j) {
-    float s = b2[j];
+    float2 s2 = make_float2(b2[j], 0.f);
 #pragma unroll
-    for (int k = 0; k < kDensMid; ++k) s += w2[j * 32 + k] * fmaxf(h1[k], 0.f);
-    out += w3[j] * fmaxf(s, 0.f);
+    for (int k = 0; k < kDensMid / 2; ++k) s2 = __ffma2_rn(w2[j * 16 + k], h1[k], s2);
+    out += w3[j] * fmaxf(s2.x + s2.y, 0.f);
   }
   return softplus_torch(out + f.dshift);
 }
