@@ -268,14 +268,29 @@ def main():
                 field.host_wait(pend.pop(0))
         d2h = n_local * 16
     else:
-        stage = torch.empty_like(dev_rays[0])
-        res_h = torch.empty((n_local, 4)).pin_memory()
+        # pinned shard of the batch -> H2D (copy stream) -> render + overlapped all-gather -> D2H of one shard's worth of
+        # the gathered batch (download stream); the host trails the device by one step
+        copy_s = torch.cuda.Stream(device=dev)
+        stage = [torch.empty_like(dev_rays[0]) for _ in range(2)]
+        res_h = [torch.empty((n_local, 4)).pin_memory() for _ in range(2)]
+        up, free = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]
+        pend = []
         def step_e2e(i):
-            stage.copy_(host[i % N_POSES], non_blocking=True)
-            t = sharded.submit(stage, N_samples=S, white_bg=True, iteration=30001, image_width=W)
-            frame = sharded.result(t)
-            res_h.copy_(frame[:n_local], non_blocking=True)      # read back one shard's worth of the gathered batch
-            torch.cuda.synchronize()
+            b = i % 2
+            cur = torch.cuda.current_stream(dev)
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(free[b])
+                stage[b].copy_(host[i % N_POSES], non_blocking=True)
+                up[b].record(copy_s)
+            cur.wait_event(up[b])
+            t = sharded.submit(stage[b], N_samples=S, white_bg=True, iteration=30001, image_width=W)
+            free[b].record(cur)
+            pend.append(sharded.download(t, res_h[b], n_local))
+            if len(pend) > 1:
+                pend.pop(0).synchronize()
+        def e2e_drain():
+            while pend:
+                pend.pop(0).synchronize()
         d2h = n_local * 16
     for i in range(3):
         step_e2e(i)
@@ -327,7 +342,7 @@ def main():
                    "rays_per_step": n_batch, "l2": f"inputs rotate over {N_POSES} poses ({N_POSES * n_local * 24 / 1e6:.0f} MB of rays per rank > 126 MB L2)",
                    "parallelism": "single GPU" if world == 1 else f"ray-sharded dp{world}, {BLOCK}-ray interleaved blocks"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_local * 24, "d2h_bytes_per_step": d2h,
-                "api": "ngf_b200.render_frames: ngf_field_render_host_async per frame (C ABI, pinned host buffers, 3 frames in flight)" if world == 1 else "H2D + ngf_field_render + all-gather + D2H"},
+                "api": "ngf_b200.render_frames: ngf_field_render_host_async per frame (C ABI, pinned host buffers, 3 frames in flight)" if world == 1 else "pinned H2D + ngf_field_render + overlapped NCCL all-gather + D2H, host one step behind"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": roofline,

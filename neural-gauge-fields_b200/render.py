@@ -174,6 +174,8 @@ class ShardedFrameRenderer:
         self.frame = [torch.empty((self.n, 4), device=dev) for _ in range(2)]
         self.rendered = [torch.cuda.Event() for _ in range(2)]
         self.done = [torch.cuda.Event() for _ in range(2)]
+        self.read = [torch.cuda.Event() for _ in range(2)]
+        self.d2h = torch.cuda.Stream(device=dev)
         self.count = 0
 
     @torch.no_grad()
@@ -188,6 +190,7 @@ class ShardedFrameRenderer:
         self.rendered[b].record(cur)
         with torch.cuda.stream(self.comm):
             self.comm.wait_event(self.rendered[b])
+            self.comm.wait_event(self.read[b])             # a pending download of this parity's frame buffer
             dist.all_gather_into_tensor(self.gathered[b].view(self.world * self.max_shard, 4), self.local[b],
                                         group=self.group)
             src = self.gathered[b]
@@ -196,6 +199,18 @@ class ShardedFrameRenderer:
             self.done[b].record(self.comm)
         self.count += 1
         return self.count - 1
+
+    def download(self, ticket: int, out_host: torch.Tensor, n_rows: int = None):
+        """Copy the first ``n_rows`` rows (default: all) of batch ``ticket``'s gathered frame into the pinned CPU tensor
+        ``out_host`` on a dedicated stream, without stalling the compute stream; returns the event to wait on."""
+        if ticket < self.count - 2 or ticket >= self.count:
+            raise ValueError("only the last two submitted batches are still buffered")
+        b = ticket % 2
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(self.done[b])
+            out_host.copy_(self.frame[b][:n_rows] if n_rows is not None else self.frame[b], non_blocking=True)
+            self.read[b].record(self.d2h)
+        return self.read[b]
 
     def result(self, ticket: int):
         """Make the current stream wait for batch ``ticket`` (it must be one of the last two submitted) and return its

@@ -253,3 +253,14 @@ def test_frame_post_matches_reference_arithmetic():
     u8, ps = ngf_b200.frame_post(rgb.cuda(), gt.cuda())
     assert np.array_equal(u8.cpu().numpy(), want_u8)                  # byte work: bit-exact
     assert abs(ps - want_psnr) < 1e-4
+
+
+def test_render_split_into_ray_batches_by_queue_budget():
+    """With a 1 MiB colour-queue budget (NGF_QUEUE_MIB=1) every render is cut into many ray batches inside the library;
+    the frame must not change (scripts/check_small_queue.py compares with the reference goldens)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NGF_QUEUE_MIB="1")
+    res = subprocess.run([sys.executable, os.path.join(root, "scripts", "check_small_queue.py")], env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
