@@ -149,15 +149,19 @@ def run_reference(args, rank):
     spec = R.spec_from_state("triplane", state, alpha_volume=occ, gauge_on=True, **kw)
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    n_sample = 16384                                        # rays per step: 4 chunks of 4096, strided over the frame
-    def step(i):
+    def render_sample(i, n_sample):
         rays = K.synth.config_rays("C2", i % N_POSES)[:: RAYS_PER_FRAME // n_sample][:n_sample].contiguous()
         t0 = time.perf_counter()
         R.render(spec, rays, N_samples=S)
         return time.perf_counter() - t0
+    # bounded sample: rays per step sized from a short probe so that warm-up + K steps take about 1.5 minutes
+    render_sample(0, 4096)
+    probe = 4096 / render_sample(1, 4096)
+    n_sample = int(probe * 90.0 / max(args.steps + args.warmup, 1)) // 1024 * 1024
+    n_sample = max(1024, min(65536, n_sample))
     for i in range(args.warmup):
-        step(i)
-    total = sum(step(i) for i in range(args.steps))
+        render_sample(i, n_sample)
+    total = sum(render_sample(i, n_sample) for i in range(args.steps))
     v = n_sample * args.steps / total
     print(json.dumps({
         "impl": "reference", "metric": "rays/sec (800x800, 192 samples/ray)", "value": v, "unit": "rays/s",
