@@ -308,6 +308,11 @@ int ngf_neutex_copy_samples(NgfNeutex h, int64_t first_sample, int64_t n, float*
 int ngf_neutex_timing_begin(NgfNeutex h, int32_t capacity);
 int ngf_neutex_timing_read(NgfNeutex h, int32_t* n_renders, double* raygen_ms, double* mlp_ms, double* march_ms);
 
+/* Profiling aid (library built as is, NGF_NTX_DBG=4 in the environment when packing): per-layer clock64 stamps of CTA 0's
+ * first tile — [25][4] = MMA warp saw a_ready | MMA warp issued the layer | worker 0 saw acc_ready | worker 0 finished the
+ * epilogue. */
+int ngf_neutex_debug_trace(NgfNeutex h, long long* out_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,6 +100,7 @@ SIGNATURES = {
                                          C.c_void_p, C.c_void_p]),
     "ngf_neutex_last_valid_samples": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "ngf_neutex_copy_samples": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
+    "ngf_neutex_debug_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ngf_neutex_timing_begin": (C.c_int, [C.c_void_p, C.c_int32]),
     "ngf_neutex_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          C.POINTER(C.c_double)]),

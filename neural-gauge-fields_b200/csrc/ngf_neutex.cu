@@ -86,6 +86,54 @@ __device__ __forceinline__ void store_group(uint8_t* A, int group, int row, cons
   if (SPLIT) *reinterpret_cast<uint4*>(A + kALoOff + group * kKGroupBytes + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// sin and cos of |x| <~ 2000 to about 1 ulp: Cody-Waite reduction by pi/2 in three FMA steps, then the single-precision
+// minimax polynomials on [-pi/4, pi/4] (Cephes sinf / cosf coefficients).  ~35 instructions for both values; sincosf's
+// generic path (with its Payne-Hanek fallback in local memory) costs several times that.
+__device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
+  const float kf = rintf(x * 0.63661977236758134f);
+  float r = fmaf(kf, -1.57079637050628662109375f, x);
+  r = fmaf(kf, 4.37113900018624283e-8f, r);
+  r = fmaf(kf, 1.71512451805164e-15f, r);
+  const float r2 = r * r;
+  const float sp = fmaf(r * r2, fmaf(r2, fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), r);
+  const float cp = fmaf(r2 * r2, fmaf(r2, fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f),
+                        fmaf(r2, -0.5f, 1.f));
+  const int q = (int)kf & 3;
+  const float s0 = (q & 1) ? cp : sp, c0 = (q & 1) ? sp : cp;
+  s = (q & 2) ? -s0 : s0;
+  c = ((q + 1) & 2) ? -c0 : c0;
+}
+
+// One fp16 hi (+ lo) element of the A operand
+__device__ __forceinline__ void store_split_elem(uint8_t* A, int col, int row, float v) {
+  const __half h = __float2half_rn(v);
+  const uint32_t off = (uint32_t)(col >> 3) * kKGroupBytes + (uint32_t)row * 16u + (uint32_t)(col & 7) * 2u;
+  *reinterpret_cast<__half*>(A + off) = h;
+  *reinterpret_cast<__half*>(A + kALoOff + off) = __float2half_rn(v - __half2float(h));
+}
+
+// Gauge-network input [p, sin(p_d 2^f), cos(p_d 2^f)] (63 columns + one zero), split fp16, every value accurate to ~1e-7:
+// the row's two threads take 15 of the 30 (coordinate, octave) pairs each and write sin and cos of a pair from one
+// sincos_cw call.
+__device__ __forceinline__ void write_gauge_encoding(uint8_t* A, int row, int ch, const float* x) {
+#pragma unroll
+  for (int j = 0; j < 15; ++j) {
+    const int i = ch * 15 + j;                      // pair index = d * 10 + f
+    float s, c;
+    const int d0 = i / 10;
+    const float xd = d0 == 0 ? x[0] : (d0 == 1 ? x[1] : x[2]);
+    sincos_cw(xd * (float)(1 << (i % 10)), s, c);
+    store_split_elem(A, 3 + i, row, s);
+    store_split_elem(A, 33 + i, row, c);
+  }
+  if (ch == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) store_split_elem(A, d, row, x[d]);
+  } else {
+    store_split_elem(A, 63, row, 0.f);
+  }
+}
+
 // Encoding [x, sin(x_d * 2^f), cos(x_d * 2^f)] (column order of util.py:427-438: d-major, then f), zero padded to
 // 8*NG columns; with ONES, columns kOnesCol and kOnesCol+1 are 1.0.  The row's two threads each write half of the K
 // groups (CH = 0 / 1).  ACCURATE: every value from sinf / cosf (gauge network, 1e-6 budget); otherwise one sincosf per
@@ -179,13 +227,14 @@ __device__ __forceinline__ void epilogue(uint32_t taddr, uint8_t* A, int row, in
       if (NH > 0) {
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
-          float s = hacc[h];
+          float2 s2 = make_float2(hacc[h], 0.f);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 w = __ldg(reinterpret_cast<const float4*>(headw + h * N + col0 + c0) + q);
-            s += v[4 * q] * w.x + v[4 * q + 1] * w.y + v[4 * q + 2] * w.z + v[4 * q + 3] * w.w;
+            s2 = __ffma2_rn(make_float2(v[4 * q], v[4 * q + 1]), make_float2(w.x, w.y), s2);
+            s2 = __ffma2_rn(make_float2(v[4 * q + 2], v[4 * q + 3]), make_float2(w.z, w.w), s2);
           }
-          hacc[h] = s;
+          hacc[h] = s2.x + s2.y;
         }
       }
       if (MODE != 2) {
@@ -276,6 +325,8 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
           mbar_wait(&bars->a_ready, par_a);
           par_a ^= 1u;
           tc_fence_after();
+          const bool tr = (net.dbg & 4) && blockIdx.x == 0 && tile == blockIdx.x;
+          if (tr) net.trace[l * 4 + 0] = clock64();
           for (int k0 = 0; k0 < nk; k0 += kSlicesPerStage, ++it) {
             const uint32_t s = it % kStages;
             const int n = nk - k0 < kSlicesPerStage ? nk - k0 : kSlicesPerStage;
@@ -306,6 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
             umma_commit(&bars->empty[s]);
           }
           umma_commit(&bars->acc_ready);
+          if (tr) net.trace[l * 4 + 1] = clock64();
         }
       }
     }
@@ -317,16 +369,20 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
     uint8_t* A = smem + offA;
     float4* hx = reinterpret_cast<float4*>(smem + offHx);      // [2 column halves][256 rows]
     uint32_t par_acc = 0;
+    int trace_l = 0;
+    bool trace_on = false;
     auto signal_a = [&]() {
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->a_ready);
     };
+    auto mark_done = [&]() { if (trace_on && trace_l < kNumLayers) { net.trace[trace_l * 4 + 3] = clock64(); ++trace_l; } };
     auto wait_acc = [&]() {
       mbar_wait_backoff(&bars->acc_ready, par_acc);
       par_acc ^= 1u;
       tc_fence_after();
+      if (trace_on && trace_l < kNumLayers) net.trace[trace_l * 4 + 2] = clock64();
     };
     // add the partial head sums of the row's other column half
     auto combine = [&](float* v, int n) {
@@ -344,6 +400,8 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
       write_encoding<3, 6, 6, false, false, true>(smem + offA2, row, ch, zero);
     }
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      trace_on = (net.dbg & 4) && blockIdx.x == 0 && tile == blockIdx.x && tid == 0;
+      trace_l = 0;
       const uint32_t item = tile * kRows + row;
       int id = -1;
       float p[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
@@ -360,27 +418,32 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
       for (int l = 0; l < 10; ++l) {
         wait_acc();
         epilogue<256, 0, 0, 0>(taddr, A, row, ch, nullptr, nullptr);
+        mark_done();
         signal_a();
       }
       float raw = 0.f;
       wait_acc();
       epilogue<256, 0, 2, 1>(taddr, A, row, ch, heads + kHeadGeo, &raw);
+      mark_done();
       combine(&raw, 1);
       const float sigma = softplus_t(raw + __ldg(heads + kHeadGeoB));
       // ---- gauge: [p, PE(p,10)] -> 64 -> 128 -> 128 -> 128 (ReLU) -> 2 -> tanh, split fp16   (gauge_fields.py:8-74)
-      write_encoding<3, 10, 8, true, true, false>(A, row, ch, p);
+      write_gauge_encoding(A, row, ch, p);
       signal_a();
       wait_acc();
       epilogue<64, 0, 1, 0>(taddr, A, row, ch, nullptr, nullptr);
+      mark_done();
       signal_a();
       for (int r = 0; r < 2; ++r) {
         wait_acc();
         epilogue<128, 0, 1, 0>(taddr, A, row, ch, nullptr, nullptr);
+        mark_done();
         signal_a();
       }
       float uvr[2] = {0.f, 0.f};
       wait_acc();
       epilogue<128, 0, 2, 2>(taddr, A, row, ch, heads + kHeadGauge, uvr);
+      mark_done();
       combine(uvr, 2);
       float uv[2] = {tanhf(uvr[0] + __ldg(heads + kHeadGaugeB)), tanhf(uvr[1] + __ldg(heads + kHeadGaugeB + 1))};
       // ---- texture block1: [uv, PE(uv,10)] -> 256 -> 5 x 256 (LeakyReLU 0.2); color1 256 -> 3 softplus   (decoder.py:56-78)
@@ -390,11 +453,13 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
       for (int r = 0; r < 5; ++r) {
         wait_acc();
         epilogue<256, 1, 0, 0>(taddr, A, row, ch, nullptr, nullptr);
+        mark_done();
         signal_a();
       }
       float c1[3] = {0.f, 0.f, 0.f};
       wait_acc();
       epilogue<256, 1, 0, 3>(taddr, A, row, ch, heads + kHeadC1, c1);
+      mark_done();
       signal_a();
       combine(c1, 3);
 #pragma unroll
@@ -403,11 +468,13 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
       for (int r = 0; r < 3; ++r) {
         wait_acc();
         epilogue<256, 1, 0, 0>(taddr, A, row, ch, nullptr, nullptr);
+        mark_done();
         signal_a();
       }
       float c2[3] = {0.f, 0.f, 0.f};
       wait_acc();
       epilogue<256, 1, 2, 3>(taddr, A, row, ch, heads + kHeadB2, c2);
+      mark_done();
       combine(c2, 3);
       if (ch == 0 && id >= 0) {
         float rgb[3];

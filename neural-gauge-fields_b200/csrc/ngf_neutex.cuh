@@ -46,7 +46,9 @@ struct NetDev {
   const float* texture;   // [h][w][c] edited texture or nullptr
   int tex_h, tex_w, tex_c;
   float jitter;
-  int dbg;                // NGF_NTX_DBG (profiling experiments only): 1 = skip epilogue bodies, 2 = skip MMA issue
+  int dbg;                // NGF_NTX_DBG (profiling experiments only): 2 = skip MMA issue, 4 = record a timeline
+  long long* trace;       // dbg & 4: [25 layers][4] clock64 stamps of CTA 0's first tile (a_ready seen, MMAs issued,
+                          //          acc_ready seen by worker 0, epilogue done by worker 0)
 };
 
 // geometry head [256] | gauge head [2][128] | color1 [3][256] | block2 head [3][256] | biases 1 + 2 + 3 + 3

@@ -215,6 +215,11 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
   h->net.texture = h->texture; h->net.tex_h = d->tex_h; h->net.tex_w = d->tex_w; h->net.tex_c = d->tex_c;
   h->net.jitter = d->jitter;
   { const char* e = getenv("NGF_NTX_DBG"); h->net.dbg = e ? atoi(e) : 0; }
+  h->net.trace = nullptr;
+  if (h->net.dbg & 4) {
+    cudaMalloc(reinterpret_cast<void**>(&h->net.trace), kNumLayers * 4 * sizeof(long long));
+    cudaMemset(h->net.trace, 0, kNumLayers * 4 * sizeof(long long));
+  }
   *out = h;
   return NGF_OK;
 }
@@ -357,6 +362,15 @@ int ngf_neutex_copy_samples(NgfNeutex h, int64_t first_sample, int64_t n, float*
   if (sigma_rgb_host && n) CUN(cudaMemcpy(sigma_rgb_host, h->sample_out + first_sample, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
   if (valid_mask_host && n_mask_rays)
     CUN(cudaMemcpy(valid_mask_host, h->valid_mask + first_ray, (size_t)n_mask_rays * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return NGF_OK;
+}
+
+int ngf_neutex_debug_trace(NgfNeutex h, long long* out_host) {     /* NGF_NTX_DBG=4 only: 25 x 4 clock64 stamps */
+  if (!h || !out_host) return ngf_set_error(NGF_EINVAL, "NULL argument");
+  if (!h->net.trace) return ngf_set_error(NGF_EINVAL, "tracing is off (NGF_NTX_DBG=4)");
+  Guard g(h->device);
+  CUN(cudaDeviceSynchronize());
+  CUN(cudaMemcpy(out_host, h->net.trace, kNumLayers * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
   return NGF_OK;
 }
 
