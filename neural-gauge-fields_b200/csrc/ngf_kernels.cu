@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
 
 #include "ngf_internal.h"
 #include "ngf_mlp.cuh"

@@ -273,41 +273,62 @@ __device__ __forceinline__ void blend8(const __half* __restrict__ base, int chan
 //   dir / dir_stride : view direction of entry id is dir[id*dir_stride + 0..2]; with a camera (cam != nullptr) it is
 //                      regenerated from the pixel index instead
 // ----------------------------------------------------------------------------------------------------------
-template <int V>
-__device__ __forceinline__ void mlp_gather(const FieldDev& f, uint8_t* smem, uint32_t head,
-                                           const float* __restrict__ dir, int dir_stride, const CamDev* cam) {
+// q: the tile's 128 work items; A: the layer-1 operand; tapbuf: 12 KiB of scratch (TriPlane only); tid: 0..NT-1 within the
+// NT threads (256 or 384) that share the work; sync(): a barrier over exactly those threads.
+template <int V, int NT, class Sync>
+__device__ __forceinline__ void mlp_gather_at(const FieldDev& f, const QEntry* __restrict__ q, uint8_t* A, TapsH* tapbuf,
+                                              int tid, const float* __restrict__ dir, int dir_stride, const CamDev* cam,
+                                              Sync sync) {
   using L = MlpSmem<V>;
   constexpr int AC = Cfg<V>::AC, F = Cfg<V>::F;
-  const QEntry* q = reinterpret_cast<const QEntry*>(smem + L::offQueue);
-  uint8_t* A = smem + L::offA;
-  const int tid = threadIdx.x;
+  constexpr uint32_t head = 0;
   if (V == 0) {
     // Phase 1: bilinear tap sets of the 128 x 3 (row, plane) pairs -> shared memory (aliases the layer-2 operand, which is
     // only written after this tile's layer-1 MMA).
-    TapsH* tapbuf = reinterpret_cast<TapsH*>(smem + L::offH);
-    for (int it = tid; it < kTileM * 3; it += kThreads) {
+    for (int it = tid; it < kTileM * 3; it += NT) {
       const int m = it & (kTileM - 1), pl = it >> 7;
       const QEntry& e = q[(head + m) & (kQueueCap - 1)];
       const PlaneDev& P = f.plane[pl];
       tapbuf[it] = to_half_taps(make_taps(e.c[2 * pl], e.c[2 * pl + 1], P.W, P.H, P.wm1, P.hm1));
     }
-    __syncthreads();
+    sync();
     // Phase 2: consecutive lanes take consecutive 16-byte chunks of the SAME texel (6 chunks = 96 contiguous bytes per
-    // tap), so a warp-wide load touches ~8 cache lines instead of 32.
+    // tap), so a warp-wide load touches ~8 cache lines instead of 32.  The gather is latency-bound, so all 4 x J texel
+    // loads of a plane are issued before the first one is used.
+    constexpr int J = 768 / NT;                            // items per thread and plane (128 rows x 6 chunks = 768)
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {
       const PlaneDev& P = f.plane[pl];
+      TapsH t[J];
+      uint4 raw[J][4];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int it = tid + kThreads * j;                 // < 768 = 128 rows x 6 chunks
-        const int chunk = it % 6, m = it / 6;
-        const TapsH t = tapbuf[pl * kTileM + m];
-        *reinterpret_cast<uint4*>(A + (size_t)(pl * 6 + chunk) * L::kLboA + m * 16) = blend8h(P.app, chunk * 8, AC, t);
+      for (int j = 0; j < J; ++j) t[j] = tapbuf[pl * kTileM + (tid + NT * j) / 6];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int chunk = (tid + NT * j) % 6;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          raw[j][k] = __ldg(reinterpret_cast<const uint4*>(P.app + (size_t)t[j].off[k] * AC + chunk * 8));
+      }
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int it = tid + NT * j, chunk = it % 6, m = it / 6;
+        __half2 acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const __half2* h = reinterpret_cast<const __half2*>(&raw[j][k]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[e] = k == 0 ? __hmul2(t[j].w[0], h[e]) : __hfma2(t[j].w[k], h[e], acc[e]);
+        }
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t*>(&acc[0]); o.y = *reinterpret_cast<uint32_t*>(&acc[1]);
+        o.z = *reinterpret_cast<uint32_t*>(&acc[2]); o.w = *reinterpret_cast<uint32_t*>(&acc[3]);
+        *reinterpret_cast<uint4*>(A + (size_t)(pl * 6 + chunk) * L::kLboA + m * 16) = o;
       }
     }
   } else {
     // items (row m, 8-channel chunk): the phase code is shared by the three planes
-    for (int it = tid; it < kTileM * 9; it += kThreads) {
+    for (int it = tid; it < kTileM * 9; it += NT) {
       const int m = it & (kTileM - 1), chunk = it >> 7;
       const QEntry& e = q[(head + m) & (kQueueCap - 1)];
       const float xyz[3] = {e.c[0], e.c[1], e.c[3]};
@@ -366,6 +387,16 @@ __device__ __forceinline__ void mlp_gather(const FieldDev& f, uint8_t* smem, uin
     *reinterpret_cast<uint4*>(A + (size_t)(F / 8) * L::kLboA + m * 16) = o0;
     *reinterpret_cast<uint4*>(A + (size_t)(F / 8 + 1) * L::kLboA + m * 16) = o1;
   }
+}
+
+template <int V>
+__device__ __forceinline__ void mlp_gather(const FieldDev& f, uint8_t* smem, uint32_t head,
+                                           const float* __restrict__ dir, int dir_stride, const CamDev* cam) {
+  using L = MlpSmem<V>;
+  (void)head;                                   // every caller stages the tile at slot 0
+  mlp_gather_at<V, kThreads>(f, reinterpret_cast<const QEntry*>(smem + L::offQueue), smem + L::offA,
+                   reinterpret_cast<TapsH*>(smem + L::offH), (int)threadIdx.x, dir, dir_stride, cam,
+                   [] { __syncthreads(); });
 }
 
 // ----------------------------------------------------------------------------------------------------------
