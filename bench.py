@@ -339,11 +339,11 @@ def main():
     line = {
         "metric": "rays/sec (800x800, 192 samples/ray)", "value": value, "unit": "rays/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16 tensor-core operands, fp32 accumulate)",
-        "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"TriPlane {args.field} field, 800x800 rays x 192 samples/ray, gauge on, 256^3 alpha mask "
                                f"(BASELINE configs[1]" + (")" if world == 1 else f"; configs[4]: {world} frames/step ray-sharded + NCCL all-gather)"),
-                   "rays_per_step": n_batch, "l2": f"inputs rotate over {N_POSES} poses ({N_POSES * n_local * 24 / 1e6:.0f} MB of rays per rank > 126 MB L2)",
+                   "rays_per_step": n_batch,
+                   "arithmetic": "fp32 march / density / compositing; colour MLP fp16 operands with fp32 accumulation (tcgen05, TMEM)", "l2": f"inputs rotate over {N_POSES} poses ({N_POSES * n_local * 24 / 1e6:.0f} MB of rays per rank > 126 MB L2)",
                    "parallelism": "single GPU" if world == 1 else f"ray-sharded dp{world}, {BLOCK}-ray interleaved blocks"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_local * 24, "d2h_bytes_per_step": d2h,
                 "api": "ngf_b200.render_frames: ngf_field_render_host_async per frame (C ABI, pinned host buffers, 3 frames in flight)" if world == 1 else "pinned H2D + ngf_field_render + overlapped NCCL all-gather + D2H, host one step behind"},
