@@ -310,7 +310,8 @@ int ngf_neutex_timing_read(NgfNeutex h, int32_t* n_renders, double* raygen_ms, d
 
 /* Profiling aid (library built as is, NGF_NTX_DBG=4 in the environment when packing): per-layer clock64 stamps of CTA 0's
  * first tile — [25][4] = MMA warp saw a_ready | MMA warp issued the layer | worker 0 saw acc_ready | worker 0 finished the
- * epilogue. */
+ * epilogue — followed by 64 stamps of the weight ring during layer 5 ([2i], [2i+1] = MMA warp saw stage i full | issued its
+ * MMAs; [32+i] = producer saw the stage's slot empty).  out_host holds 164 values. */
 int ngf_neutex_debug_trace(NgfNeutex h, long long* out_host);
 
 #ifdef __cplusplus

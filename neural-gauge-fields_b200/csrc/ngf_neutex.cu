@@ -40,6 +40,71 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {      // one lane of a converged warp
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// ---- CTA-pair (cta_group::2) helpers: the two CTAs of a cluster run one M=256 MMA together; only rank 0 issues ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {        // every thread of both CTAs
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
+  uint32_t ok = 0, spins = 0;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 24)) __trap();
+  } while (!ok);
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem, uint32_t cols) {   // the same warp of both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D (128 lanes x N columns in each CTA) += A (each CTA's own 128 rows) . B (N rows: rank 0 holds [0, N/2), rank 1 the rest)
+__device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this offset in both CTAs of the pair once every MMA issued so far has completed
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
 // shared-memory map of ntx_mlp_kernel
 constexpr uint32_t kKGroupBytes = kRows * 16;            // one 8-wide K group of the 256-row A operand
 constexpr uint32_t offA = 0;                             // [32 K groups][256 rows][8 halves]  (split: lo half at +64 KiB)
@@ -59,8 +124,10 @@ struct Bars {
   uint64_t empty[kStages];
   uint64_t acc_ready;
   uint64_t a_ready;
+  uint64_t peer_full[kStages];   // CTA pairs, rank 0 only: rank 1's ring stage has landed (relayed by rank 1)
   uint32_t tmem_base;
 };
+static_assert(sizeof(Bars) <= 256, "barrier block");
 
 __device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkerThreads) : "memory"); }
@@ -190,9 +257,13 @@ __device__ __forceinline__ void write_encoding(uint8_t* A, int row, int ch, cons
 // ---------------------------------------------------------------------------------------------------------
 template <int ACT>
 __device__ __forceinline__ uint32_t act_pack(float a, float b) {
+  if (ACT == 0) {      // ReLU folded into the conversion: max(rn(x), 0) == rn(max(x, 0))
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+  }
   __half2 h = __floats2half2_rn(a, b);
-  if (ACT == 0) h = __hmax2(h, __float2half2_rn(0.f));
-  else h = __hmax2(h, __hmul2(h, __float2half2_rn(0.2f)));
+  h = __hmax2(h, __hmul2(h, __float2half2_rn(0.2f)));
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
@@ -269,96 +340,207 @@ __device__ __forceinline__ void sample_texture(const NetDev& net, float u, float
   }
 }
 
+// CG = 1: one CTA per 256-sample tile, every CTA streams the whole weight stream (cta_group::1 MMAs, M = 128).
+// CG = 2: the two CTAs of a cluster take 256 samples each and run every MMA together (cta_group::2, M = 256): each
+//         CTA streams only the weights of half of every layer's output rows — the pair's tensor cores read both halves —
+//         so the per-SM weight stream and its shared-memory operand traffic are halved and the 64 KiB ring reaches a
+//         whole 256x256 layer ahead.  Rank 0 issues the MMAs; its commits are multicast to the barriers of both CTAs;
+//         rank 1 relays "my ring stage has landed" and "my A operand is written" to rank 0's barriers.
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_constant__ NetDev net,
                                                               const __grid_constant__ RenderArgsN a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Bars* bars = reinterpret_cast<Bars*>(smem + offBar);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint32_t count = *reinterpret_cast<volatile const unsigned int*>(a.counters);
-  const uint32_t n_tiles = (count + kRows - 1) / kRows;
-  if (blockIdx.x >= n_tiles) return;
+  // a unit = the CG tiles one CTA (pair) works on together; both CTAs of a pair see the same unit sequence
+  const uint32_t n_tiles = (count + kRows * CG - 1) / (kRows * CG);
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;
+  const uint32_t unit0 = CG == 2 ? blockIdx.x >> 1 : blockIdx.x, unit_step = CG == 2 ? gridDim.x >> 1 : gridDim.x;
+  if (unit0 >= n_tiles) return;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+      mbar_init(&bars->peer_full[s], 1);
+    }
     mbar_init(&bars->acc_ready, 1);
-    mbar_init(&bars->a_ready, kWorkerWarps);
+    mbar_init(&bars->a_ready, kWorkerWarps * CG);
     fence_mbar_init();
   }
-  __syncthreads();
-  if (warp == kWorkerWarps) tmem_alloc(&bars->tmem_base, 512);
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == kWorkerWarps) {
+    if (CG == 2) tmem_alloc_cg2(&bars->tmem_base, 512); else tmem_alloc(&bars->tmem_base, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
+  const uint32_t nst = net.stream_bytes / kStageBytes;       // ring stages per unit
   if (warp == kWorkerWarps + 1) {
     // ------------------------------------------------------------------ weight producer
+    // this rank's stream is a run of whole ring stages; it is copied stage after stage, unit after unit
+    if (lane == 0) {
+      const uint8_t* wsrc = net.wstream + (size_t)crank * net.stream_bytes;
+      uint32_t it = 0;
+      const uint32_t q0 = net.layer[kTraceLayer].off / kStageBytes;
+      for (uint32_t unit = unit0; unit < n_tiles; unit += unit_step) {
+        for (uint32_t q = 0; q < nst; ++q, ++it) {
+          const uint32_t s = it % kStages;
+          mbar_wait(&bars->empty[s], ((it / kStages) & 1u) ^ 1u);
+          if ((net.dbg & 4) && blockIdx.x == 0 && unit == unit0 && q - q0 < 12u) net.trace[100 + 32 + (q - q0)] = clock64();
+          if (net.dbg & 8) { mbar_arrive(&bars->full[s]); continue; }
+          mbar_expect_tx(&bars->full[s], kStageBytes);
+          bulk_g2s(smem + offRing + s * kStageBytes, wsrc + (size_t)q * kStageBytes, kStageBytes, &bars->full[s]);
+        }
+      }
+    }
+  } else if (warp == kWorkerWarps && CG == 2 && crank != 0) {
+    // ------------------------------------------------------------------ rank 1: relay "stage landed" to rank 0
     if (lane == 0) {
       uint32_t it = 0;
-      const uint8_t* wsrc = net.wpack + (size_t)(blockIdx.x % (unsigned)net.w_copies) * net.wpack_stride;
-      for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int l = 0; l < kNumLayers; ++l) {
-          const LayerDesc& L = net.layer[l];
-          const int nk = (L.K + L.Kext) / 16 + L.bias_slice;
-          for (int kk = 0; kk < nk; kk += kSlicesPerStage, ++it) {
-            const uint32_t s = it % kStages;
-            const int n = nk - kk < kSlicesPerStage ? nk - kk : kSlicesPerStage;
-            const uint32_t bytes = (uint32_t)n * L.chunk_bytes;          // consecutive slices are contiguous
-            mbar_wait(&bars->empty[s], ((it / kStages) & 1u) ^ 1u);
-            mbar_expect_tx(&bars->full[s], bytes);
-            bulk_g2s(smem + offRing + s * kStageBytes, wsrc + L.w_off + (size_t)kk * L.chunk_bytes, bytes, &bars->full[s]);
-          }
+      for (uint32_t unit = unit0; unit < n_tiles; unit += unit_step) {
+        for (uint32_t q = 0; q < nst; ++q, ++it) {
+          const uint32_t s = it % kStages;
+          mbar_wait(&bars->full[s], (it / kStages) & 1u);
+          mbar_arrive_cluster(map_to_cta(smem_u32(&bars->peer_full[s]), 0));
         }
       }
     }
   } else if (warp == kWorkerWarps) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      uint32_t it = 0, par_a = 0;
-      const uint32_t a0 = smem_u32(smem + offA), a2 = smem_u32(smem + offA2), r0 = smem_u32(smem + offRing);
-      for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int l = 0; l < kNumLayers; ++l) {
-          const LayerDesc& L = net.layer[l];
-          const int nk_main = L.K / 16, nk_ext = L.Kext / 16, nk = nk_main + nk_ext + L.bias_slice;
-          const uint32_t idesc = umma_idesc(128, L.N);
-          const uint32_t lboB = (uint32_t)L.N * 16u;
-          mbar_wait(&bars->a_ready, par_a);
-          par_a ^= 1u;
-          tc_fence_after();
-          const bool tr = (net.dbg & 4) && blockIdx.x == 0 && tile == blockIdx.x;
+    // ------------------------------------------------------------------ MMA issuer (rank 0 of a pair)
+    // The whole warp walks the loop in lock step and one elected lane issues: every operand of the issue loop then
+    // derives from warp-uniform values (kernel parameters, loop counters, warp-broadcast loads), so the descriptors
+    // are built in the uniform datapath.  (With the loop under `if (lane == 0)` they went through vector registers,
+    // R2UR and a replay loop around each tcgen05.mma: ~226 cycles per M128 N256 K16 MMA instead of the 128-cycle floor,
+    // scripts/micro/umma_issue.cu.)
+    const uint32_t n_units = __shfl_sync(0xffffffffu, n_tiles, 0);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t a0 = smem_u32(smem + offA), a2 = smem_u32(smem + offA2), r0 = smem_u32(smem + offRing);
+    constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);              // SBO = 128 B, descriptor version 1
+    constexpr uint32_t kALo = (kKGroupBytes >> 4) << 16;                // LBO of the A operand
+    const bool skip = (net.dbg & 2) != 0;
+    // The tensor pipe queues only about two MMAs behind the one it is executing, so everything the issuing lane does
+    // between the last MMA of one ring stage and the first of the next (commit, barrier wait, descriptor set-up) has
+    // to fit in ~256 cycles or the pipe drains and pays its ~300-cycle start-up again: no divisions, no warp-wide
+    // hand-offs inside a layer; where a layer's first / last stage is shared with its neighbours is precomputed on the
+    // host (LayerDesc::first_have, tail_release).
+    uint32_t par_a = 0, ui = 0;
+    for (uint32_t unit = unit0; unit < n_units; unit += unit_step, ++ui) {
+#pragma unroll 1
+      for (int l = 0; l < kNumLayers; ++l) {
+        const LayerDesc& L = net.layer[l];
+        const uint32_t idesc = umma_idesc(128 * CG, L.N);
+        const uint32_t rowsB = (uint32_t)L.N / CG;
+        const uint32_t bLo = ((rowsB * 16u) >> 4) << 16;                // LBO of the B operand
+        const uint32_t bLoOff = (rowsB * 32u) >> 4;                     // lo part of a split slice, in descriptor units
+        const uint32_t slice = L.slice;
+        const int nk_main = L.K >> 4, nk_ext = L.Kext >> 4, nk = nk_main + nk_ext + L.bias_slice;
+        const bool split = L.split != 0;
+        if (CG == 2) mbar_wait_cluster(&bars->a_ready, par_a); else mbar_wait(&bars->a_ready, par_a);
+        par_a ^= 1u;
+        tc_fence_after();
+        const bool tr = (net.dbg & 4) && blockIdx.x == 0 && unit == unit0;
+        if (elect_one()) {
           if (tr) net.trace[l * 4 + 0] = clock64();
-          for (int k0 = 0; k0 < nk; k0 += kSlicesPerStage, ++it) {
-            const uint32_t s = it % kStages;
-            const int n = nk - k0 < kSlicesPerStage ? nk - k0 : kSlicesPerStage;
-            mbar_wait(&bars->full[s], (it / kStages) & 1u);
-            for (int j = 0; j < n; ++j) {
-              const int kk = k0 + j;
-              const bool bias_only = kk >= nk_main + nk_ext;         // A = the constant-one columns, weights = bias
-              const uint32_t abase = kk < nk_main ? a0 + (uint32_t)kk * 2u * kKGroupBytes
-                                     : bias_only  ? a2 + 4u * kKGroupBytes
-                                                  : a2 + (uint32_t)(kk - nk_main) * 2u * kKGroupBytes;
-              const uint32_t bbase = r0 + s * kStageBytes + (uint32_t)j * L.chunk_bytes;
-              if (net.dbg & 2) continue;
+          // ring state of the layer's first slice
+          const uint32_t g0 = ui * nst + (L.off >> 14);          // kStageBytes == 1 << 14
+          uint32_t s = g0 % kStages, par = (g0 / kStages) & 1u;
+          uint32_t rem = kStageBytes - (L.off & (kStageBytes - 1u));      // bytes of the stage still unread
+          auto wait_stage = [&](uint32_t st, uint32_t ph) {
+            mbar_wait(&bars->full[st], ph);
+            if (CG == 2) mbar_wait_cluster(&bars->peer_full[st], ph);
+            tc_fence_after();
+          };
+          if (!L.first_have) wait_stage(s, par);                 // else the previous layer left this stage acquired
+          uint32_t b_lo = (((r0 + s * kStageBytes + (L.off & (kStageBytes - 1u))) & 0x3FFFFu) >> 4) | bLo;
+          const uint32_t b_step = slice >> 4;
+          const bool tail_release = L.tail_release != 0;
+          uint32_t acc = 0;                                      // 0 only for the layer's first K step
+          int left = nk;                                         // slices of the layer still to issue
+          // `n` consecutive K=16 slices whose A operand starts at abase and advances by two K groups per slice
+          auto run = [&](uint32_t abase, int n, bool lo_terms) {
+            uint32_t a_lo = ((abase & 0x3FFFFu) >> 4) | kALo;
+            // fast path: whole ring stages of a 256-wide layer as straight-line code (2 * CG slices, 4 * CG MMAs),
+            // so that the descriptors stay in uniform registers from one MMA to the next
+            constexpr int SPS = 2 * CG;
+            const bool fast = !lo_terms && slice == kSliceBytes / CG && !skip;
+#pragma unroll 1
+            for (; n > 0; --n, --left) {
+              while (fast && n >= SPS && rem == kStageBytes) {
+                const uint32_t s_next = (s + 1u) % kStages, par_next = par ^ (s == kStages - 1u ? 1u : 0u);
 #pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                const uint32_t d = tmem + (uint32_t)half * 256u;
-                const uint32_t ah = abase + (uint32_t)half * 128u * 16u;
-                const uint64_t da_hi = umma_desc(ah, kKGroupBytes, 128u);
-                const uint64_t db_hi = umma_desc(bbase, lboB, 128u);
-                umma_f16(d, da_hi, db_hi, idesc, kk > 0);
-                if (L.split && !bias_only) {
-                  const uint64_t da_lo = umma_desc(ah + kALoOff, kKGroupBytes, 128u);
-                  const uint64_t db_lo = umma_desc(bbase + (uint32_t)L.N * 32u, lboB, 128u);
-                  umma_f16(d, da_lo, db_hi, idesc, 1u);
-                  umma_f16(d, da_hi, db_lo, idesc, 1u);
+                for (int j = 0; j < SPS; ++j) {
+                  if (j == SPS - 1 && left > SPS) wait_stage(s_next, par_next);   // one slice early, under queued MMAs
+                  const uint64_t db = ((uint64_t)kDescHi << 32) | (b_lo + (uint32_t)j * ((kSliceBytes / CG) >> 4));
+                  const uint64_t da0 = ((uint64_t)kDescHi << 32) | (a_lo + (uint32_t)j * ((2u * kKGroupBytes) >> 4));
+                  const uint64_t da1 = da0 + ((128u * 16u) >> 4);
+                  if (CG == 2) {
+                    umma_f16_cg2(tm, da0, db, idesc, j == 0 ? acc : 1u);
+                    umma_f16_cg2(tm + 256u, da1, db, idesc, j == 0 ? acc : 1u);
+                  } else {
+                    umma_f16(tm, da0, db, idesc, j == 0 ? acc : 1u);
+                    umma_f16(tm + 256u, da1, db, idesc, j == 0 ? acc : 1u);
+                  }
+                }
+                if (CG == 2) umma_commit_cg2(&bars->empty[s]); else umma_commit(&bars->empty[s]);
+                acc = 1u;
+                a_lo += (uint32_t)SPS * ((2u * kKGroupBytes) >> 4);
+                n -= SPS;
+                left -= SPS;
+                s = s_next;
+                par = par_next;
+                b_lo = (((r0 + s * kStageBytes) & 0x3FFFFu) >> 4) | bLo;
+              }
+              if (n == 0) break;
+              // generic path, one slice: stages shared with other layers, split layers, view-direction and bias slices.
+              // The wait for the next stage goes one slice early, under the MMAs that are still queued
+              if (rem == slice && left > 1) wait_stage((s + 1u) % kStages, par ^ (s == kStages - 1u ? 1u : 0u));
+              if (!skip) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                  const uint32_t d = tm + (uint32_t)half * 256u;
+                  const uint64_t da_hi = ((uint64_t)kDescHi << 32) | (a_lo + (uint32_t)half * ((128u * 16u) >> 4));
+                  const uint64_t db_hi = ((uint64_t)kDescHi << 32) | b_lo;
+                  if (CG == 2) umma_f16_cg2(d, da_hi, db_hi, idesc, acc); else umma_f16(d, da_hi, db_hi, idesc, acc);
+                  if (lo_terms) {
+                    const uint64_t da_lo = da_hi + (kALoOff >> 4);
+                    const uint64_t db_lo = db_hi + bLoOff;
+                    if (CG == 2) {
+                      umma_f16_cg2(d, da_lo, db_hi, idesc, 1u);
+                      umma_f16_cg2(d, da_hi, db_lo, idesc, 1u);
+                    } else {
+                      umma_f16(d, da_lo, db_hi, idesc, 1u);
+                      umma_f16(d, da_hi, db_lo, idesc, 1u);
+                    }
+                  }
                 }
               }
+              acc = 1u;
+              a_lo += (2u * kKGroupBytes) >> 4;
+              b_lo += b_step;
+              rem -= slice;
+              // hand the stage back once its MMAs have completed: it is used up, or the rest of it is padding
+              if (rem == 0u || (left == 1 && tail_release)) {
+                if (CG == 2) umma_commit_cg2(&bars->empty[s]); else umma_commit(&bars->empty[s]);
+              }
+              if (rem == 0u) {
+                s = (s + 1u) % kStages;
+                par ^= (s == 0u) ? 1u : 0u;
+                rem = kStageBytes;
+                b_lo = (((r0 + s * kStageBytes) & 0x3FFFFu) >> 4) | bLo;
+              }
             }
-            umma_commit(&bars->empty[s]);
-          }
-          umma_commit(&bars->acc_ready);
+          };
+          run(a0, nk_main, split);                               // the layer's own inputs
+          run(a2, nk_ext, split);                                // view-direction inputs (block2 layer 0)
+          run(a2 + 4u * kKGroupBytes, L.bias_slice, false);      // constant-one columns x (bias_hi, bias_lo)
+          if (CG == 2) umma_commit_cg2(&bars->acc_ready); else umma_commit(&bars->acc_ready);
           if (tr) net.trace[l * 4 + 1] = clock64();
         }
+        __syncwarp();
       }
     }
   } else {
@@ -371,15 +553,26 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
     uint32_t par_acc = 0;
     int trace_l = 0;
     bool trace_on = false;
+    const uint32_t a_ready_rank0 = CG == 2 ? map_to_cta(smem_u32(&bars->a_ready), 0) : 0u;
     auto signal_a = [&]() {
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->a_ready);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(a_ready_rank0);     // both CTAs' 16 worker warps arrive on rank 0's barrier
+        else mbar_arrive(&bars->a_ready);
+      }
     };
     auto mark_done = [&]() { if (trace_on && trace_l < kNumLayers) { net.trace[trace_l * 4 + 3] = clock64(); ++trace_l; } };
+    // One warp watches the mbarrier, the other fifteen sleep on a hardware barrier: sixteen warps polling acc_ready
+    // through the whole MMA phase slowed the tensor pipe's own shared-memory traffic down.
     auto wait_acc = [&]() {
-      mbar_wait_backoff(&bars->acc_ready, par_acc);
+      if (net.dbg & 16) {
+        mbar_wait_backoff(&bars->acc_ready, par_acc);
+      } else {
+        if (warp == 0) mbar_wait(&bars->acc_ready, par_acc);
+        asm volatile("bar.sync 2, %0;" ::"n"(kWorkerThreads) : "memory");
+      }
       par_acc ^= 1u;
       tc_fence_after();
       if (trace_on && trace_l < kNumLayers) net.trace[trace_l * 4 + 2] = clock64();
@@ -399,10 +592,10 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
       const float zero[3] = {0.f, 0.f, 0.f};
       write_encoding<3, 6, 6, false, false, true>(smem + offA2, row, ch, zero);
     }
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      trace_on = (net.dbg & 4) && blockIdx.x == 0 && tile == blockIdx.x && tid == 0;
+    for (uint32_t tile = unit0; tile < n_tiles; tile += unit_step) {
+      trace_on = (net.dbg & 4) && blockIdx.x == 0 && tile == unit0 && tid == 0;
       trace_l = 0;
-      const uint32_t item = tile * kRows + row;
+      const uint32_t item = (tile * CG + crank) * kRows + row;
       int id = -1;
       float p[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
       if (item < count) {
@@ -497,9 +690,17 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
       }
     }
   }
+  __syncwarp();            // lane 0 of the producer / issuer / relay warps re-joins its warp
   tc_fence_before();
-  __syncthreads();
-  if (warp == kWorkerWarps) tmem_dealloc(tmem, 512);
+  if (CG == 2) {
+    // every worker of both CTAs has seen the last acc_ready, i.e. every MMA and every multicast commit of rank 0 is
+    // done; neither CTA may release its shared memory or TMEM before the other has got this far
+    cluster_sync_all();
+    if (warp == kWorkerWarps) tmem_dealloc_cg2(tmem, 512);
+  } else {
+    __syncthreads();
+    if (warp == kWorkerWarps) tmem_dealloc(tmem, 512);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -628,14 +829,35 @@ cudaError_t launch_neutex_raygen(const NetDev& net, const RenderArgsN& a, cudaSt
 cudaError_t launch_neutex_mlp(const NetDev& net, const RenderArgsN& a, int num_sms, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ntx_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(ntx_mlp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(ntx_mlp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
+  }
+  if (net.cg == 2) {
+    // one CTA pair (a cluster of two, i.e. the two SMs of a TPC) per 512 work items
+    long long worst = (a.n_rays * kS + 2 * kRows - 1) / (2 * kRows);
+    long long pairs = num_sms / 2 < worst ? num_sms / 2 : worst;
+    if (pairs < 1) pairs = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, ntx_mlp_kernel<2>, net, a);
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
   }
   long long worst = (a.n_rays * kS + kRows - 1) / kRows;
   long long grid = num_sms < worst ? num_sms : worst;
   if (grid < 1) grid = 1;
-  ntx_mlp_kernel<<<(unsigned)grid, kThreads, kSmemBytes, st>>>(net, a);
+  ntx_mlp_kernel<1><<<(unsigned)grid, kThreads, kSmemBytes, st>>>(net, a);
   count_launch();
   return cudaGetLastError();
 }

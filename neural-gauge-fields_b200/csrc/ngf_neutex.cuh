@@ -21,9 +21,10 @@ constexpr int kWorkerThreads = 512;    // two threads per tile row (TMEM lane): 
 constexpr int kWorkerWarps = kWorkerThreads / 32;
 constexpr int kThreads = kWorkerThreads + 64;   // + 1 MMA-issue warp + 1 weight-producer warp
 constexpr int kStages = 4;             // weight ring
-constexpr int kSlicesPerStage = 2;     // K=16 weight slices per ring stage: one wait / copy / commit per stage
-constexpr uint32_t kSliceBytes = 8192; // one K=16 slice of a 256-wide layer (or hi+lo slices of a <=128-wide one)
-constexpr uint32_t kStageBytes = kSlicesPerStage * kSliceBytes;
+constexpr uint32_t kSliceBytes = 8192; // largest K=16 slice: a 256-wide layer (or hi+lo of a 128-wide one) at cg = 1
+constexpr uint32_t kStageBytes = 16384; // one cp.async.bulk per stage: two 8 KiB slices (cg = 1), four 4 KiB (cg = 2)
+constexpr int kTraceWords = 25 * 4 + 64;   // NGF_NTX_DBG=4: per-layer stamps + ring stamps of layer kTraceLayer
+constexpr int kTraceLayer = 5;
 constexpr int kNumLayers = 25;         // MMA layers per tile: geometry 11, gauge 4, texture block1 6, block2 4
 
 struct LayerDesc {
@@ -33,20 +34,26 @@ struct LayerDesc {
   int split;            // 1: hi/lo split-fp16 operands, 3 MMAs per K step (gauge network)
   int bias_slice;       // 1: one more K=16 slice whose A operand is the constant-one columns of the view operand and
                         //    whose weights are (bias_hi, bias_lo); 0: the bias rides in the Kext slices (block2 layer 0)
-  uint32_t w_off;       // byte offset of the layer's first weight chunk in the packed weight stream
-  uint32_t chunk_bytes; // bytes per K=16 chunk (N*32, doubled when split)
+  uint32_t off;         // byte offset of the layer's first K=16 slice inside one rank's weight stream (8 KiB aligned)
+  uint32_t slice;       // bytes per K=16 slice of one rank: (N / cg) * 32, doubled when split
+  int first_have;       // 1: the layer's first slice lies in the ring stage the previous layer ended in (already waited for)
+  int tail_release;     // 1: the layer's last (partly used) stage holds nothing of the next layer: hand it back
 };
 
 struct NetDev {
   LayerDesc layer[kNumLayers];
-  const uint8_t* wpack;   // all weight chunks, tcgen05 K-major core-matrix order, in execution order
-  uint32_t wpack_stride;  // optional replicas of the stream (NGF_NTX_COPIES, default 1): CTA b reads copy b % w_copies
-  int w_copies;
+  // Weight stream(s), tcgen05 K-major core-matrix order, layers in execution order, padded to whole ring stages.
+  // cg = 1: one stream with all N output rows of every layer.  cg = 2: [rank 0 stream][rank 1 stream]; rank r holds the
+  // output rows [r*N/2, (r+1)*N/2) of every layer (its half of the B operand of the pair's M=256 MMAs).
+  const uint8_t* wstream;
+  uint32_t stream_bytes;  // bytes of one rank's stream
+  int cg;                 // 1: one CTA per 256-sample tile (cta_group::1); 2: CTA pairs (cta_group::2) (NGF_NTX_CG)
   const float* heads;     // fp32 head weights (16-byte aligned rows first, then the biases), offsets kHead* below
   const float* texture;   // [h][w][c] edited texture or nullptr
   int tex_h, tex_w, tex_c;
   float jitter;
-  int dbg;                // NGF_NTX_DBG (profiling experiments only): 2 = skip MMA issue, 4 = record a timeline
+  int dbg;                // NGF_NTX_DBG (profiling experiments only): 2 = skip MMA issue, 4 = record a timeline,
+                          //          8 = skip the weight copies (ring stages are released without data)
   long long* trace;       // dbg & 4: [25 layers][4] clock64 stamps of CTA 0's first tile (a_ready seen, MMAs issued,
                           //          acc_ready seen by worker 0, epilogue done by worker 0)
 };

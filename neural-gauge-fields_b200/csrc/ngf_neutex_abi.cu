@@ -34,7 +34,7 @@ struct NgfNeutex_ {
   int device = 0;
   int num_sms = 0;
   NetDev net{};
-  uint8_t* wpack = nullptr;
+  uint8_t* wstream = nullptr;                // weight stream(s) of the MLP kernel (one per CTA rank)
   float* heads = nullptr;
   float* texture = nullptr;
   // workspace for up to cap_rays rays
@@ -67,7 +67,7 @@ static void ntx_free_all(NgfNeutex_* h) {
   ntx_free_ws(h);
   ntx_free_chunks(h);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
-  cudaFree(h->wpack); cudaFree(h->heads); cudaFree(h->texture); cudaFree(h->counters); cudaFree(h->cam_bg);
+  cudaFree(h->wstream); cudaFree(h->heads); cudaFree(h->texture); cudaFree(h->counters); cudaFree(h->cam_bg);
 }
 
 struct Guard {
@@ -89,24 +89,27 @@ static cudaError_t fetch(std::vector<float>& dst, const float* src, size_t n) {
   return cudaMemcpy(dst.data(), src, n * sizeof(float), cudaMemcpyDefault);
 }
 
-// Append the tcgen05 K-major chunks of one layer: for each K=16 step, [hi: 2 K-groups x N rows x 8 halves][lo: same]
-static void pack_layer(std::vector<uint8_t>& out, const std::vector<float>& W, int N, int K_in, int K_total, bool split) {
-  const int nk = K_total / 16;
-  const size_t chunk = (size_t)N * 32 * (split ? 2 : 1);
-  const size_t base = out.size();
-  out.resize(base + chunk * nk, 0);
-  for (int kk = 0; kk < nk; ++kk) {
-    __half* hi = reinterpret_cast<__half*>(out.data() + base + chunk * kk);
-    __half* lo = hi + (size_t)N * 16;
-    for (int kg = 0; kg < 2; ++kg)
-      for (int r = 0; r < N; ++r)
-        for (int e = 0; e < 8; ++e) {
-          const int k = kk * 16 + kg * 8 + e;
-          const float w = k < K_in ? W[(size_t)r * K_in + k] : 0.f;
-          const __half h = __float2half_rn(w);
-          hi[((size_t)kg * N + r) * 8 + e] = h;
-          if (split) lo[((size_t)kg * N + r) * 8 + e] = __float2half_rn(w - __half2float(h));
-        }
+// Append one layer to the weight stream(s).  ranks = 1: one stream with all N output rows.  ranks = 2 (CTA pairs): rank r
+// gets the rows [r*N/2, (r+1)*N/2).  Per K=16 step a rank's slice is [hi: 2 K-groups x rows x 8 halves][lo: same, split
+// layers only] in tcgen05 K-major core-matrix order; W is [N][K_total] row-major.
+static void pack_layer(std::vector<uint8_t>* out, int ranks, const std::vector<float>& W, int N, int K_total, bool split) {
+  const int nk = K_total / 16, rows = N / ranks;
+  const size_t slice = (size_t)rows * 32 * (split ? 2 : 1);
+  for (int rank = 0; rank < ranks; ++rank) {
+    const size_t base = out[rank].size();
+    out[rank].resize(base + slice * nk, 0);
+    for (int kk = 0; kk < nk; ++kk) {
+      __half* hi = reinterpret_cast<__half*>(out[rank].data() + base + slice * kk);
+      __half* lo = hi + (size_t)rows * 16;
+      for (int kg = 0; kg < 2; ++kg)
+        for (int r = 0; r < rows; ++r)
+          for (int e = 0; e < 8; ++e) {
+            const float w = W[(size_t)(rank * rows + r) * K_total + kk * 16 + kg * 8 + e];
+            const __half h = __float2half_rn(w);
+            hi[((size_t)kg * rows + r) * 8 + e] = h;
+            if (split) lo[((size_t)kg * rows + r) * 8 + e] = __float2half_rn(w - __half2float(h));
+          }
+    }
   }
 }
 
@@ -143,7 +146,9 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
   h->device = device;
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
 
-  std::vector<uint8_t> wp;
+  int cg = 1;
+  { const char* ce = getenv("NGF_NTX_CG"); if (ce && atoi(ce) == 2 && h->num_sms >= 2) cg = 2; }
+  std::vector<uint8_t> wp[2];
   std::vector<float> heads(kHeadFloats, 0.f), W, B, Wb;
   int li = 0;
   // The bias is accumulated by the tensor core: the view-direction operand carries two constant-one columns
@@ -158,8 +163,10 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
     const int K_total = merged ? K + Kext : K + 16;
     const int bias_col = merged ? K + 39 : K + 7;
     L.K = K; L.Kext = Kext; L.N = N; L.split = split ? 1 : 0; L.bias_slice = merged ? 0 : 1;
-    L.w_off = (uint32_t)wp.size();
-    L.chunk_bytes = (uint32_t)N * 32u * (split ? 2u : 1u);
+    const size_t al = kSliceBytes / cg;      // slices are powers of two <= al: none straddles a 16 KiB ring stage
+    for (int r = 0; r < cg; ++r) wp[r].resize((wp[r].size() + al - 1) / al * al, 0);
+    L.off = (uint32_t)wp[0].size();
+    L.slice = (uint32_t)(N / cg) * 32u * (split ? 2u : 1u);
     Wb.assign((size_t)N * K_total, 0.f);
     for (int r = 0; r < N; ++r) {
       for (int k = 0; k < l.in_dim; ++k) Wb[(size_t)r * K_total + k] = W[(size_t)r * l.in_dim + k];
@@ -167,7 +174,7 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
       Wb[(size_t)r * K_total + bias_col] = bh;
       Wb[(size_t)r * K_total + bias_col + 1] = B[r] - bh;
     }
-    pack_layer(wp, Wb, N, K_total, K_total, split);
+    pack_layer(wp, cg, Wb, N, K_total, split);
     return NGF_OK;
   };
   auto head = [&](const NgfLinear& l, int w_off, int b_off) -> int {
@@ -188,16 +195,29 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
   if (!rc) rc = head(d->tex_block2[4], kHeadB2, kHeadB2B);
   if (rc) { ntx_free_all(h); delete h; return rc; }
 
-  // Replicate the weight stream: all CTAs walk it in lock step, so a single copy is read by 148 SMs at the same
-  // addresses at the same time and serialises on a few L2 slices.
-  int copies = 1;
-  { const char* ce = getenv("NGF_NTX_COPIES"); if (ce && atoi(ce) >= 1 && atoi(ce) <= 64) copies = atoi(ce); }
-  const size_t stride = (wp.size() + 4095) / 4096 * 4096 + 4096 * 3;     // odd number of 4 KiB pages apart
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->wpack), stride * copies);
-  for (int c = 0; c < copies && e == cudaSuccess; ++c)
-    e = cudaMemcpy(h->wpack + stride * c, wp.data(), wp.size(), cudaMemcpyHostToDevice);
-  h->net.wpack_stride = (uint32_t)stride;
-  h->net.w_copies = copies;
+  // which layers share a ring stage with their neighbours (the MMA issuer waits for / hands back a stage exactly once)
+  for (int l = 0; l < kNumLayers; ++l) {
+    LayerDesc& L = h->net.layer[l];
+    const uint32_t nk = (uint32_t)((L.K + L.Kext) / 16 + L.bias_slice), end = L.off + nk * L.slice;
+    L.first_have = 0;
+    L.tail_release = 0;
+    if (l > 0) {
+      const LayerDesc& P = h->net.layer[l - 1];
+      const uint32_t pend = P.off + (uint32_t)((P.K + P.Kext) / 16 + P.bias_slice) * P.slice;
+      L.first_have = (pend % kStageBytes != 0 && pend / kStageBytes == L.off / kStageBytes) ? 1 : 0;
+    }
+    if (end % kStageBytes != 0) {
+      const bool last = l == kNumLayers - 1;
+      L.tail_release = (last || h->net.layer[l + 1].off / kStageBytes != end / kStageBytes) ? 1 : 0;
+    }
+  }
+  // every rank's stream is padded to whole ring stages: the producer copies stage after stage, unit after unit
+  for (int r = 0; r < cg; ++r) wp[r].resize((wp[r].size() + kStageBytes - 1) / kStageBytes * kStageBytes, 0);
+  h->net.stream_bytes = (uint32_t)wp[0].size();
+  h->net.cg = cg;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->wstream), (size_t)cg * wp[0].size());
+  for (int r = 0; r < cg && e == cudaSuccess; ++r)
+    e = cudaMemcpy(h->wstream + (size_t)r * wp[0].size(), wp[r].data(), wp[r].size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->heads), heads.size() * sizeof(float));
   if (e == cudaSuccess) e = cudaMemcpy(h->heads, heads.data(), heads.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->counters), 64);
@@ -211,14 +231,14 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
     ntx_free_all(h); delete h;
     return ngf_set_error(NGF_ECUDA, "ngf_neutex_pack: %s", cudaGetErrorString(e));
   }
-  h->net.wpack = h->wpack; h->net.heads = h->heads;
+  h->net.wstream = h->wstream; h->net.heads = h->heads;
   h->net.texture = h->texture; h->net.tex_h = d->tex_h; h->net.tex_w = d->tex_w; h->net.tex_c = d->tex_c;
   h->net.jitter = d->jitter;
   { const char* e = getenv("NGF_NTX_DBG"); h->net.dbg = e ? atoi(e) : 0; }
   h->net.trace = nullptr;
   if (h->net.dbg & 4) {
-    cudaMalloc(reinterpret_cast<void**>(&h->net.trace), kNumLayers * 4 * sizeof(long long));
-    cudaMemset(h->net.trace, 0, kNumLayers * 4 * sizeof(long long));
+    cudaMalloc(reinterpret_cast<void**>(&h->net.trace), kTraceWords * sizeof(long long));
+    cudaMemset(h->net.trace, 0, kTraceWords * sizeof(long long));
   }
   *out = h;
   return NGF_OK;
@@ -365,12 +385,12 @@ int ngf_neutex_copy_samples(NgfNeutex h, int64_t first_sample, int64_t n, float*
   return NGF_OK;
 }
 
-int ngf_neutex_debug_trace(NgfNeutex h, long long* out_host) {     /* NGF_NTX_DBG=4 only: 25 x 4 clock64 stamps */
+int ngf_neutex_debug_trace(NgfNeutex h, long long* out_host) {     /* NGF_NTX_DBG=4 only: 25 x 4 + 64 clock64 stamps */
   if (!h || !out_host) return ngf_set_error(NGF_EINVAL, "NULL argument");
   if (!h->net.trace) return ngf_set_error(NGF_EINVAL, "tracing is off (NGF_NTX_DBG=4)");
   Guard g(h->device);
   CUN(cudaDeviceSynchronize());
-  CUN(cudaMemcpy(out_host, h->net.trace, kNumLayers * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CUN(cudaMemcpy(out_host, h->net.trace, kTraceWords * sizeof(long long), cudaMemcpyDeviceToHost));
   return NGF_OK;
 }
 
