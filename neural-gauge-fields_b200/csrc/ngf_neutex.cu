@@ -113,8 +113,11 @@ constexpr uint32_t offA2 = offA + kABytes;               // view-direction opera
 constexpr uint32_t kA2Bytes = 6 * kKGroupBytes;          //   constant-one columns (39, 40) that carry the biases, 7 zeros
 constexpr uint32_t offRing = offA2 + kA2Bytes;
 constexpr uint32_t offHx = offRing + kStages * kStageBytes;   // head partial sums exchanged between a row's two threads
-constexpr uint32_t kHxBytes = 2 * kRows * 16;
-constexpr uint32_t offBar = offHx + kHxBytes;
+constexpr uint32_t kHxBytes = 2 * kRows * 12;                 //   [2 column halves][256 rows][3 floats]
+constexpr uint32_t offHw = offHx + kHxBytes;                  // fp32 weights of the head layer in flight (<= 3 x 256)
+constexpr uint32_t kHwBytes = 3 * 256 * 4;
+constexpr uint32_t offBar = offHw + kHwBytes;
+static_assert(offBar + 256 <= 227 * 1024, "shared memory budget");
 constexpr uint32_t kSmemBytes = offBar + 256;
 constexpr uint32_t kALoOff = 16 * kKGroupBytes;          // lo operand of split layers (K <= 128)
 constexpr int kOnesCol = 39;                             // A2 columns 39 and 40 are 1.0
@@ -317,6 +320,51 @@ __device__ __forceinline__ void epilogue(uint32_t taddr, uint8_t* A, int row, in
       }
     }
   }
+}
+
+// Epilogue of a layer that feeds a narrow fp32 head (density, uv, color1, block2 output): fp32 activation, NH partial dot
+// products over this thread's NC columns, optionally the fp16 A operand of the next layer (WRITE_A).  The head's weight
+// rows [NH][N] were staged in shared memory by stage_head() while the layer's MMAs ran: every lane reads the same
+// address (one broadcast LDS.128 per four weights).  Read from global memory they cost ~10 000 cycles per head layer:
+// with 227 KB of shared memory carved out nothing stays in L1, so each of the 96 loads was an L2 round trip; as
+// constant-bank operands (kernel parameters) the 3 KB per head thrashed the constant cache just the same.
+template <int N, int ACT, bool WRITE_A, int NH, int CH>
+__device__ __forceinline__ void epilogue_head_ch(const float* __restrict__ sw, uint32_t taddr, uint8_t* A, int row,
+                                                 float* hacc) {
+  constexpr int NC = N / 2, col0 = CH * NC;
+  float part[NH][4];
+#pragma unroll
+  for (int h = 0; h < NH; ++h)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) part[h][q] = 0.f;
+#pragma unroll 1
+  for (int c0 = 0; c0 < NC; c0 += 32) {
+    float v[32];
+    tmem_ld32(taddr + col0 + c0, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = ACT == 0 ? fmaxf(v[j], 0.f) : fmaxf(v[j], 0.2f * v[j]);
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 w = *reinterpret_cast<const float4*>(sw + h * N + col0 + c0 + 4 * q);
+        part[h][0] = fmaf(v[4 * q], w.x, part[h][0]);
+        part[h][1] = fmaf(v[4 * q + 1], w.y, part[h][1]);
+        part[h][2] = fmaf(v[4 * q + 2], w.z, part[h][2]);
+        part[h][3] = fmaf(v[4 * q + 3], w.w, part[h][3]);
+      }
+    if (WRITE_A) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) store_group<false>(A, (col0 + c0) / 8 + g, row, v + 8 * g);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < NH; ++h) hacc[h] += (part[h][0] + part[h][1]) + (part[h][2] + part[h][3]);
+}
+template <int N, int ACT, bool WRITE_A, int NH>
+__device__ __forceinline__ void epilogue_head(const float* sw, uint32_t taddr, uint8_t* A, int row, int ch, float* hacc) {
+  if (ch == 0) epilogue_head_ch<N, ACT, WRITE_A, NH, 0>(sw, taddr, A, row, hacc);
+  else epilogue_head_ch<N, ACT, WRITE_A, NH, 1>(sw, taddr, A, row, hacc);
 }
 
 // sample_square (util.py:277-282): bilinear, align_corners=False, border padding, over tex [h][w][c]
@@ -549,7 +597,15 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
     const int row = half * 128 + (warp & 3) * 32 + lane;
     const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)half * 256u;
     uint8_t* A = smem + offA;
-    float4* hx = reinterpret_cast<float4*>(smem + offHx);      // [2 column halves][256 rows]
+    float* hx = reinterpret_cast<float*>(smem + offHx);        // [2 column halves][256 rows][3]
+    float* hw = reinterpret_cast<float*>(smem + offHw);
+    const float* heads = net.heads;
+    // copy the next head layer's weight rows (n floats, a multiple of 4) into shared memory; called before wait_acc of
+    // that layer, whose barrier orders it against the readers; the previous head's readers are several barriers back
+    auto stage_head = [&](int off, int n) {
+      const int i = (warp * 32 + lane) * 4;
+      if (i < n) *reinterpret_cast<float4*>(hw + i) = __ldg(reinterpret_cast<const float4*>(heads + off + i));
+    };
     uint32_t par_acc = 0;
     int trace_l = 0;
     bool trace_on = false;
@@ -564,30 +620,28 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
       }
     };
     auto mark_done = [&]() { if (trace_on && trace_l < kNumLayers) { net.trace[trace_l * 4 + 3] = clock64(); ++trace_l; } };
-    // One warp watches the mbarrier, the other fifteen sleep on a hardware barrier: sixteen warps polling acc_ready
-    // through the whole MMA phase slowed the tensor pipe's own shared-memory traffic down.
+    // One warp watches the mbarrier, the other fifteen sleep on a hardware barrier (which also orders stage_head's
+    // shared-memory writes against the head epilogue's reads)
     auto wait_acc = [&]() {
-      if (net.dbg & 16) {
-        mbar_wait_backoff(&bars->acc_ready, par_acc);
-      } else {
-        if (warp == 0) mbar_wait(&bars->acc_ready, par_acc);
-        asm volatile("bar.sync 2, %0;" ::"n"(kWorkerThreads) : "memory");
-      }
+      if (warp == 0) mbar_wait(&bars->acc_ready, par_acc);
+      asm volatile("bar.sync 2, %0;" ::"n"(kWorkerThreads) : "memory");
       par_acc ^= 1u;
       tc_fence_after();
       if (trace_on && trace_l < kNumLayers) net.trace[trace_l * 4 + 2] = clock64();
     };
     // add the partial head sums of the row's other column half
     auto combine = [&](float* v, int n) {
-      hx[ch * kRows + row] = make_float4(v[0], n > 1 ? v[1] : 0.f, n > 2 ? v[2] : 0.f, 0.f);
+      float* mine = hx + (ch * kRows + row) * 3;
+      mine[0] = v[0];
+      if (n > 1) mine[1] = v[1];
+      if (n > 2) mine[2] = v[2];
       worker_bar();
-      const float4 o = hx[(ch ^ 1) * kRows + row];
-      v[0] += o.x;
-      if (n > 1) v[1] += o.y;
-      if (n > 2) v[2] += o.z;
+      const float* other = hx + ((ch ^ 1) * kRows + row) * 3;
+      v[0] += other[0];
+      if (n > 1) v[1] += other[1];
+      if (n > 2) v[2] += other[2];
       worker_bar();              // the buffer may be rewritten by the next head layer only after every read
     };
-    const float* heads = net.heads;
     {   // the constant-one columns must exist before the first bias slice is multiplied
       const float zero[3] = {0.f, 0.f, 0.f};
       write_encoding<3, 6, 6, false, false, true>(smem + offA2, row, ch, zero);
@@ -615,8 +669,9 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
         signal_a();
       }
       float raw = 0.f;
+      stage_head(kHeadGeo, 256);
       wait_acc();
-      epilogue<256, 0, 2, 1>(taddr, A, row, ch, heads + kHeadGeo, &raw);
+      epilogue_head<256, 0, false, 1>(hw, taddr, A, row, ch, &raw);
       mark_done();
       combine(&raw, 1);
       const float sigma = softplus_t(raw + __ldg(heads + kHeadGeoB));
@@ -634,8 +689,9 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
         signal_a();
       }
       float uvr[2] = {0.f, 0.f};
+      stage_head(kHeadGauge, 256);
       wait_acc();
-      epilogue<128, 0, 2, 2>(taddr, A, row, ch, heads + kHeadGauge, uvr);
+      epilogue_head<128, 0, false, 2>(hw, taddr, A, row, ch, uvr);
       mark_done();
       combine(uvr, 2);
       float uv[2] = {tanhf(uvr[0] + __ldg(heads + kHeadGaugeB)), tanhf(uvr[1] + __ldg(heads + kHeadGaugeB + 1))};
@@ -650,8 +706,9 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
         signal_a();
       }
       float c1[3] = {0.f, 0.f, 0.f};
+      stage_head(kHeadC1, 768);
       wait_acc();
-      epilogue<256, 1, 0, 3>(taddr, A, row, ch, heads + kHeadC1, c1);
+      epilogue_head<256, 1, true, 3>(hw, taddr, A, row, ch, c1);
       mark_done();
       signal_a();
       combine(c1, 3);
@@ -665,8 +722,9 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
         signal_a();
       }
       float c2[3] = {0.f, 0.f, 0.f};
+      stage_head(kHeadB2, 768);
       wait_acc();
-      epilogue<256, 1, 2, 3>(taddr, A, row, ch, heads + kHeadB2, c2);
+      epilogue_head<256, 1, false, 3>(hw, taddr, A, row, ch, c2);
       mark_done();
       combine(c2, 3);
       if (ch == 0 && id >= 0) {

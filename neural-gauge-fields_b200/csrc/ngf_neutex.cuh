@@ -27,6 +27,10 @@ constexpr int kTraceWords = 25 * 4 + 64;   // NGF_NTX_DBG=4: per-layer stamps + 
 constexpr int kTraceLayer = 5;
 constexpr int kNumLayers = 25;         // MMA layers per tile: geometry 11, gauge 4, texture block1 6, block2 4
 
+// geometry head [256] | gauge head [2][128] | color1 [3][256] | block2 head [3][256] | biases 1 + 2 + 3 + 3
+constexpr int kHeadGeo = 0, kHeadGauge = 256, kHeadC1 = 512, kHeadB2 = 1280, kHeadGeoB = 2048, kHeadGaugeB = 2049,
+              kHeadC1B = 2051, kHeadB2B = 2054, kHeadFloats = 2060;
+
 struct LayerDesc {
   int K;                // K of the main A operand (multiple of 16)
   int Kext;             // extra K taken from the view-direction operand (block2 layer 0: 48), else 0
@@ -48,7 +52,7 @@ struct NetDev {
   const uint8_t* wstream;
   uint32_t stream_bytes;  // bytes of one rank's stream
   int cg;                 // 1: one CTA per 256-sample tile (cta_group::1); 2: CTA pairs (cta_group::2) (NGF_NTX_CG)
-  const float* heads;     // fp32 head weights (16-byte aligned rows first, then the biases), offsets kHead* below
+  const float* heads;     // fp32 head weights (16-byte aligned rows first, then the biases), offsets kHead* above
   const float* texture;   // [h][w][c] edited texture or nullptr
   int tex_h, tex_w, tex_c;
   float jitter;
@@ -57,10 +61,6 @@ struct NetDev {
   long long* trace;       // dbg & 4: [25 layers][4] clock64 stamps of CTA 0's first tile (a_ready seen, MMAs issued,
                           //          acc_ready seen by worker 0, epilogue done by worker 0)
 };
-
-// geometry head [256] | gauge head [2][128] | color1 [3][256] | block2 head [3][256] | biases 1 + 2 + 3 + 3
-constexpr int kHeadGeo = 0, kHeadGauge = 256, kHeadC1 = 512, kHeadB2 = 1280, kHeadGeoB = 2048, kHeadGaugeB = 2049,
-              kHeadC1B = 2051, kHeadB2B = 2054, kHeadFloats = 2060;
 
 struct RenderArgsN {
   const float* campos;     // [3]
