@@ -82,3 +82,23 @@ def test_neutex_full_frame_properties():
     o_c, o_t = U.render(U.NeuTexSpec(state), campos, raydir[:, idx], bg, noise[:, idx])
     assert (color[:, idx] - o_c).abs().max() < TOL
     assert (out["transmittance"].cpu()[:, idx] - o_t).abs().max() < TOL
+
+
+def test_neutex_cta_pair_variant_matches_golden(monkeypatch):
+    """NGF_NTX_CG=2 (read when the network is packed): CTA pairs run every layer as cta_group::2 M=256 MMAs, each CTA
+    streaming half of the weights.  Same tolerance as the default one-CTA kernel, and the two agree closely."""
+    case = K.NEUTEX_BY_NAME["neutex_white"]
+    gold = load_golden("neutex_white")
+    state, tex, campos, raydir, bg, noise = K.build_neutex_inputs(case)
+    args = (campos.cuda(), raydir.cuda(), bg.cuda())
+    ref = _build(state, tex)(*args, noise=noise.cuda())["color"].cpu()
+    monkeypatch.setenv("NGF_NTX_CG", "2")
+    m = _build(state, tex)
+    out = m(*args, noise=noise.cuda())
+    torch.cuda.synchronize()
+    assert np.abs(out["color"].cpu().numpy() - gold["color"]).max() < TOL
+    assert np.abs(out["transmittance"].cpu().numpy() - gold["transmittance"]).max() < TOL
+    assert float((out["color"].cpu() - ref).abs().max()) < 2e-4       # same operands, different MMA shapes
+    for n in (1, 300):                                                 # one pair with an idle second CTA; two tiles
+        o = m(campos.cuda(), raydir[:, :n].cuda(), bg.cuda(), noise=noise[:, :n].cuda())
+        assert np.abs(o["color"].cpu().numpy() - gold["color"][:, :n]).max() < TOL
