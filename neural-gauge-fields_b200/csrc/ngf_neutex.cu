@@ -115,7 +115,8 @@ constexpr uint32_t offRing = offA2 + kA2Bytes;
 constexpr uint32_t offHx = offRing + kStages * kStageBytes;   // head partial sums exchanged between a row's two threads
 constexpr uint32_t kHxBytes = 2 * kRows * 12;                 //   [2 column halves][256 rows][3 floats]
 constexpr uint32_t offHw = offHx + kHxBytes;                  // fp32 weights of the head layer in flight (<= 3 x 256)
-constexpr uint32_t kHwBytes = 3 * 256 * 4;
+constexpr uint32_t kHwBytes = 3 * 256 * 4 + 16;                // + the head's bias (<= 3 floats) at float index kHwBias
+constexpr int kHwBias = 3 * 256;
 constexpr uint32_t offBar = offHw + kHwBytes;
 static_assert(offBar + 256 <= 227 * 1024, "shared memory budget");
 constexpr uint32_t kSmemBytes = offBar + 256;
@@ -602,9 +603,10 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
     const float* heads = net.heads;
     // copy the next head layer's weight rows (n floats, a multiple of 4) into shared memory; called before wait_acc of
     // that layer, whose barrier orders it against the readers; the previous head's readers are several barriers back
-    auto stage_head = [&](int off, int n) {
-      const int i = (warp * 32 + lane) * 4;
+    auto stage_head = [&](int off, int n, int bias_off, int n_bias) {
+      const int t = warp * 32 + lane, i = t * 4;
       if (i < n) *reinterpret_cast<float4*>(hw + i) = __ldg(reinterpret_cast<const float4*>(heads + off + i));
+      else if (t - 256 >= 0 && t - 256 < n_bias) hw[kHwBias + t - 256] = __ldg(heads + bias_off + t - 256);
     };
     uint32_t par_acc = 0;
     int trace_l = 0;
@@ -669,12 +671,12 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
         signal_a();
       }
       float raw = 0.f;
-      stage_head(kHeadGeo, 256);
+      stage_head(kHeadGeo, 256, kHeadGeoB, 1);
       wait_acc();
       epilogue_head<256, 0, false, 1>(hw, taddr, A, row, ch, &raw);
       mark_done();
       combine(&raw, 1);
-      const float sigma = softplus_t(raw + __ldg(heads + kHeadGeoB));
+      const float sigma = softplus_t(raw + hw[kHwBias]);
       // ---- gauge: [p, PE(p,10)] -> 64 -> 128 -> 128 -> 128 (ReLU) -> 2 -> tanh, split fp16   (gauge_fields.py:8-74)
       write_gauge_encoding(A, row, ch, p);
       signal_a();
@@ -689,12 +691,12 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
         signal_a();
       }
       float uvr[2] = {0.f, 0.f};
-      stage_head(kHeadGauge, 256);
+      stage_head(kHeadGauge, 256, kHeadGaugeB, 2);
       wait_acc();
       epilogue_head<128, 0, false, 2>(hw, taddr, A, row, ch, uvr);
       mark_done();
       combine(uvr, 2);
-      float uv[2] = {tanhf(uvr[0] + __ldg(heads + kHeadGaugeB)), tanhf(uvr[1] + __ldg(heads + kHeadGaugeB + 1))};
+      float uv[2] = {tanhf(uvr[0] + hw[kHwBias]), tanhf(uvr[1] + hw[kHwBias + 1])};
       // ---- texture block1: [uv, PE(uv,10)] -> 256 -> 5 x 256 (LeakyReLU 0.2); color1 256 -> 3 softplus   (decoder.py:56-78)
       write_encoding<2, 10, 6, false, false, false>(A, row, ch, uv);
       write_encoding<3, 6, 6, false, false, true>(smem + offA2, row, ch, dir);
@@ -706,14 +708,14 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
         signal_a();
       }
       float c1[3] = {0.f, 0.f, 0.f};
-      stage_head(kHeadC1, 768);
+      stage_head(kHeadC1, 768, kHeadC1B, 3);
       wait_acc();
       epilogue_head<256, 1, true, 3>(hw, taddr, A, row, ch, c1);
       mark_done();
       signal_a();
       combine(c1, 3);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) c1[k] = softplus_t(c1[k] + __ldg(heads + kHeadC1B + k));
+      for (int k = 0; k < 3; ++k) c1[k] = softplus_t(c1[k] + hw[kHwBias + k]);
       // ---- texture block2: [h, d, PE(d,6)] -> 256 -> 3 x 256 (LeakyReLU) -> 3
       for (int r = 0; r < 3; ++r) {
         wait_acc();
@@ -722,7 +724,7 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
         signal_a();
       }
       float c2[3] = {0.f, 0.f, 0.f};
-      stage_head(kHeadB2, 768);
+      stage_head(kHeadB2, 768, kHeadB2B, 3);
       wait_acc();
       epilogue_head<256, 1, false, 3>(hw, taddr, A, row, ch, c2);
       mark_done();
@@ -730,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
       if (ch == 0 && id >= 0) {
         float rgb[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) rgb[k] = c1[k] + c2[k] + __ldg(heads + kHeadB2B + k);
+        for (int k = 0; k < 3; ++k) rgb[k] = c1[k] + c2[k] + hw[kHwBias + k];
         if (net.texture == nullptr) {
 #pragma unroll
           for (int k = 0; k < 3; ++k) rgb[k] = fmaxf(rgb[k], 0.f);                     // (c1 + c2).clamp(min=0)
