@@ -431,7 +431,7 @@ __device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint3
     if (tid == 0) {
       tc_fence_after();
       const uint32_t a0 = smem_u32(smem + L::offA), b0 = smem_u32(smem + L::offW1);
-#pragma unroll 1
+#pragma unroll
       for (int j = 0; j < NKC / 2; ++j)
         umma_f16(tmem, umma_desc(a0 + j * 2 * lboA, lboA, sboA), umma_desc(b0 + j * 2 * kMid * 16, lboB, sboB),
                  idesc, j > 0);
@@ -489,7 +489,7 @@ __device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint3
     if (tid == 0) {
       tc_fence_after();
       const uint32_t a0 = smem_u32(H), b0 = smem_u32(smem + L::offW2);
-#pragma unroll 1
+#pragma unroll
       for (int j = 0; j < kMid / 16; ++j)
         umma_f16(tmem + 64, umma_desc(a0 + j * 2 * kTileM * 16, lboA, sboA),
                  umma_desc(b0 + j * 2 * kMid * 16, lboB, sboB), idesc, j > 0);
