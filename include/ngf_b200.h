@@ -308,6 +308,10 @@ int ngf_neutex_copy_samples(NgfNeutex h, int64_t first_sample, int64_t n, float*
 int ngf_neutex_timing_begin(NgfNeutex h, int32_t capacity);
 int ngf_neutex_timing_read(NgfNeutex h, int32_t* n_renders, double* raygen_ms, double* mlp_ms, double* march_ms);
 
+/* Environment read by ngf_neutex_pack: NGF_NTX_CG=2 packs per-CTA-rank weight streams and renders with CTA pairs
+ * (cta_group::2 MMAs, M = 256) instead of one CTA per 256-sample tile (default 1; same results within fp32 rounding of the
+ * accumulation order); NGF_NTX_DBG is a profiling switch (2: skip the MMAs, 4: record a timeline, 8: skip the weight copies
+ * — results are then meaningless). */
 /* Profiling aid (library built as is, NGF_NTX_DBG=4 in the environment when packing): per-layer clock64 stamps of CTA 0's
  * first tile — [25][4] = MMA warp saw a_ready | MMA warp issued the layer | worker 0 saw acc_ready | worker 0 finished the
  * epilogue — followed by 64 stamps of the weight ring during layer 5 ([2i], [2i+1] = MMA warp saw stage i full | issued its

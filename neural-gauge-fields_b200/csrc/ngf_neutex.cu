@@ -4,13 +4,17 @@
 //                       segment lengths, end points by a double-precision running sum (torch's CPU cumsum accumulates
 //                       in double), mid points, p = campos + raydir * mid, strict in-cube test.  In-cube samples are
 //                       compacted (warp prefix sum, one atomic per warp) into a work list.
-//   ntx_mlp_kernel      persistent CTAs (one per SM), 256-sample tiles.  Every K=16 weight slice streamed from L2 by a
-//                       producer warp (cp.async.bulk -> mbarrier ring) feeds two M=128 tcgen05.mma tiles whose
-//                       accumulators fill the SM's TMEM (2 x 256 fp32 columns); 256 worker threads own one sample
-//                       row each: they build the sinusoidal encodings, run the epilogues TMEM -> bias/activation ->
-//                       fp16 -> shared-memory A operand of the next layer, and evaluate the narrow heads
-//                       (density, uv, colour) in fp32.  The gauge network runs split-fp16 (hi + lo, 3 MMAs per slice)
-//                       because its output is multiplied by 2^9 inside PE(uv, 10).
+//   ntx_mlp_kernel      persistent CTAs (one per SM), 256-sample tiles.  The 25-layer weight stream is copied ring stage
+//                       after ring stage (cp.async.bulk -> mbarrier ring) by a producer warp; every K=16 slice feeds two
+//                       M=128 tcgen05.mma tiles whose accumulators fill the SM's TMEM (2 x 256 fp32 columns); 512
+//                       worker threads (two per sample row, half of a layer's columns each) build the sinusoidal
+//                       encodings, run the epilogues TMEM -> activation -> fp16 -> shared-memory A operand of the next
+//                       layer, and evaluate the narrow heads (density, uv, colour) in fp32 from weights staged in
+//                       shared memory.  Biases ride on the MMA (a constant-one column times a bias slice).  The gauge
+//                       network runs split-fp16 (hi + lo, 3 MMAs per slice) because its output is multiplied by 2^9
+//                       inside PE(uv, 10).  The MMA-issue loop is written for the tensor pipe's short queue: whole ring
+//                       stages as straight-line code, the wait for the next stage under the last slice's MMAs
+//                       (DESIGN.md 4.3).  NGF_NTX_CG=2 (when packing) runs CTA pairs with cta_group::2 MMAs instead.
 //   ntx_march_kernel    ray_march + alpha_blend + background + simple_tone_map (model/renderer.py:4-11,176-247;
 //                       model/model.py:46-50), one ray per thread, transmittance as a double running product.
 #include "ngf_neutex.cuh"
@@ -333,11 +337,11 @@ template <int N, int ACT, bool WRITE_A, int NH, int CH>
 __device__ __forceinline__ void epilogue_head_ch(const float* __restrict__ sw, uint32_t taddr, uint8_t* A, int row,
                                                  float* hacc) {
   constexpr int NC = N / 2, col0 = CH * NC;
-  float part[NH][4];
+  float2 part[NH][2];        // packed fp32 FMAs (two exact fp32 FMAs per instruction on sm_100)
 #pragma unroll
   for (int h = 0; h < NH; ++h)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) part[h][q] = 0.f;
+    for (int q = 0; q < 2; ++q) part[h][q] = make_float2(0.f, 0.f);
 #pragma unroll 1
   for (int c0 = 0; c0 < NC; c0 += 32) {
     float v[32];
@@ -349,10 +353,8 @@ __device__ __forceinline__ void epilogue_head_ch(const float* __restrict__ sw, u
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 w = *reinterpret_cast<const float4*>(sw + h * N + col0 + c0 + 4 * q);
-        part[h][0] = fmaf(v[4 * q], w.x, part[h][0]);
-        part[h][1] = fmaf(v[4 * q + 1], w.y, part[h][1]);
-        part[h][2] = fmaf(v[4 * q + 2], w.z, part[h][2]);
-        part[h][3] = fmaf(v[4 * q + 3], w.w, part[h][3]);
+        part[h][0] = __ffma2_rn(make_float2(v[4 * q], v[4 * q + 1]), make_float2(w.x, w.y), part[h][0]);
+        part[h][1] = __ffma2_rn(make_float2(v[4 * q + 2], v[4 * q + 3]), make_float2(w.z, w.w), part[h][1]);
       }
     if (WRITE_A) {
 #pragma unroll
@@ -360,7 +362,7 @@ __device__ __forceinline__ void epilogue_head_ch(const float* __restrict__ sw, u
     }
   }
 #pragma unroll
-  for (int h = 0; h < NH; ++h) hacc[h] += (part[h][0] + part[h][1]) + (part[h][2] + part[h][3]);
+  for (int h = 0; h < NH; ++h) hacc[h] += (part[h][0].x + part[h][0].y) + (part[h][1].x + part[h][1].y);
 }
 template <int N, int ACT, bool WRITE_A, int NH>
 __device__ __forceinline__ void epilogue_head(const float* sw, uint32_t taddr, uint8_t* A, int row, int ch, float* hacc) {
@@ -495,7 +497,7 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
         if (elect_one()) {
           if (tr) net.trace[l * 4 + 0] = clock64();
           // ring state of the layer's first slice
-          const uint32_t g0 = ui * nst + (L.off >> 14);          // kStageBytes == 1 << 14
+          const uint32_t g0 = ui * nst + L.off / kStageBytes;
           uint32_t s = g0 % kStages, par = (g0 / kStages) & 1u;
           uint32_t rem = kStageBytes - (L.off & (kStageBytes - 1u));      // bytes of the stage still unread
           auto wait_stage = [&](uint32_t st, uint32_t ph) {
@@ -514,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
             uint32_t a_lo = ((abase & 0x3FFFFu) >> 4) | kALo;
             // fast path: whole ring stages of a 256-wide layer as straight-line code (2 * CG slices, 4 * CG MMAs),
             // so that the descriptors stay in uniform registers from one MMA to the next
-            constexpr int SPS = 2 * CG;
+            constexpr int SPS = (int)(kStageBytes / (kSliceBytes / CG));
             const bool fast = !lo_terms && slice == kSliceBytes / CG && !skip;
 #pragma unroll 1
             for (; n > 0; --n, --left) {

@@ -20,9 +20,16 @@ constexpr int kRows = 256;             // work items per MLP tile: two M=128 tcg
 constexpr int kWorkerThreads = 512;    // two threads per tile row (TMEM lane): each owns half of the layer's columns
 constexpr int kWorkerWarps = kWorkerThreads / 32;
 constexpr int kThreads = kWorkerThreads + 64;   // + 1 MMA-issue warp + 1 weight-producer warp
-constexpr int kStages = 4;             // weight ring
+#ifndef NTX_STAGES           // experiment knobs (scripts/gpu_stage_variants.sh); the defaults are what ships
+#define NTX_STAGES 4
+#endif
+#ifndef NTX_STAGE_BYTES
+#define NTX_STAGE_BYTES 16384
+#endif
+constexpr int kStages = NTX_STAGES;    // weight ring
 constexpr uint32_t kSliceBytes = 8192; // largest K=16 slice: a 256-wide layer (or hi+lo of a 128-wide one) at cg = 1
-constexpr uint32_t kStageBytes = 16384; // one cp.async.bulk per stage: two 8 KiB slices (cg = 1), four 4 KiB (cg = 2)
+constexpr uint32_t kStageBytes = NTX_STAGE_BYTES; // one cp.async.bulk per stage: two 8 KiB slices (cg = 1), four 4 KiB (cg = 2)
+static_assert((kStageBytes & (kStageBytes - 1)) == 0 && kStageBytes >= kSliceBytes, "ring stage size");
 constexpr int kTraceWords = 25 * 4 + 64;   // NGF_NTX_DBG=4: per-layer stamps + ring stamps of layer kTraceLayer
 constexpr int kTraceLayer = 5;
 constexpr int kNumLayers = 25;         // MMA layers per tile: geometry 11, gauge 4, texture block1 6, block2 4
