@@ -8,6 +8,28 @@
 
 namespace ngf {
 
+// Function attributes (dynamic shared-memory limit, carve-out) belong to the function ON ONE DEVICE: a process that
+// renders on several devices has to set them on each.  PerDevice<T> keeps one lazily filled slot per device ordinal.
+template <class T>
+struct PerDevice {
+  T slot[64] = {};
+  bool done[64] = {};
+  // returns the slot of the current device and whether it still has to be initialised
+  T* get(bool* fresh) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    *fresh = !done[dev];
+    done[dev] = true;
+    return &slot[dev];
+  }
+  void retry() {               // initialisation failed: try again on the next call
+    int dev = 0;
+    cudaGetDevice(&dev);
+    done[dev & 63] = false;
+  }
+};
+
 struct RenderArgs {
   CamDev cam;                  // cam_on: rays are generated from this camera (pixel = ray index), `rays` is unused
   int cam_on;

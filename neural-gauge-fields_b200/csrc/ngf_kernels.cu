@@ -253,10 +253,12 @@ template <int V>
 static cudaError_t launch_march_t(const FieldDev& f, const RenderArgs& a, int num_sms, cudaStream_t st) {
   auto kern = ngf_march_kernel<V>;
   const size_t smem = MarchSmem<V>::kBytes;
-  static int occ = 0;
-  if (occ == 0) {
+  static PerDevice<int> occ_of;
+  bool fresh = false;
+  int& occ = *occ_of.get(&fresh);
+  if (fresh || occ == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    if (e != cudaSuccess) { occ_of.retry(); return e; }
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     occ = blocks_per_sm(reinterpret_cast<const void*>(kern), kMarchThreads, smem);
   }
@@ -273,10 +275,12 @@ template <int V, int IMPL>
 static cudaError_t launch_colour_t(const FieldDev& f, const RenderArgs& a, int num_sms, cudaStream_t st) {
   auto kern = ngf_colour_kernel<V, IMPL>;
   const size_t smem = MlpSmem<V>::offEnd;
-  static int occ = 0;
-  if (occ == 0) {
+  static PerDevice<int> occ_of;
+  bool fresh = false;
+  int& occ = *occ_of.get(&fresh);
+  if (fresh || occ == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    if (e != cudaSuccess) { occ_of.retry(); return e; }
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     occ = blocks_per_sm(reinterpret_cast<const void*>(kern), kThreads, smem);
     if (occ > 2) occ = 2;
@@ -415,11 +419,12 @@ static cudaError_t launch_rgb_t(const FieldDev& f, const float* xy, const float*
                                 const float* dirs, long long n, float* rgb, int num_sms, cudaStream_t st) {
   auto kern = ngf_rgb_kernel<V, IMPL>;
   const size_t smem = MlpSmem<V>::offEnd;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<int> configured;
+  bool fresh = false;
+  configured.get(&fresh);
+  if (fresh) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
+    if (e != cudaSuccess) { configured.retry(); return e; }
   }
   long long n_tiles = (n + kTileM - 1) / kTileM;
   long long grid = (long long)num_sms * 2;

@@ -21,6 +21,7 @@
 
 #include <atomic>
 
+#include "ngf_internal.h"
 #include "ngf_mlp.cuh"
 
 namespace ngf {
@@ -889,13 +890,14 @@ cudaError_t launch_neutex_raygen(const NetDev& net, const RenderArgsN& a, cudaSt
 }
 
 cudaError_t launch_neutex_mlp(const NetDev& net, const RenderArgsN& a, int num_sms, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<int> configured;
+  bool fresh = false;
+  configured.get(&fresh);
+  if (fresh) {
     cudaError_t e = cudaFuncSetAttribute(ntx_mlp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(ntx_mlp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
+    if (e != cudaSuccess) { configured.retry(); return e; }
   }
   if (net.cg == 2) {
     // one CTA pair (a cluster of two, i.e. the two SMs of a TPC) per 512 work items
