@@ -156,6 +156,16 @@ int ngf_field_render(NgfField f, const float* rays_dev, int64_t n_rays, int32_t 
                      int32_t mlp_impl, void* stream);
 
 /*
+ * Same with the training-time sampling of Base.sample_ray(is_train=True) (FieldBase.py:128-132): sample i of ray r sits
+ * at t_min + stepSize * (i + jitter[r]), jitter_dev [R] fp32 in [0, 1) (the reference draws it with torch.rand_like on
+ * the host; the caller does the same and passes it in, so both implementations see the same numbers).  Forward only:
+ * there is no backward pass in this library.  jitter 0 everywhere gives ngf_field_render bit for bit.
+ */
+int ngf_field_render_jitter(NgfField f, const float* rays_dev, int64_t n_rays, int32_t ray_stride, int32_t n_samples,
+                            int32_t white_bg, int32_t tile_w, const float* jitter_dev, float* rgb_dev, float* depth_dev,
+                            float* acc_dev, int32_t mlp_impl, void* stream);
+
+/*
  * Same through HOST buffers: H2D of the rays, render, D2H of rgb/depth, chunked and overlapped on internal
  * streams; returns after the results are in rgb_host/depth_host.  This is the call the reference-facing
  * `renderer(rays_cpu, field, ...)` maps to when rays live on the CPU (main.py:64-65 does the H2D per chunk).
@@ -225,6 +235,9 @@ int ngf_field_timing_read(NgfField f, int32_t* n_launches, double* march_ms, dou
  */
 int ngf_field_sample_ray(NgfField f, const float* rays_dev, int64_t n_rays, int32_t ray_stride, int32_t n_samples,
                          float* pts_dev, float* t_dev, uint8_t* inside_dev, void* stream);
+/* Base.sample_ray, is_train=True branch: as above with t_i = t_min + stepSize * (i + jitter[r]), jitter_dev [R]. */
+int ngf_field_sample_ray_jitter(NgfField f, const float* rays_dev, int64_t n_rays, int32_t ray_stride, int32_t n_samples,
+                                const float* jitter_dev, float* pts_dev, float* t_dev, uint8_t* inside_dev, void* stream);
 int ngf_field_alpha_keep(NgfField f, const float* pts_dev, int64_t n, uint8_t* keep_dev, void* stream);
 int ngf_field_gauge(NgfField f, const float* xyz_norm_dev, int64_t n, int32_t gauge_on, float* xy_dev,
                     float* yz_dev, float* xz_dev, void* stream);

@@ -508,7 +508,8 @@ static int ensure_queue(QEntry** q, long long* cap, long long want, cudaStream_t
 
 static int render_dev(NgfField h, const float* rays, long long n_rays, int ray_stride, int n_samples, int white_bg,
                       int tile_w, float* rgb, float* depth, float* acc, unsigned int* counters, QEntry** queue,
-                      long long* queue_cap, int mlp_impl, cudaStream_t st, const CamDev* cam = nullptr) {
+                      long long* queue_cap, int mlp_impl, cudaStream_t st, const CamDev* cam = nullptr,
+                      const float* jitter = nullptr) {
   if (n_rays == 0) return NGF_OK;
   const int S = n_samples > 0 ? n_samples : h->n_samples_default;
   if (S < 1) return fail(NGF_EINVAL, "n_samples resolves to %d", S);
@@ -527,6 +528,7 @@ static int render_dev(NgfField h, const float* rays, long long n_rays, int ray_s
     const long long n = (n_rays - s0) < per ? (n_rays - s0) : per;
     RenderArgs a{};
     a.rays = rays ? rays + s0 * ray_stride : nullptr; a.n_rays = n; a.ray_stride = ray_stride;
+    a.jitter = jitter ? jitter + s0 : nullptr;
     a.cam_on = cam ? 1 : 0;
     if (cam) { a.cam = *cam; a.cam.base = cam->base + s0; }
     a.S = S;
@@ -559,9 +561,9 @@ static int render_dev(NgfField h, const float* rays, long long n_rays, int ray_s
   return NGF_OK;
 }
 
-int ngf_field_render(NgfField h, const float* rays_dev, int64_t n_rays, int32_t ray_stride, int32_t n_samples,
-                     int32_t white_bg, int32_t tile_w, float* rgb_dev, float* depth_dev, float* acc_dev,
-                     int32_t mlp_impl, void* stream) {
+static int field_render(NgfField h, const float* rays_dev, int64_t n_rays, int32_t ray_stride, int32_t n_samples,
+                        int32_t white_bg, int32_t tile_w, const float* jitter_dev, float* rgb_dev, float* depth_dev,
+                        float* acc_dev, int32_t mlp_impl, void* stream) {
   if (!h) return fail(NGF_EINVAL, "field is NULL");
   if (n_rays < 0 || n_rays > 0x7fffffffll) return fail(NGF_EINVAL, "n_rays=%lld", (long long)n_rays);
   if (n_rays == 0) return NGF_OK;
@@ -583,7 +585,22 @@ int ngf_field_render(NgfField h, const float* rays_dev, int64_t n_rays, int32_t 
     acc = h->acc_ws;
   }
   return render_dev(h, rays_dev, n_rays, ray_stride, n_samples, white_bg, tile_w, rgb_dev, depth_dev, acc,
-                    h->counters, &h->queue, &h->queue_cap, mlp_impl, st);
+                    h->counters, &h->queue, &h->queue_cap, mlp_impl, st, nullptr, jitter_dev);
+}
+
+int ngf_field_render(NgfField h, const float* rays_dev, int64_t n_rays, int32_t ray_stride, int32_t n_samples,
+                     int32_t white_bg, int32_t tile_w, float* rgb_dev, float* depth_dev, float* acc_dev,
+                     int32_t mlp_impl, void* stream) {
+  return field_render(h, rays_dev, n_rays, ray_stride, n_samples, white_bg, tile_w, nullptr, rgb_dev, depth_dev, acc_dev,
+                      mlp_impl, stream);
+}
+
+int ngf_field_render_jitter(NgfField h, const float* rays_dev, int64_t n_rays, int32_t ray_stride, int32_t n_samples,
+                            int32_t white_bg, int32_t tile_w, const float* jitter_dev, float* rgb_dev, float* depth_dev,
+                            float* acc_dev, int32_t mlp_impl, void* stream) {
+  if (!jitter_dev && n_rays > 0) return fail(NGF_EINVAL, "jitter is NULL");
+  return field_render(h, rays_dev, n_rays, ray_stride, n_samples, white_bg, tile_w, jitter_dev, rgb_dev, depth_dev,
+                      acc_dev, mlp_impl, stream);
 }
 
 // Enqueue one whole frame as a three-stage pipeline over chunks: uploads back to back on s_in, kernels on kHostComp
@@ -910,7 +927,17 @@ int ngf_field_sample_ray(NgfField h, const float* rays_dev, int64_t n, int32_t r
   if (!rays_dev || !pts_dev || !t_dev || !inside_dev) return fail(NGF_EINVAL, "NULL pointer");
   if (ray_stride < 6) return fail(NGF_EINVAL, "ray_stride=%d (< 6)", ray_stride);
   const int S = n_samples > 0 ? n_samples : h->n_samples_default;
-  CU(launch_sample_ray(h->dev, rays_dev, n, ray_stride, S, pts_dev, t_dev, inside_dev, st));
+  CU(launch_sample_ray(h->dev, rays_dev, n, ray_stride, S, nullptr, pts_dev, t_dev, inside_dev, st));
+  return NGF_OK;
+}
+
+int ngf_field_sample_ray_jitter(NgfField h, const float* rays_dev, int64_t n, int32_t ray_stride, int32_t n_samples,
+                                const float* jitter_dev, float* pts_dev, float* t_dev, uint8_t* inside_dev, void* stream) {
+  NGF_POINTWISE_PROLOGUE();
+  if (!rays_dev || !jitter_dev || !pts_dev || !t_dev || !inside_dev) return fail(NGF_EINVAL, "NULL pointer");
+  if (ray_stride < 6) return fail(NGF_EINVAL, "ray_stride=%d (< 6)", ray_stride);
+  const int S = n_samples > 0 ? n_samples : h->n_samples_default;
+  CU(launch_sample_ray(h->dev, rays_dev, n, ray_stride, S, jitter_dev, pts_dev, t_dev, inside_dev, st));
   return NGF_OK;
 }
 

@@ -113,7 +113,7 @@ __device__ __forceinline__ float ray_t0(const FieldDev& f, const float o[3], con
 // by the rounding error of p = o + d*t mapped back to t (huge for near-zero direction components, which then
 // leave the axis unconstrained) plus two whole steps.
 __device__ __forceinline__ void ray_index_range(const FieldDev& f, const float o[3], const float d[3], float t0,
-                                                int S, int& i_lo, int& i_hi) {
+                                                int S, int& i_lo, int& i_hi, float extra = 0.f) {
   float t_in = -INFINITY, t_out = INFINITY;
   bool empty = false;
 #pragma unroll
@@ -133,8 +133,8 @@ __device__ __forceinline__ void ray_index_range(const FieldDev& f, const float o
     t_out = fminf(t_out, fmaxf(a, b) + m);
   }
   if (empty || t_out < t_in) { i_lo = 0; i_hi = -1; return; }
-  float a = floorf((t_in - t0) / f.step) - 2.f;
-  float b = ceilf((t_out - t0) / f.step) + 2.f;
+  float a = floorf((t_in - t0) / f.step) - 2.f - extra;     // extra: a jittered sample i sits at t0 + step * (i + u)
+  float b = ceilf((t_out - t0) / f.step) + 2.f + extra;
   a = fminf(fmaxf(a, 0.f), (float)S);
   b = fminf(fmaxf(b, -1.f), (float)(S - 1));
   i_lo = (int)a;
@@ -144,6 +144,10 @@ __device__ __forceinline__ void ray_index_range(const FieldDev& f, const float o
 // t_i = t0 + stepSize * i  (FieldBase.py:131-132: mul, then add)
 __device__ __forceinline__ float sample_t(const FieldDev& f, float t0, int i) {
   return __fadd_rn(t0, __fmul_rn(f.step, (float)i));
+}
+// training-time sampling (FieldBase.py:128-132): rng = i + u with one u ~ U[0,1) per ray, step = stepSize * rng
+__device__ __forceinline__ float sample_t(const FieldDev& f, float t0, int i, float u) {
+  return __fadd_rn(t0, __fmul_rn(f.step, __fadd_rn((float)i, u)));
 }
 
 // p = o + d * t (FieldBase.py:134) and the bbox test (FieldBase.py:135)

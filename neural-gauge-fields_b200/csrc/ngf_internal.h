@@ -34,6 +34,7 @@ struct RenderArgs {
   CamDev cam;                  // cam_on: rays are generated from this camera (pixel = ray index), `rays` is unused
   int cam_on;
   const float* rays;
+  const float* jitter;         // [R] or nullptr: per-ray u of the training-time sampling (FieldBase.py:128-130)
   long long n_rays;
   int ray_stride;
   int S;
@@ -54,8 +55,8 @@ struct RenderArgs {
 cudaError_t launch_march(const FieldDev& f, const RenderArgs& a, int num_sms, cudaStream_t st);
 cudaError_t launch_colour(const FieldDev& f, const RenderArgs& a, int mlp_impl, int num_sms, cudaStream_t st);
 cudaError_t launch_finalize(float* rgb, const float* acc, long long n_rays, int white_bg, cudaStream_t st);
-cudaError_t launch_sample_ray(const FieldDev& f, const float* rays, long long n_rays, int stride, int S, float* pts,
-                              float* t, uint8_t* inside, cudaStream_t st);
+cudaError_t launch_sample_ray(const FieldDev& f, const float* rays, long long n_rays, int stride, int S,
+                              const float* jitter, float* pts, float* t, uint8_t* inside, cudaStream_t st);
 cudaError_t launch_alpha_keep(const FieldDev& f, const float* pts, long long n, uint8_t* keep, cudaStream_t st);
 cudaError_t launch_gauge(const FieldDev& f, const float* xyz, long long n, int gauge_on, float* xy, float* yz,
                          float* xz, cudaStream_t st);

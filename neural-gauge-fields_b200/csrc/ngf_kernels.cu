@@ -40,7 +40,9 @@ struct MarchSmem {
   static constexpr uint32_t kBytes = offDmlp + (V == 1 ? ((kDmlpFloats * 4 + 15) / 16) * 16 : 0);
 };
 
-template <int V>
+// JIT: training-time sampling, every sample of ray r shifted by u_r steps (a.jitter); the JIT = false instantiation is
+// the evaluation kernel, unchanged.
+template <int V, bool JIT = false>
 __global__ void __launch_bounds__(kMarchThreads, V == 0 ? 3 : 2) ngf_march_kernel(const __grid_constant__ FieldDev f,
                                                                 const __grid_constant__ RenderArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(kMarchThreads, V == 0 ? 3 : 2) ngf_march_kerne
 
   // per-lane ray state
   float o[3] = {0, 0, 0}, d[3] = {0, 0, 1}, t0 = 0.f, T = 1.f, acc = 0.f, dep = 0.f, last_col = 0.f;
+  float jit = 0.f;
   int i = 0, i_end = 0;
   long long ray = -1;
   bool live = false;
@@ -102,8 +105,9 @@ __global__ void __launch_bounds__(kMarchThreads, V == 0 ? 3 : 2) ngf_march_kerne
           last_col = __ldg(rp + a.ray_stride - 1);
         }
         t0 = ray_t0(f, o, d);
+        if (JIT) jit = __ldg(a.jitter + ray);
         int lo_i, hi_i;
-        ray_index_range(f, o, d, t0, S, lo_i, hi_i);
+        ray_index_range(f, o, d, t0, S, lo_i, hi_i, JIT ? 1.f : 0.f);
         i = lo_i; i_end = hi_i + 1;
         T = 1.f; acc = 0.f; dep = 0.f;
         live = i < i_end;
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(kMarchThreads, V == 0 ? 3 : 2) ngf_march_kerne
     bool found = false;
     float t = 0.f, p[3] = {0, 0, 0};
     while (live && !found) {
-      t = sample_t(f, t0, i);
+      t = JIT ? sample_t(f, t0, i, jit) : sample_t(f, t0, i);
       bool in = sample_pos(f, o, d, t, p);
       if (in) ++st_box;
       if (in && f.has_occ) in = occ_keep(f, p);
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(kMarchThreads, V == 0 ? 3 : 2) ngf_march_kerne
       const float sigma = (V == 0) ? sigma_triplane(f, c) : sigma_infoinv(f, c, dmlp_s);
       ++st_den;
       // raw2alpha (FieldBase.py:12-19) with dists from the rounded t values (FieldBase.py:258, 288)
-      const float tn = sample_t(f, t0, i + 1);
+      const float tn = JIT ? sample_t(f, t0, i + 1, jit) : sample_t(f, t0, i + 1);
       const float delta = (i == S - 1) ? 0.f : __fmul_rn(__fsub_rn(tn, t), f.dscale);
       const float alpha = __fsub_rn(1.f, expf(-__fmul_rn(sigma, delta)));
       w = __fmul_rn(alpha, T);
@@ -249,9 +253,9 @@ static int blocks_per_sm(const void* kern, int threads, size_t dyn_smem) {
   return occ < 1 ? 1 : occ;
 }
 
-template <int V>
+template <int V, bool JIT>
 static cudaError_t launch_march_t(const FieldDev& f, const RenderArgs& a, int num_sms, cudaStream_t st) {
-  auto kern = ngf_march_kernel<V>;
+  auto kern = ngf_march_kernel<V, JIT>;
   const size_t smem = MarchSmem<V>::kBytes;
   static PerDevice<int> occ_of;
   bool fresh = false;
@@ -295,7 +299,8 @@ static cudaError_t launch_colour_t(const FieldDev& f, const RenderArgs& a, int n
 }
 
 cudaError_t launch_march(const FieldDev& f, const RenderArgs& a, int num_sms, cudaStream_t st) {
-  return f.variant == 0 ? launch_march_t<0>(f, a, num_sms, st) : launch_march_t<1>(f, a, num_sms, st);
+  if (a.jitter) return f.variant == 0 ? launch_march_t<0, true>(f, a, num_sms, st) : launch_march_t<1, true>(f, a, num_sms, st);
+  return f.variant == 0 ? launch_march_t<0, false>(f, a, num_sms, st) : launch_march_t<1, false>(f, a, num_sms, st);
 }
 
 cudaError_t launch_colour(const FieldDev& f, const RenderArgs& a, int mlp_impl, int num_sms, cudaStream_t st) {
@@ -317,8 +322,8 @@ cudaError_t launch_finalize(float* rgb, const float* acc, long long n_rays, int 
 
 // Base.sample_ray, eval branch (FieldBase.py:118-137)
 __global__ void ngf_sample_ray_kernel(const __grid_constant__ FieldDev f, const float* __restrict__ rays,
-                                      long long n_rays, int stride, int S, float* __restrict__ pts,
-                                      float* __restrict__ tout, uint8_t* __restrict__ inside) {
+                                      long long n_rays, int stride, int S, const float* __restrict__ jitter,
+                                      float* __restrict__ pts, float* __restrict__ tout, uint8_t* __restrict__ inside) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_rays * S) return;
   long long r = idx / S;
@@ -326,7 +331,7 @@ __global__ void ngf_sample_ray_kernel(const __grid_constant__ FieldDev f, const 
   const float* rp = rays + r * stride;
   float o[3] = {rp[0], rp[1], rp[2]}, d[3] = {rp[3], rp[4], rp[5]};
   float t0 = ray_t0(f, o, d);
-  float t = sample_t(f, t0, i), p[3];
+  float t = jitter ? sample_t(f, t0, i, jitter[r]) : sample_t(f, t0, i), p[3];
   bool in = sample_pos(f, o, d, t, p);
   pts[idx * 3 + 0] = p[0]; pts[idx * 3 + 1] = p[1]; pts[idx * 3 + 2] = p[2];
   tout[idx] = t;
@@ -446,11 +451,11 @@ cudaError_t launch_rgb(const FieldDev& f, const float* xy, const float* yz, cons
 
 static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
-cudaError_t launch_sample_ray(const FieldDev& f, const float* rays, long long n_rays, int stride, int S, float* pts,
-                              float* t, uint8_t* inside, cudaStream_t st) {
+cudaError_t launch_sample_ray(const FieldDev& f, const float* rays, long long n_rays, int stride, int S,
+                              const float* jitter, float* pts, float* t, uint8_t* inside, cudaStream_t st) {
   long long n = n_rays * S;
   if (n <= 0) return cudaSuccess;
-  ngf_sample_ray_kernel<<<blocks_for(n, 256), 256, 0, st>>>(f, rays, n_rays, stride, S, pts, t, inside);
+  ngf_sample_ray_kernel<<<blocks_for(n, 256), 256, 0, st>>>(f, rays, n_rays, stride, S, jitter, pts, t, inside);
   NGF_COUNT_LAUNCH();
   return cudaGetLastError();
 }

@@ -4,8 +4,9 @@ render path executed by ``libngf_b200.so`` (hand-written sm_100a CUDA) through t
 ``include/ngf_b200.h``.
 
 There is deliberately no CPU implementation here: a field living on the CPU, a missing shared library or a
-non-Blackwell GPU raises.  Training-time forward (``is_train=True``: jittered sampling + autograd,
-FieldBase.py:128-130) is outside the current scope and raises ``NotImplementedError``.
+non-Blackwell GPU raises.  ``is_train=True`` runs the reference's jittered sampling (FieldBase.py:128-130) as a
+forward-only render; there is no backward pass, so calling it with autograd enabled on a field
+whose parameters require gradients raises ``NotImplementedError`` instead of silently returning detached tensors.
 """
 from __future__ import annotations
 
@@ -253,14 +254,21 @@ class Base(torch.nn.Module):
     def _set_switches(self, lib, h, **fwd_kw):
         pass
 
-    @torch.no_grad()
     def forward(self, rays_chunk, white_bg=True, is_train=False, N_samples=-1, image_width=0, **fwd_kw):
         """Reference: Base.forward (FieldBase.py:251-312).  Returns {'rgb_map': [R,3], 'depth_map': [R]} on the
         field's device.  ``image_width`` (optional, not in the reference) tells the kernel that the rays are the
-        row-major pixels of an image so warps can take 8x4 pixel blocks."""
-        if is_train:
-            raise NotImplementedError("training-time forward (jittered samples + autograd) is not part of the "
-                                      "B200 render path yet (SURVEY.md §8f row 3)")
+        row-major pixels of an image so warps can take 8x4 pixel blocks.
+
+        ``is_train=True`` (forward only): every ray's samples are shifted by one ``u ~ U[0,1)`` step, drawn exactly as
+        the reference does (``torch.rand_like`` of a CPU ``[R,1]`` tensor, FieldBase.py:128-130) or passed in as
+        ``jitter=`` ([R] or [R,1]); a non-white background is made white with probability 1/2 (FieldBase.py:299)."""
+        if is_train and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("the B200 render path has no backward pass (SURVEY.md §8f row 3): call the "
+                                      "training-time forward under torch.no_grad()")
+        with torch.no_grad():
+            return self._forward(rays_chunk, white_bg, is_train, N_samples, image_width, **fwd_kw)
+
+    def _forward(self, rays_chunk, white_bg, is_train, N_samples, image_width, jitter=None, **fwd_kw):
         h = self._ensure_handle()
         lib = _lib.load()
         self._set_switches(lib, h, **fwd_kw)
@@ -274,10 +282,24 @@ class Base(torch.nn.Module):
         rgb = torch.empty((R, 3), dtype=torch.float32, device=self.device)
         depth = torch.empty((R,), dtype=torch.float32, device=self.device)
         acc = torch.empty((R,), dtype=torch.float32, device=self.device)
+        if is_train:
+            if jitter is None:
+                jitter = torch.rand_like(torch.empty((R, 1), dtype=torch.float32))      # CPU draw, as the reference
+            jitter = _f32c(jitter.reshape(-1).to(self.device))
+            if jitter.numel() != R:
+                raise ValueError(f"jitter must have one value per ray ({R}), got {jitter.numel()}")
+            white_bg = bool(white_bg) or bool(torch.rand((1,)) < 0.5)
         with torch.cuda.device(self.device):
-            _lib.check(lib.ngf_field_render(h, rays.data_ptr(), R, rays.shape[1], int(N_samples), int(bool(white_bg)),
-                                            int(image_width), rgb.data_ptr(), depth.data_ptr(), acc.data_ptr(),
-                                            self._mlp_impl, _cuda_stream_ptr(self.device)), "ngf_field_render")
+            if is_train:
+                _lib.check(lib.ngf_field_render_jitter(h, rays.data_ptr(), R, rays.shape[1], int(N_samples),
+                                                       int(bool(white_bg)), int(image_width), jitter.data_ptr(),
+                                                       rgb.data_ptr(), depth.data_ptr(), acc.data_ptr(), self._mlp_impl,
+                                                       _cuda_stream_ptr(self.device)), "ngf_field_render_jitter")
+            else:
+                _lib.check(lib.ngf_field_render(h, rays.data_ptr(), R, rays.shape[1], int(N_samples),
+                                                int(bool(white_bg)), int(image_width), rgb.data_ptr(), depth.data_ptr(),
+                                                acc.data_ptr(), self._mlp_impl, _cuda_stream_ptr(self.device)),
+                           "ngf_field_render")
         self._last_acc = acc
         return {'rgb_map': rgb, 'depth_map': depth}
 
@@ -385,11 +407,10 @@ class Base(torch.nn.Module):
         raise NotImplementedError
 
     @torch.no_grad()
-    def sample_ray(self, rays_o, rays_d, is_train=True, N_samples=-1):
-        """Reference: Base.sample_ray (FieldBase.py:118-137), eval branch.  -> (rays_pts [R,S,3], interpx [R,S],
-        ~mask_outbbox [R,S] bool)."""
-        if is_train:
-            raise NotImplementedError("jittered training-time sampling is not part of the B200 render path yet")
+    def sample_ray(self, rays_o, rays_d, is_train=True, N_samples=-1, jitter=None):
+        """Reference: Base.sample_ray (FieldBase.py:118-137).  -> (rays_pts [R,S,3], interpx [R,S],
+        ~mask_outbbox [R,S] bool).  ``is_train``: one ``u ~ U[0,1)`` per ray shifts its samples, drawn as the
+        reference does (CPU ``torch.rand_like``) unless ``jitter`` ([R] or [R,1]) is given."""
         h = self._ensure_handle()
         S = N_samples if N_samples > 0 else self.nSamples
         rays = _f32c(torch.cat([rays_o, rays_d], -1).to(self.device))
@@ -397,9 +418,20 @@ class Base(torch.nn.Module):
         pts = torch.empty((R, S, 3), dtype=torch.float32, device=self.device)
         t = torch.empty((R, S), dtype=torch.float32, device=self.device)
         inside = torch.empty((R, S), dtype=torch.uint8, device=self.device)
+        lib = _lib.load()
         with torch.cuda.device(self.device):
-            _lib.check(_lib.load().ngf_field_sample_ray(h, rays.data_ptr(), R, 6, S, pts.data_ptr(), t.data_ptr(),
-                                                        inside.data_ptr(), _cuda_stream_ptr(self.device)))
+            if is_train:
+                if jitter is None:
+                    jitter = torch.rand_like(torch.empty((R, 1), dtype=torch.float32))
+                jitter = _f32c(jitter.reshape(-1).to(self.device))
+                if jitter.numel() != R:
+                    raise ValueError(f"jitter must have one value per ray ({R}), got {jitter.numel()}")
+                _lib.check(lib.ngf_field_sample_ray_jitter(h, rays.data_ptr(), R, 6, S, jitter.data_ptr(), pts.data_ptr(),
+                                                           t.data_ptr(), inside.data_ptr(),
+                                                           _cuda_stream_ptr(self.device)))
+            else:
+                _lib.check(lib.ngf_field_sample_ray(h, rays.data_ptr(), R, 6, S, pts.data_ptr(), t.data_ptr(),
+                                                    inside.data_ptr(), _cuda_stream_ptr(self.device)))
         return pts, t, inside.bool()
 
     @torch.no_grad()

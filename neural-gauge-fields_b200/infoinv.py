@@ -61,9 +61,9 @@ class TriPlane(Base):
     def _apply_alpha_kw(self, infoinv=True, **_):
         _lib.check(_lib.load().ngf_field_set_infoinv(self._ensure_handle(), int(bool(infoinv))))
 
-    def forward(self, rays_chunk, white_bg=True, is_train=False, N_samples=-1, infoinv=True, image_width=0):
+    def forward(self, rays_chunk, white_bg=True, is_train=False, N_samples=-1, infoinv=True, image_width=0, jitter=None):
         return super().forward(rays_chunk, white_bg=white_bg, is_train=is_train, N_samples=N_samples,
-                               image_width=image_width, infoinv=infoinv)
+                               image_width=image_width, infoinv=infoinv, jitter=jitter)
 
     def feature2density(self, density_features, density_shift=-10):
         return F.softplus(density_features + density_shift)

@@ -67,9 +67,9 @@ class TriPlane(Base):
         # Field.py:58: the gauge offsets apply once iteration >= gauge_start (main.py:67 passes 30001 at eval)
         _lib.check(lib.ngf_field_set_gauge(h, int(iteration >= self.gauge_start)))
 
-    def forward(self, rays_chunk, white_bg=True, is_train=False, N_samples=-1, iteration=0, image_width=0):
+    def forward(self, rays_chunk, white_bg=True, is_train=False, N_samples=-1, iteration=0, image_width=0, jitter=None):
         return super().forward(rays_chunk, white_bg=white_bg, is_train=is_train, N_samples=N_samples,
-                               image_width=image_width, iteration=iteration)
+                               image_width=image_width, iteration=iteration, jitter=jitter)
 
     # Reference: Field.py:48-50
     def feature2density(self, density_features, density_shift=-10):

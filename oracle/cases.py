@@ -70,6 +70,16 @@ CASES = [
 ]
 CASE_BY_NAME = {c.name: c for c in CASES}
 
+# forward(is_train=True): jittered sampling (FieldBase.py:128-130), one 4096-ray chunk each so that the reference draws
+# its random numbers exactly once (u [R,1], then the background coin when white_bg is False).  Forward only.
+TRAIN_SEED = 4242
+TRAIN_CASES = [
+    Case("train_tp_hull"),
+    Case("train_tp_fog_blackbg", kind="fog", white_bg=False, pose=5),
+    Case("train_ii_fog", variant="infoinv", kind="fog", pose=4),
+]
+TRAIN_BY_NAME = {c.name: c for c in TRAIN_CASES}
+
 
 @functools.lru_cache(maxsize=8)
 def _field_state(variant, kind, seed, res):

@@ -60,6 +60,26 @@ def make_case(case: K.Case) -> str:
 
 
 @torch.no_grad()
+def make_train_case(case: K.Case) -> str:
+    """The reference's forward(is_train=True) on one chunk.  Its random draws (FieldBase.py:130, :299) are recorded by
+    drawing the same numbers from the same seed first: u = rand_like([R,1]), then the background coin rand(1)."""
+    field, state, kw, occ, rays = build_reference_field(case)
+    assert rays.shape[0] <= 4096
+    torch.manual_seed(K.TRAIN_SEED)
+    u = torch.rand_like(torch.empty((rays.shape[0], 1), dtype=torch.float32))
+    coin = float(torch.rand((1,)))
+    torch.manual_seed(K.TRAIN_SEED)
+    out = field(rays, is_train=True, white_bg=case.white_bg, N_samples=case.n_samples, **forward_kwargs(case))
+    path = K.golden_path(case.name)
+    np.savez_compressed(path, rgb=out["rgb_map"].numpy().astype(np.float32),
+                        depth=out["depth_map"].numpy().astype(np.float32), jitter=u.numpy().astype(np.float32),
+                        coin=np.float32(coin), white_used=np.bool_(case.white_bg or coin < 0.5),
+                        seed=np.int64(K.TRAIN_SEED), fingerprint=K.fingerprint(state, rays, occ),
+                        torch_version=torch.__version__)
+    return path
+
+
+@torch.no_grad()
 def make_pointwise(variant: str) -> str:
     case = K.Case(f"pointwise_{variant}", variant=variant, kind="rand")
     field, state, kw, occ, rays = build_reference_field(case)
@@ -162,9 +182,11 @@ def main(argv):
     if not ref_loader.available():
         raise SystemExit("reference tree not found: golden vectors can only be generated in the build container")
     names = argv or [c.name for c in K.CASES] + ["pointwise_triplane", "pointwise_infoinv", "alphamask_triplane"] + \
-        [c.name for c in K.NEUTEX_CASES]
+        [c.name for c in K.NEUTEX_CASES] + [c.name for c in K.TRAIN_CASES]
     for n in names:
-        if n == "alphamask_triplane":
+        if n in K.TRAIN_BY_NAME:
+            p = make_train_case(K.TRAIN_BY_NAME[n])
+        elif n == "alphamask_triplane":
             p = make_alphamask()
         elif n in K.NEUTEX_BY_NAME:
             p = make_neutex(K.NEUTEX_BY_NAME[n])

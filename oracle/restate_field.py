@@ -161,14 +161,18 @@ def reference_rays(H: int, W: int, focal, c2w: torch.Tensor, center=None) -> tor
 # --------------------------------------------------------------------------------------------------------------
 # a2  ray march (FieldBase.py:118-137)
 # --------------------------------------------------------------------------------------------------------------
-def march(spec: FieldSpec, o: torch.Tensor, d: torch.Tensor, S: int):
-    """-> p [R,S,3], t [R,S], inside [R,S] bool.  Every op is a separate fp32 rounding, as in eager torch."""
+def march(spec: FieldSpec, o: torch.Tensor, d: torch.Tensor, S: int, jitter=None):
+    """-> p [R,S,3], t [R,S], inside [R,S] bool.  Every op is a separate fp32 rounding, as in eager torch.
+    jitter [R,1] (is_train, FieldBase.py:128-130): rng = arange(S) + u, one u per ray."""
     lo, hi = spec.aabb[0], spec.aabb[1]
     safe_d = torch.where(d == 0, torch.full_like(d, 1e-6), d)
     ta = (hi - o) / safe_d
     tb = (lo - o) / safe_d
     t0 = torch.minimum(ta, tb).amax(-1).clamp(min=spec.near, max=spec.far)
     k = torch.arange(S)[None].float()
+    if jitter is not None:
+        k = k.repeat(d.shape[-2], 1)
+        k += jitter.reshape(-1, 1)
     t = t0[:, None] + spec.step_size * k                     # mul, then add
     p = o[:, None, :] + d[:, None, :] * t[..., None]          # mul, then add
     outside = ((lo > p) | (p > hi)).any(dim=-1)
@@ -330,14 +334,14 @@ def transmittance(sig: torch.Tensor, delta: torch.Tensor):
 
 
 # --------------------------------------------------------------------------------------------------------------
-# forward (FieldBase.py:251-312), eval only
+# forward (FieldBase.py:251-312); jitter = the per-ray u of is_train=True, passed in (forward only)
 # --------------------------------------------------------------------------------------------------------------
 @torch.no_grad()
-def render_chunk(spec: FieldSpec, rays: torch.Tensor, white_bg: bool = True, N_samples: int = -1):
+def render_chunk(spec: FieldSpec, rays: torch.Tensor, white_bg: bool = True, N_samples: int = -1, jitter=None):
     """rays [R,>=6] fp32 CPU -> rgb [R,3], depth [R].  Accumulates n_valid / n_active into spec.stats."""
     S = N_samples if N_samples > 0 else spec.n_samples
     o, d = rays[:, :3], rays[:, 3:6]
-    p, t, live = march(spec, o, d, S)
+    p, t, live = march(spec, o, d, S, jitter)
     delta = torch.cat([t[:, 1:] - t[:, :-1], torch.zeros_like(t[:, :1])], -1)
     if spec.alpha_volume is not None:
         keep = alpha_keep(spec, p[live])
@@ -371,11 +375,13 @@ def render_chunk(spec: FieldSpec, rays: torch.Tensor, white_bg: bool = True, N_s
 
 
 @torch.no_grad()
-def render(spec: FieldSpec, rays: torch.Tensor, chunk: int = 4096, white_bg: bool = True, N_samples: int = -1):
+def render(spec: FieldSpec, rays: torch.Tensor, chunk: int = 4096, white_bg: bool = True, N_samples: int = -1,
+           jitter=None):
     """Chunk loop of TriPlane/main.py:60-71."""
     rgbs, depths = [], []
     for s in range(0, rays.shape[0], chunk):
-        r, z = render_chunk(spec, rays[s:s + chunk], white_bg=white_bg, N_samples=N_samples)
+        r, z = render_chunk(spec, rays[s:s + chunk], white_bg=white_bg, N_samples=N_samples,
+                            jitter=None if jitter is None else jitter.reshape(-1, 1)[s:s + chunk])
         rgbs.append(r)
         depths.append(z)
     return torch.cat(rgbs), torch.cat(depths)

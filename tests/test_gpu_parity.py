@@ -264,3 +264,53 @@ def test_render_split_into_ray_batches_by_queue_budget():
     res = subprocess.run([sys.executable, os.path.join(root, "scripts", "check_small_queue.py")], env=env,
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", [c.name for c in K.TRAIN_CASES])
+def test_train_forward_matches_reference_golden(name):
+    """forward(is_train=True), forward only: jittered sampling (FieldBase.py:128-130) and the background coin
+    (FieldBase.py:299) drawn from torch's CPU generator in the reference's order, so the same seed gives the
+    reference's own numbers."""
+    case = K.TRAIN_BY_NAME[name]
+    gold = load_golden(name)
+    state, kw, occ, rays = K.build_inputs(case)
+    assert K.fingerprint(state, rays, occ) == str(gold["fingerprint"])
+    f = build_cuda_field(case, state, kw, occ)
+    with torch.no_grad():
+        torch.manual_seed(int(gold["seed"]))
+        out = f(rays.cuda(), white_bg=case.white_bg, is_train=True, N_samples=case.n_samples, **forward_kwargs(case))
+    torch.cuda.synchronize()
+    err = np.abs(out["rgb_map"].cpu().numpy() - gold["rgb"]).max()
+    derr = np.abs(out["depth_map"].cpu().numpy() - gold["depth"]).max()
+    assert err < RGB_TOL, f"{name}: rgb max-abs {err:.3e}"
+    assert derr < DEPTH_TOL, f"{name}: depth max-abs {derr:.3e}"
+    # the same jitter passed in explicitly (and the background the coin chose)
+    u = torch.from_numpy(gold["jitter"])
+    with torch.no_grad():
+        torch.manual_seed(int(gold["seed"]) + 1 if case.white_bg else 0)
+        out2 = f(rays.cuda(), white_bg=bool(gold["white_used"]), is_train=True, N_samples=case.n_samples, jitter=u,
+                 **forward_kwargs(case))
+    if bool(gold["white_used"]):      # (the colour kernel accumulates with atomics: equal up to summation order)
+        assert float((out2["rgb_map"] - out["rgb_map"]).abs().max()) < 1e-5
+        assert torch.equal(out2["depth_map"], out["depth_map"])
+    # sample positions are a decision chain: bit-exact against the oracle
+    spec = oracle_spec(case, state, kw, occ)
+    p, t, inside = R.march(spec, rays[:256, :3], rays[:256, 3:6], 48, u[:256])
+    pc, tc, ic = f.sample_ray(rays[:256, :3], rays[:256, 3:6], is_train=True, N_samples=48, jitter=u[:256])
+    assert torch.equal(pc.cpu(), p) and torch.equal(tc.cpu(), t) and torch.equal(ic.cpu(), inside)
+
+
+def test_train_forward_zero_jitter_is_eval_and_backward_is_refused():
+    case = K.CASE_BY_NAME["tp_hull_c1"]
+    state, kw, occ, rays = K.build_inputs(case)
+    f = build_cuda_field(case, state, kw, occ)
+    r = rays.cuda()
+    ev = f(r, white_bg=True, N_samples=case.n_samples, **forward_kwargs(case))
+    with torch.no_grad():
+        tr = f(r, white_bg=True, is_train=True, N_samples=case.n_samples, jitter=torch.zeros(r.shape[0]),
+               **forward_kwargs(case))
+    assert float((ev["rgb_map"] - tr["rgb_map"]).abs().max()) < 1e-5      # atomics: equal up to summation order
+    assert torch.equal(ev["depth_map"], tr["depth_map"])
+    assert any(p.requires_grad for p in f.parameters())
+    with pytest.raises(NotImplementedError):
+        f(r, white_bg=True, is_train=True, N_samples=case.n_samples, **forward_kwargs(case))
