@@ -463,11 +463,10 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
     }
   } else if (warp == kWorkerWarps) {
     // ------------------------------------------------------------------ MMA issuer (rank 0 of a pair)
-    // The whole warp walks the loop in lock step and one elected lane issues: every operand of the issue loop then
-    // derives from warp-uniform values (kernel parameters, loop counters, warp-broadcast loads), so the descriptors
-    // are built in the uniform datapath.  (With the loop under `if (lane == 0)` they went through vector registers,
-    // R2UR and a replay loop around each tcgen05.mma: ~226 cycles per M128 N256 K16 MMA instead of the 128-cycle floor,
-    // scripts/micro/umma_issue.cu.)
+    // The warp walks the layers together and one lane, chosen with elect.sync, issues a whole layer.  (With the loop
+    // under `if (lane == 0)` ptxas wrapped every tcgen05.mma in a replay loop over possibly divergent operands and the
+    // per-slice address arithmetic sat between the MMAs: ~226 cycles per M128 N256 K16 MMA against the pipe's 128,
+    // scripts/micro/umma_issue.cu.  Under elect.sync it knows a single lane is active.)
     const uint32_t n_units = __shfl_sync(0xffffffffu, n_tiles, 0);
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t a0 = smem_u32(smem + offA), a2 = smem_u32(smem + offA2), r0 = smem_u32(smem + offRing);
