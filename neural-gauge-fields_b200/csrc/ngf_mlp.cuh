@@ -296,20 +296,22 @@ __device__ __forceinline__ void mlp_gather_at(const FieldDev& f, const QEntry* _
     // tap), so a warp-wide load touches ~8 cache lines instead of 32.  The gather is latency-bound, so all 4 x J texel
     // loads of a plane are issued before the first one is used.
     constexpr int J = 768 / NT;                            // items per thread and plane (128 rows x 6 chunks = 768)
+    // The gather is bound by load latency, so the loads run one plane ahead of the blend: item j of
+    // plane pl + 1 is requested as soon as item j of plane pl has been blended and its registers are free.
+    TapsH t[J];
+    uint4 raw[J][4];
+    auto request = [&](int pl, int j) {
+      const int it = tid + NT * j, chunk = it % 6;
+      t[j] = tapbuf[pl * kTileM + it / 6];
+      const __half* app = f.plane[pl].app;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        raw[j][k] = __ldg(reinterpret_cast<const uint4*>(app + (size_t)t[j].off[k] * AC + chunk * 8));
+    };
+#pragma unroll
+    for (int j = 0; j < J; ++j) request(0, j);
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {
-      const PlaneDev& P = f.plane[pl];
-      TapsH t[J];
-      uint4 raw[J][4];
-#pragma unroll
-      for (int j = 0; j < J; ++j) t[j] = tapbuf[pl * kTileM + (tid + NT * j) / 6];
-#pragma unroll
-      for (int j = 0; j < J; ++j) {
-        const int chunk = (tid + NT * j) % 6;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          raw[j][k] = __ldg(reinterpret_cast<const uint4*>(P.app + (size_t)t[j].off[k] * AC + chunk * 8));
-      }
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         const int it = tid + NT * j, chunk = it % 6, m = it / 6;
@@ -320,6 +322,7 @@ __device__ __forceinline__ void mlp_gather_at(const FieldDev& f, const QEntry* _
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc[e] = k == 0 ? __hmul2(t[j].w[0], h[e]) : __hfma2(t[j].w[k], h[e], acc[e]);
         }
+        if (pl < 2) request(pl + 1, j);
         uint4 o;
         o.x = *reinterpret_cast<uint32_t*>(&acc[0]); o.y = *reinterpret_cast<uint32_t*>(&acc[1]);
         o.z = *reinterpret_cast<uint32_t*>(&acc[2]); o.w = *reinterpret_cast<uint32_t*>(&acc[3]);
