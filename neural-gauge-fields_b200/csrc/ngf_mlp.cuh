@@ -250,24 +250,6 @@ __device__ __forceinline__ uint4 blend8h(const __half* __restrict__ base, int ch
   return o;
 }
 
-// fp32 variant (InfoInv multiplies the blended feature by the phase code before rounding)
-__device__ __forceinline__ void blend8(const __half* __restrict__ base, int chan_off, int AC, const Taps& t,
-                                       float out[8]) {
-#pragma unroll
-  for (int e = 0; e < 8; ++e) out[e] = 0.f;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + (size_t)t.off[k] * AC + chan_off));
-    const __half2* h = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float2 v = __half22float2(h[e]);
-      out[2 * e] += t.w[k] * v.x;
-      out[2 * e + 1] += t.w[k] * v.y;
-    }
-  }
-}
-
 // ----------------------------------------------------------------------------------------------------------
 // Fill the A tile rows [0,128) from queue slots head .. head+127.
 //   dir / dir_stride : view direction of entry id is dir[id*dir_stride + 0..2]; with a camera (cam != nullptr) it is
@@ -338,12 +320,32 @@ __device__ __forceinline__ void mlp_gather_at(const FieldDev& f, const QEntry* _
       float pe[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) pe[k] = f.infoinv ? phase_value<12>(xyz, chunk * 8 + k) : 1.f;
+      // all twelve texel loads of the item are requested before the first blend (the gather is latency bound)
+      Taps t[3];
+      uint4 raw[3][4];
 #pragma unroll
       for (int pl = 0; pl < 3; ++pl) {
         const PlaneDev& P = f.plane[pl];
-        Taps t = make_taps(e.c[2 * pl], e.c[2 * pl + 1], P.W, P.H, P.wm1, P.hm1);
+        t[pl] = make_taps(e.c[2 * pl], e.c[2 * pl + 1], P.W, P.H, P.wm1, P.hm1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          raw[pl][k] = __ldg(reinterpret_cast<const uint4*>(P.app + (size_t)t[pl].off[k] * AC + chunk * 8));
+      }
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) {
         float v[8];
-        blend8(P.app, chunk * 8, AC, t, v);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) v[k2] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                    // same order of operations as blend8
+          const __half2* hh = reinterpret_cast<const __half2*>(&raw[pl][k]);
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            const float2 x = __half22float2(hh[e2]);
+            v[2 * e2] += t[pl].w[k] * x.x;
+            v[2 * e2 + 1] += t[pl].w[k] * x.y;
+          }
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] *= pe[k];
         uint4 o = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
