@@ -9,13 +9,14 @@ from . import _lib
 from .field_base import _cuda_stream_ptr
 
 
-@torch.no_grad()
 def renderer(rays, field, chunk=4096, N_samples=-1, white_bg=True, is_train=False, device='cuda', image_width=0,
              **fwd_kw):
     """Reference: ``renderer`` (TriPlane/main.py:60-71).  The reference slices the frame into ``chunk``-ray pieces
     and calls the field once per piece; the fused kernel takes the whole frame in one launch, so ``chunk`` is
     accepted for signature compatibility and ignored.  ``fwd_kw`` defaults to what the reference passes
-    (``iteration=30001`` for TriPlane, main.py:67; ``infoinv`` for InfoInv)."""
+    (``iteration=30001`` for TriPlane, main.py:67; ``infoinv`` for InfoInv).  Gradients are never recorded (the field's
+    forward runs under ``torch.no_grad()``); ``is_train=True`` with autograd enabled is refused by the field, as the
+    training loop (main.py:272) would otherwise get detached tensors."""
     if not fwd_kw and hasattr(field, "gauge_start"):
         fwd_kw = {"iteration": 30001}
     out = field(rays, is_train=is_train, white_bg=white_bg, N_samples=N_samples, image_width=image_width, **fwd_kw)
