@@ -80,6 +80,16 @@ TRAIN_CASES = [
 ]
 TRAIN_BY_NAME = {c.name: c for c in TRAIN_CASES}
 
+# one training step's loss and gradients (main.py:272-283) on the same chunks: the pin of the backward-pass oracle
+GRAD_CASES = {"grad_tp_hull": "train_tp_hull", "grad_ii_fog": "train_ii_fog"}
+GRAD_TARGET_SEED = 99
+GRAD_SAMPLES = 4096            # entries of every large gradient tensor kept in the golden file
+
+
+def grad_target(n_rays: int) -> torch.Tensor:
+    """Synthetic rgb_train: the gradients do not care what the target is, only that both sides use the same."""
+    return torch.rand((n_rays, 3), generator=torch.Generator().manual_seed(GRAD_TARGET_SEED))
+
 
 @functools.lru_cache(maxsize=8)
 def _field_state(variant, kind, seed, res):

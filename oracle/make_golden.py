@@ -79,6 +79,42 @@ def make_train_case(case: K.Case) -> str:
     return path
 
 
+def make_grad_case(name: str) -> str:
+    """The reference's own training step on one chunk (main.py:272-283): forward(is_train=True), loss = mean squared
+    error against rgb_train, loss.backward().  Small gradients are stored whole; of the plane and gauge-plane gradients
+    (sparse, up to 4 M entries) the sum, the absolute sum, the number of non-zeros and GRAD_SAMPLES of the non-zero
+    entries."""
+    case = K.TRAIN_BY_NAME[K.GRAD_CASES[name]]
+    field, state, kw, occ, rays = build_reference_field(case)
+    target = K.grad_target(rays.shape[0])
+    torch.manual_seed(K.TRAIN_SEED)
+    u = torch.rand_like(torch.empty((rays.shape[0], 1), dtype=torch.float32))
+    torch.manual_seed(K.TRAIN_SEED)
+    field.zero_grad()
+    out = field(rays, is_train=True, white_bg=True, N_samples=case.n_samples, **forward_kwargs(case))
+    loss = torch.mean((out["rgb_map"] - target) ** 2)
+    loss.backward()
+    rec = dict(loss=np.float32(loss.item()), jitter=u.numpy(), fingerprint=K.fingerprint(state, rays, occ),
+               torch_version=torch.__version__)
+    g = torch.Generator().manual_seed(7)
+    for k, p in field.named_parameters():
+        gr = p.grad.detach().reshape(-1)
+        key = k.replace(".", "__")
+        if gr.numel() <= 65536:
+            rec["full__" + key] = gr.numpy()
+        else:
+            nz = torch.nonzero(gr).reshape(-1)
+            pick = nz[torch.randperm(nz.numel(), generator=g)[:K.GRAD_SAMPLES]].sort().values
+            rec["idx__" + key] = pick.numpy().astype(np.int64)
+            rec["val__" + key] = gr[pick].numpy()
+            rec["sum__" + key] = np.float64(gr.double().sum().item())
+            rec["abs__" + key] = np.float64(gr.double().abs().sum().item())
+            rec["nnz__" + key] = np.int64(nz.numel())
+    path = K.golden_path(name)
+    np.savez_compressed(path, **rec)
+    return path
+
+
 @torch.no_grad()
 def make_pointwise(variant: str) -> str:
     case = K.Case(f"pointwise_{variant}", variant=variant, kind="rand")
@@ -182,9 +218,11 @@ def main(argv):
     if not ref_loader.available():
         raise SystemExit("reference tree not found: golden vectors can only be generated in the build container")
     names = argv or [c.name for c in K.CASES] + ["pointwise_triplane", "pointwise_infoinv", "alphamask_triplane"] + \
-        [c.name for c in K.NEUTEX_CASES] + [c.name for c in K.TRAIN_CASES]
+        [c.name for c in K.NEUTEX_CASES] + [c.name for c in K.TRAIN_CASES] + list(K.GRAD_CASES)
     for n in names:
-        if n in K.TRAIN_BY_NAME:
+        if n in K.GRAD_CASES:
+            p = make_grad_case(n)
+        elif n in K.TRAIN_BY_NAME:
             p = make_train_case(K.TRAIN_BY_NAME[n])
         elif n == "alphamask_triplane":
             p = make_alphamask()

@@ -339,6 +339,11 @@ def transmittance(sig: torch.Tensor, delta: torch.Tensor):
 @torch.no_grad()
 def render_chunk(spec: FieldSpec, rays: torch.Tensor, white_bg: bool = True, N_samples: int = -1, jitter=None):
     """rays [R,>=6] fp32 CPU -> rgb [R,3], depth [R].  Accumulates n_valid / n_active into spec.stats."""
+    return _render_chunk(spec, rays, white_bg, N_samples, jitter)
+
+
+def _render_chunk(spec: FieldSpec, rays: torch.Tensor, white_bg: bool = True, N_samples: int = -1, jitter=None):
+    """Body of render_chunk; differentiable when the spec's parameter tensors require gradients (loss_and_grads)."""
     S = N_samples if N_samples > 0 else spec.n_samples
     o, d = rays[:, :3], rays[:, 3:6]
     p, t, live = march(spec, o, d, S, jitter)
@@ -366,7 +371,8 @@ def render_chunk(spec: FieldSpec, rays: torch.Tensor, white_bg: bool = True, N_s
     if white_bg:
         out = out + (1.0 - acc[:, None])
     out = out.clamp(0, 1)
-    depth = (w * t).sum(-1) + (1.0 - acc) * rays[:, -1]                  # NB last ray column (FieldBase.py:306)
+    with torch.no_grad():                                                # FieldBase.py:304-306
+        depth = (w * t).sum(-1) + (1.0 - acc) * rays[:, -1]              # NB last ray column (FieldBase.py:306)
     st = spec.stats
     st["rays"] = st.get("rays", 0) + R
     st["n_valid"] = st.get("n_valid", 0) + int(live.sum())
@@ -385,6 +391,45 @@ def render(spec: FieldSpec, rays: torch.Tensor, chunk: int = 4096, white_bg: boo
         rgbs.append(r)
         depths.append(z)
     return torch.cat(rgbs), torch.cat(depths)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# §8f rank 3  one training step's loss and gradients (TriPlane/main.py:272-283), the oracle of the backward pass that
+# the CUDA path does not have yet: forward(is_train=True) with the given jitter, loss = mean((rgb_map - rgb_train)^2),
+# autograd through the same restated ops.  Parameter names are the reference's state_dict keys.
+# --------------------------------------------------------------------------------------------------------------
+def param_tensors(spec: FieldSpec) -> dict:
+    p = {"plane_xy": spec.planes[0], "plane_yz": spec.planes[1], "plane_xz": spec.planes[2],
+         "rgb_decoder.basis.weight": spec.basis_w}
+    if spec.gauge is not None:
+        p.update({"gauge_xy": spec.gauge[0], "gauge_yz": spec.gauge[1], "gauge_xz": spec.gauge[2]})
+    for i, (w, b) in zip((0, 2, 4), spec.rgb_layers):
+        p[f"rgb_decoder.mlp.{i}.weight"], p[f"rgb_decoder.mlp.{i}.bias"] = w, b
+    if spec.variant == "infoinv":
+        for i, (w, b) in zip((0, 2, 4), spec.density_layers):
+            p[f"density_decoder.mlp.{i}.weight"], p[f"density_decoder.mlp.{i}.bias"] = w, b
+    else:
+        p["density_decoder.weight"], p["density_decoder.bias"] = spec.density_layers[0]
+    return p
+
+
+def loss_and_grads(spec: FieldSpec, rays: torch.Tensor, target: torch.Tensor, jitter, white_bg: bool = True,
+                   N_samples: int = -1):
+    """-> (loss 0-d, {state_dict key: gradient}) for one chunk of training rays.  ``spec`` is not modified."""
+    import dataclasses
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in param_tensors(spec).items()}
+    s2 = dataclasses.replace(
+        spec, planes=[leaf["plane_xy"], leaf["plane_yz"], leaf["plane_xz"]], basis_w=leaf["rgb_decoder.basis.weight"],
+        gauge=None if spec.gauge is None else [leaf["gauge_xy"], leaf["gauge_yz"], leaf["gauge_xz"]],
+        rgb_layers=[(leaf[f"rgb_decoder.mlp.{i}.weight"], leaf[f"rgb_decoder.mlp.{i}.bias"]) for i in (0, 2, 4)],
+        density_layers=([(leaf[f"density_decoder.mlp.{i}.weight"], leaf[f"density_decoder.mlp.{i}.bias"]) for i in (0, 2, 4)]
+                        if spec.variant == "infoinv" else [(leaf["density_decoder.weight"], leaf["density_decoder.bias"])]),
+        stats={})
+    with torch.enable_grad():
+        rgb, _ = _render_chunk(s2, rays, white_bg, N_samples, jitter)
+        loss = torch.mean((rgb - target) ** 2)
+        loss.backward()
+    return loss.detach(), {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaf.items()}
 
 
 # --------------------------------------------------------------------------------------------------------------
