@@ -36,6 +36,7 @@ RAYS_PER_FRAME = H * W
 HBM_BYTES_PER_RAY = 40            # 24 B ray in + 16 B (rgb, depth) out: SURVEY.md §8(d)
 MLP_FLOPS_PER_COLOUR_SAMPLE = 70400   # reference arithmetic incl. the 144x144 basis: SURVEY.md §8(a) row a9
 MLP_FLOPS_PER_DENSITY_SAMPLE = 96
+MLP_FLOPS_EXECUTED_PER_COLOUR_SAMPLE = 2 * (160 * 64 + 64 * 64 + 64 * 3)   # basis folded into layer 1, K padded to 160
 
 
 def parse():
@@ -139,7 +140,9 @@ def cpu_port_rate(spec, R, rays, budget_s: float, threads: int):
 
 def run_reference(args, rank):
     """--impl reference: the reference's own algorithm on the host cores.  /root/reference does not exist on the GPU
-    box and the reference is Python (nothing to compile into oracle/_ref), so this times the oracle port."""
+    box and the reference is Python (nothing to compile into oracle/_ref), so this times the oracle port — bit-identical
+    to the imported reference on the same torch build (tests/golden).  A step renders the whole 640 000-ray frame in
+    4096-ray chunks (TriPlane/main.py:60-71) when warm-up + K steps fit ~4 minutes, else a strided sample of it."""
     if rank != 0:
         return
     from oracle import cases as K
@@ -150,27 +153,30 @@ def run_reference(args, rank):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     def render_sample(i, n_sample):
-        rays = K.synth.config_rays("C2", i % N_POSES)[:: RAYS_PER_FRAME // n_sample][:n_sample].contiguous()
+        rays = K.synth.config_rays("C2", i % N_POSES)
+        if n_sample < RAYS_PER_FRAME:
+            rays = rays[:: RAYS_PER_FRAME // n_sample][:n_sample].contiguous()
         t0 = time.perf_counter()
         R.render(spec, rays, N_samples=S)
         return time.perf_counter() - t0
-    # bounded sample: rays per step sized from a short probe so that warm-up + K steps take about 1.5 minutes
     render_sample(0, 4096)
-    probe = 4096 / render_sample(1, 4096)
-    n_sample = int(probe * 90.0 / max(args.steps + args.warmup, 1)) // 1024 * 1024
-    n_sample = max(1024, min(65536, n_sample))
+    probe = 16384 / render_sample(1, 16384)
+    n_steps = max(args.steps + args.warmup, 1)
+    n_sample = int(probe * 240.0 / n_steps) // 1024 * 1024
+    n_sample = RAYS_PER_FRAME if n_sample >= RAYS_PER_FRAME else max(1024, n_sample)
     for i in range(args.warmup):
         render_sample(i, n_sample)
     total = sum(render_sample(i, n_sample) for i in range(args.steps))
     v = n_sample * args.steps / total
+    what = "the whole 640000-ray frame" if n_sample == RAYS_PER_FRAME else f"a {n_sample}-ray strided sample of one frame"
     print(json.dumps({
         "impl": "reference", "metric": "rays/sec (800x800, 192 samples/ray)", "value": v, "unit": "rays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"TriPlane {args.field} field 800x800 rays x 192 samples, gauge on, alpha mask "
-                               f"(BASELINE configs[1]); each step = {n_sample}-ray strided sample of one frame"},
+        "config": {"workload": f"TriPlane {args.field} field, 800x800 rays x 192 samples/ray, gauge on, 256^3 alpha mask "
+                               f"(BASELINE configs[1]); each step = {what}", "rays_per_step": n_sample},
         "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
-                         "sample": f"{n_sample} rays/step strided over the frame, 4096-ray chunks"},
+                         "sample": f"{what} per step, 4096-ray chunks, torch CPU fp32"},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -189,7 +195,6 @@ def main():
     import torch.distributed as dist
     import ngf_b200
     from ngf_b200 import synth
-    from ngf_b200.render import frame_allgather
 
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -208,21 +213,52 @@ def main():
     host = [shard_of_batch(synth, p * world, world, rank).pin_memory() for p in range(N_POSES)]
     n_local = host[0].shape[0]
     dev_rays = [h.to(dev) for h in host]
-    img_w = W if world == 1 else 0
     n_batch = world * RAYS_PER_FRAME
 
-    sharded = ngf_b200.ShardedFrameRenderer(field, n_batch, BLOCK) if world > 1 else None
+    # ---- multi-GPU: the exchange runs inside the C ABI over NVLink peer memory (copy engines by default);
+    # NGF_BENCH_COMM=store|nccl selects the fused-store variant or the torch.distributed NCCL all-gather baseline
+    sharded, comm_mode, comm_note = None, None, None
+    if world > 1:
+        comm_mode = os.environ.get("NGF_BENCH_COMM", "copy")
+        try:
+            sharded = ngf_b200.ShardedFrameRenderer(field, n_batch, BLOCK, mode=comm_mode)
+            ok = 1
+        except RuntimeError as e:
+            ok, comm_note = 0, f"{comm_mode} unavailable on rank {rank}: {e}"
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if sharded is not None and sharded.comm is not None:
+                sharded.comm.close()
+            comm_note = comm_note or f"{comm_mode} unavailable on another rank"
+            comm_mode = "nccl"
+            sharded = ngf_b200.ShardedFrameRenderer(field, n_batch, BLOCK, mode="nccl")
+
+    prev = []
 
     def step_device(rays):
         if world == 1:
-            out = field(rays, white_bg=True, N_samples=S, iteration=30001, image_width=img_w)
+            out = field(rays, white_bg=True, N_samples=S, iteration=30001, image_width=W)
             return out["rgb_map"], out["depth_map"]
-        # render my shard; the all-gather of this batch overlaps the kernels of the next one (double-buffered)
-        return sharded.submit(rays, N_samples=S, white_bg=True, iteration=30001, image_width=W), None
+        # render my shard; the exchange of this batch overlaps the kernels of the next one.  The consumer of a gathered
+        # batch trails by one step: complete the all-gather of the previous ticket on this stream, then release it.
+        t = sharded.submit(rays, N_samples=S, white_bg=True, iteration=30001, image_width=W)
+        if prev:
+            p0 = prev.pop(0)
+            sharded.result(p0)
+            sharded.release(p0)
+        prev.append(t)
+        return t, None
+
+    def drain_device():
+        while prev:
+            p0 = prev.pop(0)
+            sharded.result(p0)
+            sharded.release(p0)
 
     def barrier():
         if world > 1:
-            torch.cuda.synchronize()          # includes the side stream of the overlapped all-gathers
+            torch.cuda.synchronize()          # includes the side streams of the overlapped exchange
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -233,11 +269,34 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- parity of the gathered batch (outside every timed region): batch 0 = frames 0..world-1, gathered on every
+    # rank, against this rank's own single-GPU render of the same frames through ngf_field_render
+    parity = None
+    if world > 1:
+        t = sharded.submit(dev_rays[0], N_samples=S, white_bg=True, iteration=30001, image_width=W)
+        got = sharded.result(t).clone()
+        sharded.release(t)
+        e_rgb = e_dep = 0.0
+        for fidx in range(world):
+            full = synth.config_rays("C2", fidx).to(dev)
+            o = field(full, white_bg=True, N_samples=S, iteration=30001, image_width=W)
+            g = got[fidx * RAYS_PER_FRAME:(fidx + 1) * RAYS_PER_FRAME]
+            e_rgb = max(e_rgb, float((g[:, :3] - o["rgb_map"]).abs().max()))
+            e_dep = max(e_dep, float((g[:, 3] - o["depth_map"]).abs().max()))
+            del full, o
+        e_rgb, e_dep = max_over_ranks(e_rgb), max_over_ranks(e_dep)
+        parity = {"parity_ok": bool(e_rgb < 1e-3 and e_dep < 2e-3), "rgb_max_abs": e_rgb, "depth_max_abs": e_dep,
+                  "what": f"gathered batch 0 ({world} frames, every rank) vs single-GPU ngf_field_render of the same frames; "
+                          "tolerance 1e-3 rgb / 2e-3 depth (the golden tolerance; differences come from the order of the "
+                          "fp32 atomic adds only)"}
+
     # ---- device-resident timed region (value)
     for i in range(max(args.warmup, 3)):
         step_device(dev_rays[i % N_POSES])
+    if world > 1:
+        drain_device()
     barrier()
-    stats = field.last_stats()
+    stats = field.last_stats() if world == 1 else None
     field.kernel_timing(min(args.steps, 4096))
     l0 = ngf_b200._lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -246,6 +305,8 @@ def main():
         e0.record()
         for i in range(args.steps):
             step_device(dev_rays[i % N_POSES])
+        if world > 1:
+            drain_device()
         e1.record()
         barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -253,14 +314,16 @@ def main():
     n_k, march_ms, colour_ms = field.kernel_timing_read()
     field.kernel_timing(0)
     value = n_batch * args.steps / (ms * 1e-3)
+    if stats is None:
+        # the sharded path renders from the comm's own workspace; the sample statistics come from one plain render
+        field(dev_rays[0], white_bg=True, N_samples=S, iteration=30001, image_width=W)
+        stats = field.last_stats()
 
-    # ---- end-to-end timed region: pinned host rays -> H2D -> render (+ all-gather) -> D2H of the results
-    e2e_drain = lambda: None
+    # ---- end-to-end timed region: pinned host rays -> H2D -> render (+ exchange) -> D2H of the results, through the
+    # C ABI's host-buffer entry points, 3 steps in flight
+    pend = []
     if world == 1:
-        # the repo's public call for a sequence of frames: ngf_b200.render_frames = ngf_field_render_host_async per frame,
-        # frame k+1 uploading while frame k renders and frame k-1 downloads (3 result buffers in rotation)
         outs = [(torch.empty((n_local, 3)).pin_memory(), torch.empty((n_local,)).pin_memory()) for _ in range(3)]
-        pend = []
         def step_e2e(i):
             r, d = outs[i % 3]
             pend.append(field.render_host_async(host[i % N_POSES], r, d, white_bg=True, N_samples=S, image_width=W,
@@ -270,15 +333,25 @@ def main():
         def e2e_drain():
             while pend:
                 field.host_wait(pend.pop(0))
-        d2h = n_local * 16
+        e2e_api = "ngf_b200.render_frames: ngf_field_render_host_async per frame (C ABI, pinned host buffers, 3 frames in flight)"
+    elif sharded.comm is not None:
+        # each rank uploads its 640 000 rays and downloads one whole gathered frame (rows of frame `rank` of the batch)
+        res_h = [torch.empty((RAYS_PER_FRAME, 4)).pin_memory() for _ in range(3)]
+        def step_e2e(i):
+            pend.append(sharded.comm.submit_host(host[i % N_POSES], res_h[i % 3], first_row=rank * RAYS_PER_FRAME,
+                                                 N_samples=S, white_bg=True, image_width=W, iteration=30001))
+            if len(pend) > 2:
+                sharded.comm.wait(pend.pop(0))
+        def e2e_drain():
+            while pend:
+                sharded.comm.wait(pend.pop(0))
+        e2e_api = ("ngf_field_render_sharded_host_async per batch (C ABI: pinned H2D of the rank's rays, render, peer-memory "
+                   "all-gather, D2H of one gathered frame per rank; 3 batches in flight)")
     else:
-        # pinned shard of the batch -> H2D (copy stream) -> render + overlapped all-gather -> D2H of one shard's worth of
-        # the gathered batch (download stream); the host trails the device by one step
         copy_s = torch.cuda.Stream(device=dev)
         stage = [torch.empty_like(dev_rays[0]) for _ in range(2)]
         res_h = [torch.empty((n_local, 4)).pin_memory() for _ in range(2)]
         up, free = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]
-        pend = []
         def step_e2e(i):
             b = i % 2
             cur = torch.cuda.current_stream(dev)
@@ -295,7 +368,8 @@ def main():
         def e2e_drain():
             while pend:
                 pend.pop(0).synchronize()
-        d2h = n_local * 16
+        e2e_api = "pinned H2D + ngf_field_render + torch.distributed NCCL all-gather + D2H, host one step behind"
+    d2h = n_local * 16
     for i in range(3):
         step_e2e(i)
     e2e_drain()
@@ -308,6 +382,10 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = n_batch * args.steps / e2e_s
 
+    # ---- second end-to-end figure: what evaluation_path needs (TriPlane/main.py:155-161) — a camera pose in, the
+    # uint8 image out: rays generated on the device, uint8 conversion on the device, 1.92 MB D2H per frame
+    e2e_cam = camera_e2e(ngf_b200, synth, field, dev, args.steps) if world == 1 else None
+
     # ---- roofline of the dominant kernel, from CUDA events around each kernel of the pair (measured live above)
     pk = peaks()
     n_k = max(n_k, 1)
@@ -316,41 +394,57 @@ def main():
     nV = stats["samples_density"] / n_local
     nA = stats["samples_colour"] / n_local
     alg_bytes = n_local * HBM_BYTES_PER_RAY
-    traffic = None
+    tj = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(f"march_kernel_{args.field}_dram_bytes_per_launch")
-    achieved = alg_bytes / march_s / 1e9
+        tj = json.load(open(tp))
     mlp_flops = n_local * nA * MLP_FLOPS_PER_COLOUR_SAMPLE
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
-                "traffic": traffic, "kernel": "ngf_march_kernel<TriPlane>", "kernel_ms": march_s * 1e3,
-                "kernel_share_of_step": march_s / step_s,
-                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": pk["src"],
-                "note": "sparse regime: 40 B/ray of compulsory HBM traffic; the march is issue / L2-gather bound (DESIGN.md)",
-                "colour_kernel": {"kernel": "ngf_colour_kernel<TriPlane,tcgen05>", "kernel_ms": colour_s * 1e3,
-                                  "kernel_share_of_step": colour_s / step_s, "bound": "tensor",
-                                  "achieved": mlp_flops / colour_s / 1e12 if colour_s > 0 else None,
-                                  "peak": pk["tensor"], "unit": "TFLOP/s",
-                                  "frac": mlp_flops / colour_s / 1e12 / pk["tensor"] if colour_s > 0 else None},
-                "density_samples_per_ray": nV, "colour_samples_per_ray": nA,
-                "mlp_flop_roofline_frac_of_step": n_local * (nV * MLP_FLOPS_PER_DENSITY_SAMPLE + nA * MLP_FLOPS_PER_COLOUR_SAMPLE)
-                                                  / step_s / 1e12 / pk["tensor"]}
+    mlp_exec = n_local * nA * MLP_FLOPS_EXECUTED_PER_COLOUR_SAMPLE
+    k_march = {"bound": "hbm", "kernel": "ngf_march_kernel<TriPlane>", "achieved": alg_bytes / march_s / 1e9 if march_s > 0 else None,
+               "peak": pk["hbm"], "unit": "GB/s", "frac": alg_bytes / march_s / 1e9 / pk["hbm"] if march_s > 0 else None,
+               "traffic": tj.get(f"march_kernel_{args.field}_dram_bytes_per_launch"), "kernel_ms": march_s * 1e3,
+               "kernel_share_of_step": march_s / step_s, "algorithmic_bytes_per_launch": alg_bytes,
+               "note": "sparse regime: 40 B/ray of compulsory HBM traffic; the march is issue / L2-gather bound (DESIGN.md)"}
+    k_colour = {"bound": "tensor", "kernel": "ngf_colour_kernel<TriPlane,tcgen05>",
+                "achieved": mlp_flops / colour_s / 1e12 if colour_s > 0 else None, "peak": pk["tensor"], "unit": "TFLOP/s",
+                "frac": mlp_flops / colour_s / 1e12 / pk["tensor"] if colour_s > 0 else None,
+                "frac_executed": mlp_exec / colour_s / 1e12 / pk["tensor"] if colour_s > 0 else None,
+                "traffic": tj.get(f"colour_kernel_{args.field}_dram_bytes_per_launch"), "kernel_ms": colour_s * 1e3,
+                "kernel_share_of_step": colour_s / step_s, "algorithmic_flops_per_launch": mlp_flops,
+                "note": "frac counts the reference's arithmetic (70 400 FLOP per colour sample incl. the 144x144 basis); "
+                        "frac_executed what the kernel runs after folding the basis into layer 1 (K padded to 160)"}
+    dom, other = (k_colour, k_march) if colour_s >= march_s else (k_march, k_colour)
+    roofline = dict(dom)
+    roofline.update({"peak_source": pk["src"], "other_kernel": other,
+                     "density_samples_per_ray": nV, "colour_samples_per_ray": nA,
+                     "mlp_flop_roofline_frac_of_step": n_local * (nV * MLP_FLOPS_PER_DENSITY_SAMPLE + nA * MLP_FLOPS_PER_COLOUR_SAMPLE)
+                                                       / step_s / 1e12 / pk["tensor"]})
 
+    coll = "" if world == 1 else {"copy": "peer-memory all-gather on the copy engines (C ABI)",
+                                  "store": "peer-memory all-gather fused into the finalize kernel (C ABI)",
+                                  "nccl": "torch.distributed NCCL all-gather"}[comm_mode]
     line = {
         "metric": "rays/sec (800x800, 192 samples/ray)", "value": value, "unit": "rays/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"TriPlane {args.field} field, 800x800 rays x 192 samples/ray, gauge on, 256^3 alpha mask "
-                               f"(BASELINE configs[1]" + (")" if world == 1 else f"; configs[4]: {world} frames/step ray-sharded + NCCL all-gather)"),
+                               f"(BASELINE configs[1]" + (")" if world == 1 else f"; configs[4]: {world} frames/step ray-sharded + one all-gather of the rendered batch)"),
                    "rays_per_step": n_batch,
                    "arithmetic": "fp32 march / density / compositing; colour MLP fp16 operands with fp32 accumulation (tcgen05, TMEM)", "l2": f"inputs rotate over {N_POSES} poses ({N_POSES * n_local * 24 / 1e6:.0f} MB of rays per rank > 126 MB L2)",
-                   "parallelism": "single GPU" if world == 1 else f"ray-sharded dp{world}, {BLOCK}-ray interleaved blocks"},
+                   "parallelism": "single GPU" if world == 1 else f"ray-sharded dp{world}, {BLOCK}-ray interleaved blocks, {coll}"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_local * 24, "d2h_bytes_per_step": d2h,
-                "api": "ngf_b200.render_frames: ngf_field_render_host_async per frame (C ABI, pinned host buffers, 3 frames in flight)" if world == 1 else "pinned H2D + ngf_field_render + overlapped NCCL all-gather + D2H, host one step behind"},
+                "api": e2e_api},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": roofline,
     }
+    if e2e_cam is not None:
+        line["e2e_camera"] = e2e_cam
+    if parity is not None:
+        line["parity_ok"] = parity["parity_ok"]
+        line["parity"] = parity
+    if comm_note:
+        line["config"]["collective_note"] = comm_note
 
     # ---- dense regime side measurement (tensor-bound): every in-box sample is colour-active
     if world == 1 and not args.no_dense:
@@ -358,10 +452,11 @@ def main():
 
     # ---- the other single-GPU configurations of BASELINE.json, as side measurements
     if world == 1 and not args.no_extra:
-        line["other_configs"] = {"infoinv": infoinv_config(ngf_b200, synth, dev, pk, dev_rays),
-                                 "neutex": neutex_config(ngf_b200, synth, dev, pk)}
+        line["other_configs"] = {"infoinv": infoinv_config(ngf_b200, synth, dev, pk, dev_rays, host, args),
+                                 "neutex": neutex_config(ngf_b200, synth, dev, pk, args)}
 
-    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample of the same workload
+    # ---- baselines: the oracle port on this box's host cores and on this GPU through torch (the reference's normal
+    # device, TriPlane/main.py:18), bounded samples of the same workload
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import restate_field as R
         spec = R.spec_from_state("triplane", state, alpha_volume=occ, gauge_on=True, **kw)
@@ -370,12 +465,67 @@ def main():
         v, done, dt = cpu_port_rate(spec, R, sample, args.cpu_seconds, threads)
         line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
                                 "sample": f"first {done} rays of frames 0-1 (4096-ray chunks, torch CPU fp32, {threads} threads) in {dt:.1f} s"}
+        line["torch_cuda_baseline"] = torch_cuda_rate(R, spec, dev, host)
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        if sharded.comm is not None:
+            barrier()
+            sharded.comm.close()
         dist.destroy_process_group()
+
+
+def torch_cuda_rate(R, spec, dev, host):
+    """The reference's algorithm on its normal device: the oracle port (same torch ops, same order) with every tensor on
+    this GPU, one whole 640 000-ray frame in 4096-ray chunks as TriPlane/main.py:60-71 renders it (rays uploaded per chunk,
+    main.py:65).  One warm-up frame, one timed frame."""
+    gspec = R.spec_to_device(spec, dev)
+    def frame(i):
+        rays = host[i]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = []
+        for s0 in range(0, rays.shape[0], 4096):
+            out.append(R.render_chunk(gspec, rays[s0:s0 + 4096].to(dev, non_blocking=True), white_bg=True, N_samples=S))
+        rgb = torch.cat([o[0] for o in out]).cpu()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, rgb
+    frame(1)
+    dt, _ = frame(0)
+    return {"value": RAYS_PER_FRAME / dt, "unit": "rays/s", "kind": "port on torch-CUDA (eager PyTorch ops on the same B200)",
+            "sample": f"one whole frame, 4096-ray chunks, {dt * 1e3:.0f} ms", "torch": torch.__version__}
+
+
+def camera_e2e(ngf_b200, synth, field, dev, steps):
+    """evaluation_path's per-frame work (TriPlane/main.py:155-161,116): c2w -> rays -> render -> uint8 image, through
+    ngf_field_render_camera_u8_host_async: the pose travels as 18 numbers, rays are generated in the march kernel, the
+    uint8 conversion runs on the device and 1.92 MB come back per frame; 3 frames in flight."""
+    steps = max(10, min(steps, 1000))
+    poses = [synth.look_at_c2w(*synth.pose_angles(p)) for p in range(N_POSES)]
+    u8_h = [torch.empty((RAYS_PER_FRAME, 3), dtype=torch.uint8).pin_memory() for _ in range(3)]
+    pend = []
+    def step(i):
+        pend.append(field.render_camera_u8_host_async(poses[i % N_POSES], H, W, synth.FOCAL_800, u8_h[i % 3], white_bg=True,
+                                                      N_samples=S, iteration=30001))
+        if len(pend) > 2:
+            field.host_wait(pend.pop(0))
+    def drain():
+        while pend:
+            field.host_wait(pend.pop(0))
+    for i in range(3):
+        step(i)
+    drain()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    drain()
+    dt = time.perf_counter() - t0
+    return {"value": RAYS_PER_FRAME * steps / dt, "unit": "rays/s", "h2d_bytes_per_step": 18 * 4,
+            "d2h_bytes_per_step": RAYS_PER_FRAME * 3, "steps": steps,
+            "api": "ngf_field_render_camera_u8_host_async (C ABI): pose in, rays generated in the march kernel, uint8 image "
+                   "out, 3 frames in flight"}
 
 
 def dense_regime(ngf_b200, synth, dev, pk, dev_rays):
@@ -411,19 +561,20 @@ def dense_regime(ngf_b200, synth, dev, pk, dev_rays):
                                  "basis); executed counts what the kernel runs after folding the basis into layer 1"}}
 
 
-def infoinv_config(ngf_b200, synth, dev, pk, dev_rays):
+def infoinv_config(ngf_b200, synth, dev, pk, dev_rays, host, args):
     """BASELINE configs[2]: InfoInv (sinusoidal phase product, 72->32->32->1 density MLP, 216-wide colour input),
     800x800 rays x 192 samples, hull field + alpha mask."""
     kw = synth.field_kwargs("C2")
     f = ngf_b200.InfoInvTriPlane(kw["aabb"], kw["gridSize"], dev, near_far=kw["near_far"], step_ratio=kw["step_ratio"],
                                  distance_scale=kw["distance_scale"], rayMarch_weight_thres=kw["rayMarch_weight_thres"])
-    synth.load_into(f, synth.field_state("infoinv", "hull"), synth.occupancy_volume("hull"), ngf_b200.AlphaGridMask)
+    state, occ = synth.field_state("infoinv", "hull"), synth.occupancy_volume("hull")
+    synth.load_into(f, state, occ, ngf_b200.AlphaGridMask)
     n = dev_rays[0].shape[0]
     for i in range(3):
         f(dev_rays[i], white_bg=True, N_samples=S, infoinv=True, image_width=W)
     torch.cuda.synchronize()
     st = f.last_stats()
-    steps = 10
+    steps = 20
     f.kernel_timing(steps)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -433,19 +584,58 @@ def infoinv_config(ngf_b200, synth, dev, pk, dev_rays):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     n_k, m_ms, c_ms = f.kernel_timing_read()
+    f.kernel_timing(0)
     nV, nA = st["samples_density"] / n, st["samples_colour"] / n
     flops = n * (nV * 6720 + nA * 131456)                        # InfoInv MLP FLOPs per sample
-    return {"workload": "InfoInv hull field, 800x800 rays x 192 samples/ray, infoinv=True, 256^3 alpha mask (BASELINE configs[2])",
-            "rays_per_s": n / (ms * 1e-3), "ms_per_frame": ms, "march_kernel_ms": m_ms / n_k, "colour_kernel_ms": c_ms / n_k,
-            "density_samples_per_ray": nV, "colour_samples_per_ray": nA,
-            "mlp_flop_roofline_frac": flops / (ms * 1e-3) / 1e12 / pk["tensor"]}
+    # end to end through the C ABI's host-buffer call, 3 frames in flight
+    outs = [(torch.empty((n, 3)).pin_memory(), torch.empty((n,)).pin_memory()) for _ in range(3)]
+    pend = []
+    def step_e2e(i):
+        r, d = outs[i % 3]
+        pend.append(f.render_host_async(host[i % N_POSES], r, d, white_bg=True, N_samples=S, image_width=W, infoinv=True))
+        if len(pend) > 2:
+            f.host_wait(pend.pop(0))
+    for i in range(3):
+        step_e2e(i)
+    while pend:
+        f.host_wait(pend.pop(0))
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step_e2e(i)
+    while pend:
+        f.host_wait(pend.pop(0))
+    e2e_s = (time.perf_counter() - t0) / steps
+    march_s, colour_s = m_ms / n_k * 1e-3, c_ms / n_k * 1e-3
+    dom_is_march = march_s >= colour_s
+    res = {"workload": "InfoInv hull field, 800x800 rays x 192 samples/ray, infoinv=True, 256^3 alpha mask (BASELINE configs[2])",
+           "rays_per_s": n / (ms * 1e-3), "ms_per_frame": ms, "march_kernel_ms": m_ms / n_k, "colour_kernel_ms": c_ms / n_k,
+           "density_samples_per_ray": nV, "colour_samples_per_ray": nA,
+           "mlp_flop_roofline_frac": flops / (ms * 1e-3) / 1e12 / pk["tensor"],
+           "e2e": {"value": n / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n * 16,
+                   "api": "ngf_field_render_host_async, 3 frames in flight"},
+           "roofline": {"bound": "tensor", "kernel": "ngf_march_kernel<InfoInv>" if dom_is_march else "ngf_colour_kernel<InfoInv,tcgen05>",
+                        "achieved": (n * nV * 6720 / march_s if dom_is_march else n * nA * 131456 / colour_s) / 1e12,
+                        "peak": pk["tensor"], "unit": "TFLOP/s",
+                        "frac": (n * nV * 6720 / march_s if dom_is_march else n * nA * 131456 / colour_s) / 1e12 / pk["tensor"],
+                        "kernel_ms": (march_s if dom_is_march else colour_s) * 1e3,
+                        "note": "reference MLP arithmetic of the kernel with the larger share (density MLP 6 720 FLOP per valid "
+                                "sample in the march kernel, colour MLP 131 456 FLOP per active sample in the colour kernel)"}}
+    if not args.no_cpu_baseline:
+        from oracle import restate_field as R
+        spec = R.spec_from_state("infoinv", state, alpha_volume=occ, infoinv=True, **kw)
+        threads = os.cpu_count() or 1
+        v, done, dt = cpu_port_rate(spec, R, host[0], min(args.cpu_seconds, 6.0), threads)
+        res["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
+                               "sample": f"first {done} rays of frame 0 (4096-ray chunks, torch CPU fp32) in {dt:.1f} s"}
+    return res
 
 
-def neutex_config(ngf_b200, synth, dev, pk):
+def neutex_config(ngf_b200, synth, dev, pk, args):
     """BASELINE configs[3]: UV-Mapping NeuTex render, 600x800 rays x 64 samples, random-init networks of the reference's
     shapes, synthetic DTU-like camera, explicit jitter noise."""
     m = ngf_b200.NeuTex(device=dev)
-    m.load_state_dict(synth.neutex_state(0))
+    nstate = synth.neutex_state(0)
+    m.load_state_dict(nstate)
     campos, raydir = synth.neutex_camera(0)
     R = raydir.shape[1]
     noise = synth.neutex_noise(R)
@@ -466,14 +656,33 @@ def neutex_config(ngf_b200, synth, dev, pk):
     t0 = time.perf_counter()
     m.render_host(campos, h_rd, bg, h_nz)
     e2e_s = time.perf_counter() - t0
-    return {"workload": "UV-Mapping NeuTex, 600x800 rays x 64 samples/ray, square primitive, jitter 0.05 (BASELINE configs[3])",
-            "rays_per_s": R / (total_ms * 1e-3), "ms_per_frame": total_ms, "raygen_ms": a_ms / k, "mlp_kernel_ms": b_ms / k,
-            "march_ms": c_ms / k, "in_cube_samples_per_ray": nv / R,
-            "e2e_rays_per_s": R / e2e_s, "e2e_h2d_bytes": R * (3 + 64) * 4, "e2e_d2h_bytes": R * 16,
-            "roofline": {"bound": "tensor", "kernel": "ntx_mlp_kernel", "achieved": nv * per_sample / (b_ms / k * 1e-3) / 1e12,
-                         "peak": pk["tensor"], "unit": "TFLOP/s", "frac": nv * per_sample / (b_ms / k * 1e-3) / 1e12 / pk["tensor"],
-                         "note": "reference arithmetic (2.66 MFLOP) of the in-cube samples only; the reference itself pushes all "
-                                 "64 samples/ray through the MLPs"}}
+    res = {"workload": "UV-Mapping NeuTex, 600x800 rays x 64 samples/ray, square primitive, jitter 0.05 (BASELINE configs[3])",
+           "rays_per_s": R / (total_ms * 1e-3), "ms_per_frame": total_ms, "raygen_ms": a_ms / k, "mlp_kernel_ms": b_ms / k,
+           "march_ms": c_ms / k, "in_cube_samples_per_ray": nv / R,
+           "e2e": {"value": R / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": R * (3 + 64) * 4, "d2h_bytes_per_step": R * 16,
+                   "api": "ngf_neutex_render_host"},
+           "roofline": {"bound": "tensor", "kernel": "ntx_mlp_kernel", "achieved": nv * per_sample / (b_ms / k * 1e-3) / 1e12,
+                        "peak": pk["tensor"], "unit": "TFLOP/s", "frac": nv * per_sample / (b_ms / k * 1e-3) / 1e12 / pk["tensor"],
+                        "kernel_ms": b_ms / k,
+                        "note": "reference arithmetic (2.66 MFLOP) of the in-cube samples only; the reference itself pushes all "
+                                "64 samples/ray through the MLPs"}}
+    if not args.no_cpu_baseline:
+        from oracle import restate_neutex as RN
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        spec = RN.NeuTexSpec(state=nstate)
+        n_s = 4096
+        try:
+            sel = slice(R // 2, R // 2 + n_s)              # rows through the image centre: rays that cross the cube
+            RN.render(spec, campos, raydir[:, :1024], bg, noise[:, :1024])
+            t0 = time.perf_counter()
+            RN.render(spec, campos, raydir[:, sel], bg, noise[:, sel])
+            dt = time.perf_counter() - t0
+            res["cpu_baseline"] = {"value": n_s / dt, "unit": "rays/s", "cores": threads, "kind": "port",
+                                   "sample": f"{n_s} rays from the image centre (1024-ray chunks, torch CPU fp32) in {dt:.1f} s"}
+        except Exception as e:                      # the baseline is a report, never a reason to lose the bench line
+            res["cpu_baseline"] = {"unavailable": repr(e)[:200]}
+    return res
 
 
 if __name__ == "__main__":

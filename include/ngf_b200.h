@@ -36,7 +36,8 @@ typedef enum NgfStatus {
   NGF_EINVAL = -1,       /* bad shape / stride / null pointer / alignment */
   NGF_ECUDA = -2,        /* CUDA runtime error; text in ngf_last_error()   */
   NGF_EUNSUPPORTED = -3, /* configuration outside what the kernels are built for */
-  NGF_ENOMEM = -4
+  NGF_ENOMEM = -4,
+  NGF_ECOMM = -5         /* a peer rank did not answer in time (multi-GPU frame exchange) */
 } NgfStatus;
 
 typedef enum NgfVariant {
@@ -203,6 +204,12 @@ int ngf_field_render_camera(NgfField f, const NgfCamera* camera, int32_t n_sampl
 int ngf_field_render_camera_host_async(NgfField f, const NgfCamera* camera, int32_t n_samples, int32_t white_bg,
                                        float* rgb_host, float* depth_host, int32_t mlp_impl, uint64_t* ticket);
 
+/* evaluation_path's whole per-frame job (TriPlane/main.py:155-161 + the uint8 conversion of main.py:116): camera in,
+ * rgb_map as uint8 [H*W][3] out (value = (uint8)(rgb * 255), as numpy's astype truncates), depth_map fp32 optional
+ * (NULL: not downloaded).  1.92 MB leave the device per 800x800 frame instead of 10.24 MB. */
+int ngf_field_render_camera_u8_host_async(NgfField f, const NgfCamera* camera, int32_t n_samples, int32_t white_bg,
+                                          uint8_t* u8_host, float* depth_host, int32_t mlp_impl, uint64_t* ticket);
+
 /* Per-call switches of forward(): TriPlane `iteration >= gauge_start` (TriPlane/models/Field.py:58) and InfoInv
  * `infoinv=` (InfoInv/models/FieldBase.py:228).  They only flip a flag in the handle; no repack. */
 int ngf_field_set_gauge(NgfField f, int32_t on);
@@ -270,6 +277,60 @@ int ngf_shard_gather(const float* src_dev, int64_t n_rays, int32_t width, int32_
                      int32_t world, float* dst_dev, void* stream);
 int ngf_shard_scatter(const float* src_dev, int64_t n_rays, int32_t width, int32_t block, int32_t world,
                       int64_t max_shard, float* dst_dev, void* stream);
+
+/*
+ * Ray-sharded multi-GPU frames with the frame all-gather inside the library ("ngf_comm_init /
+ * ngf_frame_allgather").  The reference has nothing here — its only multi-GPU code is the vestigial
+ * nn.DataParallel(NeuTex) at UV-Mapping/model/model.py:285 — so the contract is the survey's: one process per GPU, rays
+ * of a batch dealt to ranks in interleaved `block`-ray blocks (ngf_shard_count), every rank renders its blocks, ONE
+ * all-gather per batch leaves the whole [n_rays][4] fp32 (r, g, b, depth) batch in frame order on every rank.
+ *
+ * The exchange runs over NVLink peer mappings of the ranks' frame buffers (CUDA IPC), not through a NCCL kernel:
+ *   NGF_COMM_COPY   the render's last kernel writes the rank's rows in frame order; one strided copy per peer on the
+ *                   copy engines lands them in every peer's buffer (no SM is used by the collective);
+ *   NGF_COMM_STORE  the render's last kernel stores each finished row into every rank's buffer itself (the all-gather
+ *                   is the epilogue of the render).
+ * Completion / back-pressure are device-side step counters polled by one-CTA kernels; the host never blocks.
+ *
+ *   ngf_comm_init     allocate this rank's `n_slots` (2..4) frame buffers + flags on `device`.
+ *   ngf_comm_export   write ngf_comm_handle_bytes() opaque bytes to hand to every other rank (any transport:
+ *                     torch.distributed all_gather, MPI, a file).
+ *   ngf_comm_connect  blobs = the world's exported bytes, rank-major; maps the peers' buffers.  Needs peer access
+ *                     between the devices (NGF_EUNSUPPORTED otherwise).
+ *   ngf_field_render_sharded
+ *                     render this rank's rays (local order = its blocks, in order; n_local == ngf_comm_local_rays) of
+ *                     the next batch on `stream` and start the exchange; returns a ticket.  At most n_slots batches may
+ *                     be unreleased.
+ *   ngf_frame_allgather
+ *                     make `stream` wait until every rank's rows of `ticket` have landed; *frame_dev is then the whole
+ *                     batch [n_rays][4] in frame order on this rank (valid until ngf_frame_release + n_slots - 1 more
+ *                     batches).
+ *   ngf_frame_release the consumer on `stream` is done with the buffer: peers may overwrite it.
+ *   ngf_field_render_sharded_host_async
+ *                     the same through HOST buffers, pipelined over internal streams like ngf_field_render_host_async:
+ *                     H2D of the rank's rays, render, exchange, D2H of rows [first_row, first_row + n_rows) of the
+ *                     gathered batch into frame_host [n_rows][4]; the buffer is released internally.  Wait with
+ *                     ngf_comm_wait(ticket); NGF_ECOMM if a peer never answered (NGF_COMM_TIMEOUT_S, default 10 s).
+ */
+typedef enum NgfCommMode { NGF_COMM_COPY = 0, NGF_COMM_STORE = 1 } NgfCommMode;
+typedef struct NgfComm_* NgfComm;
+int ngf_comm_init(int32_t rank, int32_t world, int32_t device, int64_t n_rays, int32_t block, int32_t n_slots,
+                  int32_t mode, NgfComm* out);
+int64_t ngf_comm_handle_bytes(void);
+int ngf_comm_export(NgfComm c, void* blob);
+int ngf_comm_connect(NgfComm c, const void* blobs);
+void ngf_comm_free(NgfComm c);
+int64_t ngf_comm_local_rays(NgfComm c);
+int ngf_field_render_sharded(NgfField f, NgfComm c, const float* rays_local_dev, int64_t n_local, int32_t ray_stride,
+                             int32_t n_samples, int32_t white_bg, int32_t tile_w, int32_t mlp_impl, void* stream,
+                             uint64_t* ticket);
+int ngf_frame_allgather(NgfComm c, uint64_t ticket, void* stream, const float** frame_dev);
+int ngf_frame_release(NgfComm c, uint64_t ticket, void* stream);
+int ngf_field_render_sharded_host_async(NgfField f, NgfComm c, const float* rays_local_host, int64_t n_local,
+                                        int32_t ray_stride, int32_t n_samples, int32_t white_bg, int32_t tile_w,
+                                        int32_t mlp_impl, float* frame_host, int64_t first_row, int64_t n_rows,
+                                        uint64_t* ticket);
+int ngf_comm_wait(NgfComm c, uint64_t ticket);
 
 /* =====================================================================================================
  * UV-Mapping (NeuTex) render path.  Reference (paths relative to /root/reference/UV-Mapping):

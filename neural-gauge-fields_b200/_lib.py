@@ -11,7 +11,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libngf_b200.so")
 
-NGF_OK, NGF_EINVAL, NGF_ECUDA, NGF_EUNSUPPORTED, NGF_ENOMEM = 0, -1, -2, -3, -4
+NGF_OK, NGF_EINVAL, NGF_ECUDA, NGF_EUNSUPPORTED, NGF_ENOMEM, NGF_ECOMM = 0, -1, -2, -3, -4, -5
+COMM_COPY, COMM_STORE = 0, 1
 NGF_TRIPLANE, NGF_INFOINV = 0, 1
 MLP_TCGEN05, MLP_SIMT = 0, 1
 
@@ -77,6 +78,8 @@ SIGNATURES = {
                                           C.c_void_p, C.c_int32, C.c_void_p]),
     "ngf_field_render_camera_host_async": (C.c_int, [C.c_void_p, C.POINTER(NgfCamera), C.c_int32, C.c_int32, C.c_void_p,
                                                      C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]),
+    "ngf_field_render_camera_u8_host_async": (C.c_int, [C.c_void_p, C.POINTER(NgfCamera), C.c_int32, C.c_int32, C.c_void_p,
+                                                        C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]),
     "ngf_field_host_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
     "ngf_field_set_gauge": (C.c_int, [C.c_void_p, C.c_int32]),
     "ngf_field_set_infoinv": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -114,6 +117,21 @@ SIGNATURES = {
                                    C.c_void_p]),
     "ngf_shard_scatter": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
                                     C.c_void_p]),
+    "ngf_comm_init": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                C.POINTER(C.c_void_p)]),
+    "ngf_comm_handle_bytes": (C.c_int64, []),
+    "ngf_comm_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ngf_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ngf_comm_free": (None, [C.c_void_p]),
+    "ngf_comm_local_rays": (C.c_int64, [C.c_void_p]),
+    "ngf_field_render_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "ngf_frame_allgather": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ngf_frame_release": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "ngf_field_render_sharded_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                                      C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
+                                                      C.POINTER(C.c_uint64)]),
+    "ngf_comm_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
 }
 
 _lib = None
@@ -147,7 +165,7 @@ def last_error() -> str:
 def check(rc: int, what: str = "") -> None:
     if rc != NGF_OK:
         name = {NGF_EINVAL: "NGF_EINVAL", NGF_ECUDA: "NGF_ECUDA", NGF_EUNSUPPORTED: "NGF_EUNSUPPORTED",
-                NGF_ENOMEM: "NGF_ENOMEM"}.get(rc, str(rc))
+                NGF_ENOMEM: "NGF_ENOMEM", NGF_ECOMM: "NGF_ECOMM"}.get(rc, str(rc))
         raise RuntimeError(f"{what or 'libngf_b200'} failed with {name}: {last_error()}")
 
 

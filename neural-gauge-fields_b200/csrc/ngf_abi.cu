@@ -9,8 +9,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../../include/ngf_b200.h"
-#include "ngf_internal.h"
+#include "ngf_handle.h"
 
 using namespace ngf;
 
@@ -56,72 +55,6 @@ struct DeviceGuard {
   }
 };
 
-// ---------------------------------------------------------------------------------------------------------
-// handle
-// ---------------------------------------------------------------------------------------------------------
-struct HostChunk {            // one in-flight chunk of the host-buffer render path
-  cudaStream_t stream = nullptr;      // compute stream (slots 0..kHostComp-1 own one; the others borrow slot % kHostComp)
-  cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;   // upload done | kernels done | download done
-  float* rays = nullptr;
-  float* rgb = nullptr;
-  float* depth = nullptr;
-  float* acc = nullptr;
-  unsigned int* counters = nullptr;
-  QEntry* queue = nullptr;
-  long long queue_cap = 0;
-};
-
-struct NgfField_ {
-  int device = 0;
-  int num_sms = 0;
-  int has_gauge = 0;
-  FieldDev dev{};
-  int n_samples_default = 0;
-  int plane_c = 0;
-  // owned device memory
-  float* dens[3] = {nullptr, nullptr, nullptr};
-  __half* app[3] = {nullptr, nullptr, nullptr};
-  float2* gauge[3] = {nullptr, nullptr, nullptr};
-  uint32_t* occ = nullptr;
-  uint32_t* occ2 = nullptr;
-  uint32_t* occ_coarse = nullptr;
-  float* dsum[3] = {nullptr, nullptr, nullptr};
-  float* dmlp = nullptr;
-  __half* w1p = nullptr;
-  __half* w2p = nullptr;
-  float* tail = nullptr;
-  // render workspace
-  float* acc_ws = nullptr;
-  long long acc_cap = 0;
-  unsigned int* counters = nullptr;   // [0] tile counter, [1] queue count, [2..9] = 4 x u64 stats
-  QEntry* queue = nullptr;            // colour work items of the device-resident path
-  long long queue_cap = 0;
-  // kernel timing (ngf_field_timing_*)
-  std::vector<cudaEvent_t> ev;        // 3 per timed march+colour pair
-  int ev_used = 0;
-  // host path: kHostSlots chunks in flight, each on its own stream; whole-frame pipelines are replayed as CUDA graphs
-  HostChunk chunk[6];
-  cudaStream_t s_in = nullptr, s_out = nullptr;       // dedicated upload / download streams
-  int next_slot = 0;                                  // round robin over the chunk slots, across frames
-  long long chunk_cap = 0;
-  int chunk_stride = 0;
-  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
-  struct HostGraph {
-    const void *rays, *rgb, *depth;
-    long long n_rays;
-    int stride, n_samples, white_bg, tile_w, impl;
-    unsigned long long epoch;
-    cudaGraphExec_t exec;            // nullptr: capture failed once, stay eager for this key
-  };
-  std::vector<HostGraph> graphs;
-  unsigned long long epoch = 0;       // bumped whenever anything a captured kernel argument depends on changes
-  cudaEvent_t frame_done[8] = {};     // completion of the last 8 asynchronous host frames (ticket % 8)
-  unsigned long long next_ticket = 1;
-};
-static const int kHostSlots = 6;    // chunk buffers in flight
-static const int kHostComp = 3;     // compute streams
-
-static const int kCounterBytes = 64;
 
 static void drop_graphs(NgfField_* h) {
   for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -139,7 +72,7 @@ static void free_chunks(NgfField_* h) {
     if (c.ev_in) cudaEventDestroy(c.ev_in);
     if (c.ev_comp) cudaEventDestroy(c.ev_comp);
     if (c.ev_out) cudaEventDestroy(c.ev_out);
-    cudaFree(c.rays); cudaFree(c.rgb); cudaFree(c.depth); cudaFree(c.acc); cudaFree(c.counters); cudaFree(c.queue);
+    cudaFree(c.rays); cudaFree(c.rgb); cudaFree(c.depth); cudaFree(c.acc); cudaFree(c.u8); cudaFree(c.counters); cudaFree(c.queue);
     c = HostChunk{};
   }
   if (h->s_in) { cudaStreamDestroy(h->s_in); h->s_in = nullptr; }
@@ -252,6 +185,9 @@ static int pack_params(NgfField_* h, const NgfFieldDesc* d, bool allocate) {
   }
   f.step = d->step_size; f.near_t = d->near_t; f.far_t = d->far_t;
   f.dscale = d->distance_scale; f.wthres = d->weight_thres; f.dshift = d->density_shift;
+  // early-out of the march: once T <= tstop every later weight is <= tstop <= weight_thres, so no later sample can be
+  // colour-active and acc / depth lose at most tstop; a threshold <= 0 keeps every sample, as the reference does
+  f.tstop = d->weight_thres >= 1e-6f ? 1e-6f : (d->weight_thres > 0.f ? d->weight_thres : 0.f);
   h->n_samples_default = d->n_samples;
   h->plane_c = C;
 
@@ -506,10 +442,12 @@ static int ensure_queue(QEntry** q, long long* cap, long long want, cudaStream_t
   return NGF_OK;
 }
 
-static int render_dev(NgfField h, const float* rays, long long n_rays, int ray_stride, int n_samples, int white_bg,
-                      int tile_w, float* rgb, float* depth, float* acc, unsigned int* counters, QEntry** queue,
-                      long long* queue_cap, int mlp_impl, cudaStream_t st, const CamDev* cam = nullptr,
-                      const float* jitter = nullptr) {
+}  // extern "C"
+
+int ngf_render_dev(NgfField h, const float* rays, long long n_rays, int ray_stride, int n_samples, int white_bg,
+                   int tile_w, float* rgb, float* depth, float* acc, unsigned int* counters, QEntry** queue,
+                   long long* queue_cap, int mlp_impl, cudaStream_t st, const CamDev* cam, const float* jitter,
+                   const ShardOut* shard) {
   if (n_rays == 0) return NGF_OK;
   const int S = n_samples > 0 ? n_samples : h->n_samples_default;
   if (S < 1) return fail(NGF_EINVAL, "n_samples resolves to %d", S);
@@ -557,9 +495,12 @@ static int render_dev(NgfField h, const float* rays, long long n_rays, int ray_s
       h->ev_used += 3;
     }
   }
-  CU(launch_finalize(rgb, acc, n_rays, white_bg ? 1 : 0, st));
+  if (shard) CU(launch_finalize_shard(rgb, acc, depth, n_rays, white_bg ? 1 : 0, *shard, st));
+  else CU(launch_finalize(rgb, acc, n_rays, white_bg ? 1 : 0, st));
   return NGF_OK;
 }
+
+extern "C" {
 
 static int field_render(NgfField h, const float* rays_dev, int64_t n_rays, int32_t ray_stride, int32_t n_samples,
                         int32_t white_bg, int32_t tile_w, const float* jitter_dev, float* rgb_dev, float* depth_dev,
@@ -584,7 +525,7 @@ static int field_render(NgfField h, const float* rays_dev, int64_t n_rays, int32
     }
     acc = h->acc_ws;
   }
-  return render_dev(h, rays_dev, n_rays, ray_stride, n_samples, white_bg, tile_w, rgb_dev, depth_dev, acc,
+  return ngf_render_dev(h, rays_dev, n_rays, ray_stride, n_samples, white_bg, tile_w, rgb_dev, depth_dev, acc,
                     h->counters, &h->queue, &h->queue_cap, mlp_impl, st, nullptr, jitter_dev);
 }
 
@@ -609,7 +550,7 @@ int ngf_field_render_jitter(NgfField h, const float* rays_dev, int64_t n_rays, i
 // stream capture).
 static int host_enqueue(NgfField h, const float* rays_host, long long n_rays, int ray_stride, int n_samples, int white_bg,
                         int tile_w, float* rgb_host, float* depth_host, int mlp_impl, long long chunk, bool img,
-                        bool join, const CamDev* cam = nullptr) {
+                        bool join, const CamDev* cam = nullptr, uint8_t* u8_host = nullptr) {
   CU(cudaEventRecord(h->ev_fork, h->s_in));
   CU(cudaStreamWaitEvent(h->s_out, h->ev_fork, 0));
   for (int i = 0; i < kHostComp; ++i) CU(cudaStreamWaitEvent(h->chunk[i].stream, h->ev_fork, 0));
@@ -628,14 +569,16 @@ static int host_enqueue(NgfField h, const float* rays_host, long long n_rays, in
     CU(cudaStreamWaitEvent(c.stream, c.ev_out, 0));      // ... and the slot's result buffers must have been downloaded
     CamDev cam_chunk{};
     if (cam) { cam_chunk = *cam; cam_chunk.base = s; }
-    int rc = render_dev(h, cam ? nullptr : c.rays, n, ray_stride, n_samples, white_bg, img ? tile_w : 0, c.rgb, c.depth,
+    int rc = ngf_render_dev(h, cam ? nullptr : c.rays, n, ray_stride, n_samples, white_bg, img ? tile_w : 0, c.rgb, c.depth,
                         c.acc, c.counters, &c.queue, &c.queue_cap, mlp_impl, c.stream, cam ? &cam_chunk : nullptr);
     if (rc) return rc;
+    if (u8_host) CU(launch_frame_post(c.rgb, nullptr, n * 3, c.u8, nullptr, h->num_sms, c.stream));   // main.py:116
     CU(cudaEventRecord(c.ev_comp, c.stream));
     // download
     CU(cudaStreamWaitEvent(h->s_out, c.ev_comp, 0));
-    CU(cudaMemcpyAsync(rgb_host + s * 3, c.rgb, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
-    CU(cudaMemcpyAsync(depth_host + s, c.depth, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+    if (u8_host) CU(cudaMemcpyAsync(u8_host + s * 3, c.u8, (size_t)n * 3, cudaMemcpyDeviceToHost, h->s_out));
+    if (rgb_host) CU(cudaMemcpyAsync(rgb_host + s * 3, c.rgb, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+    if (depth_host) CU(cudaMemcpyAsync(depth_host + s, c.depth, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
     CU(cudaEventRecord(c.ev_out, h->s_out));
   }
   h->next_slot = ci;
@@ -653,9 +596,9 @@ static int host_enqueue(NgfField h, const float* rays_host, long long n_rays, in
 // Validate, pick the chunk size and make sure the slot buffers exist.
 static int host_prepare(NgfField h, const float* rays_host, int64_t n_rays, int32_t ray_stride, int32_t tile_w,
                         float* rgb_host, float* depth_host, int32_t mlp_impl, bool pipelined, long long* chunk_out,
-                        bool* img_out, bool camera = false) {
+                        bool* img_out, bool camera = false, bool u8_only = false) {
   if (n_rays < 0 || n_rays > 0x7fffffffll) return fail(NGF_EINVAL, "n_rays=%lld", (long long)n_rays);
-  if ((!rays_host && !camera) || !rgb_host || !depth_host) return fail(NGF_EINVAL, "NULL ray/output pointer");
+  if ((!rays_host && !camera) || ((!rgb_host || !depth_host) && !u8_only)) return fail(NGF_EINVAL, "NULL ray/output pointer");
   if (ray_stride < 6) return fail(NGF_EINVAL, "ray_stride=%d (< 6)", ray_stride);
   if (mlp_impl != NGF_MLP_TCGEN05 && mlp_impl != NGF_MLP_SIMT) return fail(NGF_EINVAL, "mlp_impl=%d", mlp_impl);
   // Chunking (whole groups of 4 image rows when the image width is known).  A single synchronous frame overlaps its own
@@ -696,6 +639,7 @@ static int host_prepare(NgfField h, const float* rays_host, int64_t n_rays, int3
       CU(dev_alloc(&c.rgb, (size_t)chunk * 3));
       CU(dev_alloc(&c.depth, (size_t)chunk));
       CU(dev_alloc(&c.acc, (size_t)chunk));
+      CU(dev_alloc(&c.u8, (size_t)chunk * 3));
       CU(cudaMalloc(reinterpret_cast<void**>(&c.counters), kCounterBytes));
     }
     h->chunk_cap = chunk;
@@ -821,7 +765,7 @@ int ngf_field_render_camera(NgfField h, const NgfCamera* camera, int32_t n_sampl
     }
     acc = h->acc_ws;
   }
-  return render_dev(h, nullptr, n_rays, 6, n_samples, white_bg, cam.W, rgb_dev, depth_dev, acc, h->counters, &h->queue,
+  return ngf_render_dev(h, nullptr, n_rays, 6, n_samples, white_bg, cam.W, rgb_dev, depth_dev, acc, h->counters, &h->queue,
                     &h->queue_cap, mlp_impl, st, &cam);
 }
 
@@ -842,6 +786,31 @@ int ngf_field_render_camera_host_async(NgfField h, const NgfCamera* camera, int3
   cudaEvent_t done = h->frame_done[t % 8];
   CU(cudaEventSynchronize(done));
   rc = host_enqueue(h, nullptr, n_rays, 6, n_samples, white_bg, cam.W, rgb_host, depth_host, mlp_impl, chunk, img, false, &cam);
+  if (rc) return rc;
+  CU(cudaEventRecord(done, h->s_out));
+  *ticket = t;
+  ++h->next_ticket;
+  return NGF_OK;
+}
+
+int ngf_field_render_camera_u8_host_async(NgfField h, const NgfCamera* camera, int32_t n_samples, int32_t white_bg,
+                                          uint8_t* u8_host, float* depth_host, int32_t mlp_impl, uint64_t* ticket) {
+  if (!h || !ticket || !u8_host) return fail(NGF_EINVAL, "NULL argument");
+  CamDev cam{};
+  int rc = check_camera(camera, &cam);
+  if (rc) return rc;
+  DeviceGuard g(h->device);
+  if (!g.ok) return fail(NGF_ECUDA, "cannot select device %d", h->device);
+  const long long n_rays = (long long)cam.W * cam.H;
+  long long chunk = 0;
+  bool img = false;
+  rc = host_prepare(h, nullptr, n_rays, 6, cam.W, nullptr, depth_host, mlp_impl, true, &chunk, &img, true, true);
+  if (rc) return rc;
+  const unsigned long long t = h->next_ticket;
+  cudaEvent_t done = h->frame_done[t % 8];
+  CU(cudaEventSynchronize(done));
+  rc = host_enqueue(h, nullptr, n_rays, 6, n_samples, white_bg, cam.W, nullptr, depth_host, mlp_impl, chunk, img, false, &cam,
+                    u8_host);
   if (rc) return rc;
   CU(cudaEventRecord(done, h->s_out));
   *ticket = t;

@@ -44,6 +44,7 @@ struct FieldDev {
   int infoinv;
   float lo[3], hi[3], inv[3];
   float step, near_t, far_t, dscale, wthres, dshift;
+  float tstop;                    // the march stops once T <= tstop: min(1e-6, wthres), 0 (never) when wthres <= 0
   // occupancy ("alpha mask"): raw bit grid + derived acceleration grids (built by ngf_field_pack)
   const uint32_t* occ;            // raw volume bits, bit (z*H + y)*W + x
   const uint32_t* occ2;           // "any of the 8 cell corners set" grid over cells x0 in [-1, W-1] (index x0+1),

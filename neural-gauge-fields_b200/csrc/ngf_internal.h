@@ -88,5 +88,6 @@ cudaError_t launch_shard_scatter(const float* src, long long n_rays, int width, 
                                  long long max_shard, float* dst, cudaStream_t st);
 
 uint64_t launch_count();
+void count_launch();
 
 }  // namespace ngf

@@ -18,7 +18,7 @@
 #include <atomic>
 #include <cstdlib>
 
-#include "ngf_internal.h"
+#include "ngf_handle.h"
 #include "ngf_mlp.cuh"
 
 namespace ngf {
@@ -28,7 +28,6 @@ uint64_t launch_count() { return g_launches.load(); }
 void count_launch() { g_launches.fetch_add(1); }
 #define NGF_COUNT_LAUNCH() g_launches.fetch_add(1)
 
-constexpr float kTStop = 1e-6f;   // stop marching once transmittance <= kTStop: all later weights sum to <= 1e-6
 constexpr int kMarchThreads = 256;
 constexpr int kMarchWarps = kMarchThreads / 32;
 constexpr int kStage = 64;        // staged colour items per warp (flushed 32 at a time)
@@ -150,7 +149,7 @@ __global__ void __launch_bounds__(kMarchThreads, V == 0 ? 3 : 2) ngf_march_kerne
       acc += w;
       dep += w * t;
       push = w > f.wthres;
-      if (++i >= i_end || T <= kTStop) live = false;
+      if (++i >= i_end || T <= f.tstop) live = false;
     }
     const unsigned pm = __ballot_sync(FULL, push);
     if (pm) {
@@ -306,6 +305,35 @@ cudaError_t launch_march(const FieldDev& f, const RenderArgs& a, int num_sms, cu
 cudaError_t launch_colour(const FieldDev& f, const RenderArgs& a, int mlp_impl, int num_sms, cudaStream_t st) {
   if (f.variant == 0) return mlp_impl == 0 ? launch_colour_t<0, 0>(f, a, num_sms, st) : launch_colour_t<0, 1>(f, a, num_sms, st);
   return mlp_impl == 0 ? launch_colour_t<1, 0>(f, a, num_sms, st) : launch_colour_t<1, 1>(f, a, num_sms, st);
+}
+
+// Ray-sharded variant: local ray l of this rank is global ray ((l / block) * world + rank) * block + l % block;
+// its (r, g, b, depth) row goes, as one 16-byte store, to the same position of every destination frame buffer — this
+// rank's own and, in the fused mode, the peer-mapped buffers of the other ranks (st.global over NVLink: the all-gather
+// is the epilogue of the render).
+__global__ void ngf_finalize_shard_kernel(const float* __restrict__ rgb, const float* __restrict__ acc,
+                                          const float* __restrict__ depth, long long n_local, int white_bg,
+                                          const __grid_constant__ ShardOut so) {
+  for (long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x; l < n_local; l += (long long)gridDim.x * blockDim.x) {
+    const float bg = white_bg ? 1.f - acc[l] : 0.f;
+    float4 v;
+    v.x = fminf(fmaxf(rgb[l * 3 + 0] + bg, 0.f), 1.f);
+    v.y = fminf(fmaxf(rgb[l * 3 + 1] + bg, 0.f), 1.f);
+    v.z = fminf(fmaxf(rgb[l * 3 + 2] + bg, 0.f), 1.f);
+    v.w = depth[l];
+    const long long g = ((l / so.block) * so.world + so.rank) * so.block + l % so.block;
+    for (int d = 0; d < so.n_dst; ++d) so.dst[d][g] = v;
+  }
+}
+
+cudaError_t launch_finalize_shard(const float* rgb, const float* acc, const float* depth, long long n_local,
+                                  int white_bg, const ShardOut& so, cudaStream_t st) {
+  if (n_local <= 0) return cudaSuccess;
+  long long blocks = (n_local + 255) / 256;
+  if (so.n_dst > 1 && blocks > 592) blocks = 592;        // remote stores only need enough warps to keep the links busy
+  ngf_finalize_shard_kernel<<<(unsigned)blocks, 256, 0, st>>>(rgb, acc, depth, n_local, white_bg, so);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
 }
 
 cudaError_t launch_finalize(float* rgb, const float* acc, long long n_rays, int white_bg, cudaStream_t st) {

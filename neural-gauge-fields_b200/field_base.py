@@ -383,6 +383,25 @@ class Base(torch.nn.Module):
                                                           C.byref(ticket)), "ngf_field_render_camera_host_async")
         return int(ticket.value)
 
+    @torch.no_grad()
+    def render_camera_u8_host_async(self, c2w, H, W, focal, u8_host, depth_host=None, center=None, white_bg=True,
+                                    N_samples=-1, **fwd_kw):
+        """evaluation_path's per-frame job (TriPlane/main.py:155-161,116): pose in, uint8 image [H*W,3] (pinned CPU
+        tensor) out, depth optional; pipelined across frames; returns a ticket for host_wait."""
+        h = self._ensure_handle()
+        lib = _lib.load()
+        self._set_switches(lib, h, **fwd_kw)
+        if u8_host.dtype != torch.uint8 or u8_host.device.type != "cpu" or not u8_host.is_contiguous():
+            raise ValueError("u8_host must be a contiguous uint8 CPU tensor")
+        cam = self._camera(c2w, H, W, focal, center)
+        ticket = C.c_uint64()
+        _lib.check(lib.ngf_field_render_camera_u8_host_async(h, C.byref(cam), int(N_samples), int(bool(white_bg)),
+                                                             u8_host.data_ptr(),
+                                                             None if depth_host is None else depth_host.data_ptr(),
+                                                             self._mlp_impl, C.byref(ticket)),
+                   "ngf_field_render_camera_u8_host_async")
+        return int(ticket.value)
+
     def host_wait(self, ticket: int):
         _lib.check(_lib.load().ngf_field_host_wait(self._ensure_handle(), int(ticket)), "ngf_field_host_wait")
 

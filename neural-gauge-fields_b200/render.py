@@ -151,25 +151,152 @@ def render_frame_sharded(rays, field, block=2048, N_samples=-1, white_bg=True, g
     return frame_allgather(local, R, block, group)
 
 
-class ShardedFrameRenderer:
-    """Ray-sharded multi-GPU rendering with the frame all-gather overlapped with the next frame's kernels.
+class _DevView:
+    """A [rows, cols] fp32 device array owned by the library, exposed through __cuda_array_interface__."""
 
-    Every rank renders its interleaved shard of a ray batch; the all-gather of the [rays, 4] (rgb, depth)
-    results and the re-ordering into frame order run on a side stream, double-buffered, so the collective of batch k
-    overlaps the march / colour kernels of batch k+1.  One NCCL all-gather per batch, no other collective.
+    def __init__(self, ptr: int, rows: int, cols: int):
+        self.__cuda_array_interface__ = {"shape": (rows, cols), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class FrameComm:
+    """Ray-sharded frames with the all-gather inside the C ABI (ngf_comm_* / ngf_field_render_sharded /
+    ngf_frame_allgather, include/ngf_b200.h): every rank renders its interleaved ``block``-ray blocks
+    of a ``n_rays_total``-ray batch straight into frame order, and the rows travel to the other ranks over NVLink peer
+    mappings — ``mode="copy"``: one strided copy per peer on the copy engines (no SM); ``mode="store"``: stored by the
+    render's last kernel itself.  torch.distributed is used once, to exchange the 128-byte buffer handles.
+
+        comm = FrameComm(field, n_rays_total, block)               # collective: every rank of `group` calls it
+        t = comm.submit(my_rays_dev, N_samples=192, image_width=800)
+        frame = comm.result(t)                                     # [n_rays_total, 4] (r, g, b, depth), stream-ordered
+        ...; comm.release(t)                                       # peers may overwrite the buffer
+    """
+
+    def __init__(self, field, n_rays_total: int, block: int, group=None, mode: str = "copy", n_slots: int = 3):
+        import ctypes as C
+        import torch.distributed as dist
+        lib = _lib.load()
+        self.field, self.n, self.block, self.group = field, int(n_rays_total), int(block), group
+        distributed = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if distributed else 1
+        self.rank = dist.get_rank(group) if distributed else 0
+        self.mode = mode
+        dev = field.device
+        dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        h = C.c_void_p()
+        _lib.check(lib.ngf_comm_init(self.rank, self.world, dev_index, self.n, self.block, int(n_slots),
+                                     {"copy": _lib.COMM_COPY, "store": _lib.COMM_STORE}[mode], C.byref(h)), "ngf_comm_init")
+        self._h = h
+        self.n_local = int(lib.ngf_comm_local_rays(h))
+        if self.world > 1:
+            nb = int(lib.ngf_comm_handle_bytes())
+            mine = C.create_string_buffer(nb)
+            _lib.check(lib.ngf_comm_export(h, mine), "ngf_comm_export")
+            blobs = [None] * self.world
+            dist.all_gather_object(blobs, bytes(mine.raw), group=group)
+            _lib.check(lib.ngf_comm_connect(h, b"".join(blobs)), "ngf_comm_connect")
+            dist.barrier(group)             # nobody starts writing into a peer that has not mapped / zeroed its flags
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().ngf_comm_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _field_handle(self, fwd_kw):
+        fh = self.field._ensure_handle()
+        self.field._set_switches(_lib.load(), fh, **fwd_kw)
+        return fh
+
+    @torch.no_grad()
+    def submit(self, rays_local, N_samples=-1, white_bg=True, image_width=0, **fwd_kw):
+        """Render this rank's rays (CUDA tensor [n_local, C >= 6], local order) of the next batch on the current stream
+        and start the exchange.  -> ticket."""
+        import ctypes as C
+        if not fwd_kw and hasattr(self.field, "gauge_start"):
+            fwd_kw = {"iteration": 30001}
+        fh = self._field_handle(fwd_kw)
+        rays = rays_local
+        if rays.dtype != torch.float32 or not rays.is_contiguous() or rays.device != self.field.device:
+            rays = rays.to(self.field.device, torch.float32).contiguous()
+        t = C.c_uint64()
+        with torch.cuda.device(self.field.device):
+            _lib.check(_lib.load().ngf_field_render_sharded(fh, self._h, rays.data_ptr(), rays.shape[0], rays.shape[1],
+                                                            int(N_samples), int(bool(white_bg)), int(image_width),
+                                                            self.field._mlp_impl, _cuda_stream_ptr(self.field.device),
+                                                            C.byref(t)), "ngf_field_render_sharded")
+        return int(t.value)
+
+    def result(self, ticket: int) -> torch.Tensor:
+        """Make the current stream wait for every rank's rows of ``ticket`` and return the gathered [n, 4] batch (a view of
+        the library's frame buffer: valid until ``release(ticket)`` and n_slots - 1 further submits)."""
+        import ctypes as C
+        p = C.c_void_p()
+        with torch.cuda.device(self.field.device):
+            _lib.check(_lib.load().ngf_frame_allgather(self._h, int(ticket), _cuda_stream_ptr(self.field.device),
+                                                       C.byref(p)), "ngf_frame_allgather")
+        return torch.as_tensor(_DevView(p.value, self.n, 4), device=self.field.device)
+
+    def release(self, ticket: int):
+        with torch.cuda.device(self.field.device):
+            _lib.check(_lib.load().ngf_frame_release(self._h, int(ticket), _cuda_stream_ptr(self.field.device)),
+                       "ngf_frame_release")
+
+    @torch.no_grad()
+    def submit_host(self, rays_local_host, frame_host, first_row=0, n_rows=None, N_samples=-1, white_bg=True,
+                    image_width=0, **fwd_kw):
+        """Host-buffer pipeline (ngf_field_render_sharded_host_async): pinned rays of this rank in, rows
+        [first_row, first_row + n_rows) of the gathered batch out into the pinned ``frame_host`` [n_rows, 4].  -> ticket
+        for ``wait``; consecutive batches overlap upload / render / exchange / download."""
+        import ctypes as C
+        if not fwd_kw and hasattr(self.field, "gauge_start"):
+            fwd_kw = {"iteration": 30001}
+        fh = self._field_handle(fwd_kw)
+        for t_ in (rays_local_host, frame_host):
+            if t_.device.type != "cpu" or t_.dtype != torch.float32 or not t_.is_contiguous():
+                raise ValueError("submit_host takes contiguous fp32 CPU tensors")
+        n_rows = frame_host.shape[0] if n_rows is None else int(n_rows)
+        t = C.c_uint64()
+        _lib.check(_lib.load().ngf_field_render_sharded_host_async(
+            fh, self._h, rays_local_host.data_ptr(), rays_local_host.shape[0], rays_local_host.shape[1], int(N_samples),
+            int(bool(white_bg)), int(image_width), self.field._mlp_impl, frame_host.data_ptr(), int(first_row), n_rows,
+            C.byref(t)), "ngf_field_render_sharded_host_async")
+        return int(t.value)
+
+    def wait(self, ticket: int):
+        _lib.check(_lib.load().ngf_comm_wait(self._h, int(ticket)), "ngf_comm_wait")
+
+
+class ShardedFrameRenderer:
+    """Ray-sharded multi-GPU rendering, one all-gather of the rendered batch per step, overlapped with the next batch.
+
+    ``mode="copy"`` / ``"store"`` (default copy): the exchange runs inside the C ABI over NVLink peer memory (FrameComm).
+    ``mode="nccl"``: the render is followed by one ``torch.distributed.all_gather_into_tensor`` (NCCL) and a re-ordering
+    kernel on a side stream, double-buffered — kept as the library baseline the peer-memory path is compared with.
 
         r = ShardedFrameRenderer(field, n_rays_total, block)
         t = r.submit(my_shard_of_rays)          # returns at once
         frame = r.result(t)                      # [n_rays_total, 4] on this rank's device, ordered as the input batch
+        r.release(t)                             # done reading (peer-memory modes; no-op for nccl)
     """
 
-    def __init__(self, field, n_rays_total: int, block: int = 2000, group=None):
+    def __init__(self, field, n_rays_total: int, block: int = 2000, group=None, mode: str = "copy"):
         import torch.distributed as dist
         self.field, self.n, self.block, self.group = field, int(n_rays_total), int(block), group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.mode = mode
+        self.comm = None
+        if mode != "nccl":
+            self.comm = FrameComm(field, n_rays_total, block, group, mode)
+            return
         dev = field.device
         self.max_shard = -(-(-(-self.n // block)) // self.world) * block
-        self.comm = torch.cuda.Stream(device=dev)
+        self.side = torch.cuda.Stream(device=dev)
         self.local = [torch.zeros((self.max_shard, 4), device=dev) for _ in range(2)]
         self.gathered = [torch.empty((self.world, self.max_shard, 4), device=dev) for _ in range(2)]
         self.frame = [torch.empty((self.n, 4), device=dev) for _ in range(2)]
@@ -181,6 +308,8 @@ class ShardedFrameRenderer:
 
     @torch.no_grad()
     def submit(self, rays_local, N_samples=-1, white_bg=True, **fwd_kw):
+        if self.comm is not None:
+            return self.comm.submit(rays_local, N_samples=N_samples, white_bg=white_bg, **fwd_kw)
         import torch.distributed as dist
         b = self.count % 2
         cur = torch.cuda.current_stream(self.field.device)
@@ -189,21 +318,23 @@ class ShardedFrameRenderer:
         n = rgb.shape[0]
         torch.cat([rgb, depth[:, None]], 1, out=self.local[b][:n])
         self.rendered[b].record(cur)
-        with torch.cuda.stream(self.comm):
-            self.comm.wait_event(self.rendered[b])
-            self.comm.wait_event(self.read[b])             # a pending download of this parity's frame buffer
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.rendered[b])
+            self.side.wait_event(self.read[b])             # a pending download of this parity's frame buffer
             dist.all_gather_into_tensor(self.gathered[b].view(self.world * self.max_shard, 4), self.local[b],
                                         group=self.group)
             src = self.gathered[b]
             _lib.check(_lib.load().ngf_shard_scatter(src.data_ptr(), self.n, 4, self.block, self.world, self.max_shard,
-                                                     self.frame[b].data_ptr(), int(self.comm.cuda_stream)))
-            self.done[b].record(self.comm)
+                                                     self.frame[b].data_ptr(), int(self.side.cuda_stream)))
+            self.done[b].record(self.side)
         self.count += 1
         return self.count - 1
 
     def download(self, ticket: int, out_host: torch.Tensor, n_rows: int = None):
-        """Copy the first ``n_rows`` rows (default: all) of batch ``ticket``'s gathered frame into the pinned CPU tensor
-        ``out_host`` on a dedicated stream, without stalling the compute stream; returns the event to wait on."""
+        """nccl mode: copy the first ``n_rows`` rows (default: all) of batch ``ticket``'s gathered frame into the pinned CPU
+        tensor ``out_host`` on a dedicated stream, without stalling the compute stream; returns the event to wait on."""
+        if self.comm is not None:
+            raise RuntimeError("download() belongs to mode='nccl'; the peer-memory modes use FrameComm.submit_host")
         if ticket < self.count - 2 or ticket >= self.count:
             raise ValueError("only the last two submitted batches are still buffered")
         b = ticket % 2
@@ -216,7 +347,13 @@ class ShardedFrameRenderer:
     def result(self, ticket: int):
         """Make the current stream wait for batch ``ticket`` (it must be one of the last two submitted) and return its
         frame buffer; the buffer is overwritten two submissions later."""
+        if self.comm is not None:
+            return self.comm.result(ticket)
         if ticket < self.count - 2 or ticket >= self.count:
             raise ValueError("only the last two submitted batches are still buffered")
         torch.cuda.current_stream(self.field.device).wait_event(self.done[ticket % 2])
         return self.frame[ticket % 2]
+
+    def release(self, ticket: int):
+        if self.comm is not None:
+            self.comm.release(ticket)

@@ -139,6 +139,23 @@ def spec_from_state(variant: str, state: dict, *, aabb, gridSize, step_ratio=2.0
     )
 
 
+def spec_to_device(spec: FieldSpec, device) -> FieldSpec:
+    """The same spec with every tensor on ``device`` — the reference's normal device is the GPU (TriPlane/main.py:18);
+    bench.py times this as the torch-CUDA baseline.  The restated ops are device-agnostic; the CPU is the parity pin."""
+    import dataclasses
+    mv = lambda x: x.to(device) if isinstance(x, torch.Tensor) else x
+    kw = {}
+    for fld in dataclasses.fields(spec):
+        v = getattr(spec, fld.name)
+        if isinstance(v, torch.Tensor):
+            v = mv(v)
+        elif isinstance(v, list):
+            v = [tuple(mv(y) for y in x) if isinstance(x, tuple) else mv(x) for x in v]
+        kw[fld.name] = v
+    kw["stats"] = {}
+    return FieldSpec(**kw)
+
+
 # --------------------------------------------------------------------------------------------------------------
 # §8f rank 1  camera rays (TriPlane/dataLoader/ray_utils.py:24-42,66-87; blender.py:46-52; main.py:155-159)
 # --------------------------------------------------------------------------------------------------------------
@@ -169,7 +186,7 @@ def march(spec: FieldSpec, o: torch.Tensor, d: torch.Tensor, S: int, jitter=None
     ta = (hi - o) / safe_d
     tb = (lo - o) / safe_d
     t0 = torch.minimum(ta, tb).amax(-1).clamp(min=spec.near, max=spec.far)
-    k = torch.arange(S)[None].float()
+    k = torch.arange(S, device=d.device)[None].float()
     if jitter is not None:
         k = k.repeat(d.shape[-2], 1)
         k += jitter.reshape(-1, 1)
@@ -277,7 +294,7 @@ def gauge_coords(spec: FieldSpec, n: torch.Tensor):
 def phase_code(xyz: torch.Tensor, n_freq: int) -> torch.Tensor:
     """positional_encoding (networks.py:205-216 / InfoInv networks.py:227-237): [N,D] -> [N,2*D*F];
     layout [sin(x0*2^0..2^(F-1)), sin(x1*...), ..., cos(same order)]."""
-    bands = 2 ** torch.arange(n_freq).float()
+    bands = 2 ** torch.arange(n_freq, device=xyz.device).float()
     a = (xyz[..., None] * bands).reshape(xyz.shape[0], -1)
     return torch.cat([torch.sin(a), torch.cos(a)], -1)
 
@@ -329,7 +346,7 @@ def colour(spec: FieldSpec, xy, yz, xz, viewdir) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------------------
 def transmittance(sig: torch.Tensor, delta: torch.Tensor):
     a = 1.0 - torch.exp(-sig * delta)
-    T = torch.cumprod(torch.cat([torch.ones(a.shape[0], 1), 1.0 - a + 1e-10], -1), -1)
+    T = torch.cumprod(torch.cat([torch.ones(a.shape[0], 1, device=a.device), 1.0 - a + 1e-10], -1), -1)
     return a, a * T[:, :-1]
 
 
@@ -353,8 +370,9 @@ def _render_chunk(spec: FieldSpec, rays: torch.Tensor, white_bg: bool = True, N_
         live = live.clone()
         live[live.clone()] = keep
     R = rays.shape[0]
-    sig = torch.zeros(R, S)
-    cxy, cyz, cxz = torch.zeros(R, S, 2), torch.zeros(R, S, 2), torch.zeros(R, S, 2)
+    dev = rays.device
+    sig = torch.zeros(R, S, device=dev)
+    cxy, cyz, cxz = torch.zeros(R, S, 2, device=dev), torch.zeros(R, S, 2, device=dev), torch.zeros(R, S, 2, device=dev)
     if live.any():
         n = to_unit_cube(spec, p)
         a, b, c = gauge_coords(spec, n[live])
@@ -362,7 +380,7 @@ def _render_chunk(spec: FieldSpec, rays: torch.Tensor, white_bg: bool = True, N_
         cxy[live], cyz[live], cxz[live] = a, b, c
     _, w = transmittance(sig, delta * spec.distance_scale)
     hot = w > spec.weight_thres
-    rgb = torch.zeros(R, S, 3)
+    rgb = torch.zeros(R, S, 3, device=dev)
     if hot.any():
         dirs = d[:, None, :].expand(R, S, 3)
         rgb[hot] = colour(spec, cxy[hot], cyz[hot], cxz[hot], dirs[hot])

@@ -1,4 +1,5 @@
-"""GPU, >= 2 devices: the ray-sharded frame render + NCCL all-gather equals the reference golden frame."""
+"""GPU, >= 2 devices: the ray-sharded frame render + all-gather (NCCL, and the C ABI's peer-memory copy / store
+variants, device-resident and through host buffers) equals the reference golden frame on every rank."""
 import os
 import subprocess
 import sys
@@ -16,4 +17,4 @@ def test_sharded_frame_matches_golden_2gpu():
            "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "scripts", "check_sharded.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert res.stdout.count("OK") == 2
+    assert res.stdout.count("=> OK") == 2, res.stdout[-3000:]

@@ -314,3 +314,139 @@ def test_train_forward_zero_jitter_is_eval_and_backward_is_refused():
     assert any(p.requires_grad for p in f.parameters())
     with pytest.raises(NotImplementedError):
         f(r, white_bg=True, is_train=True, N_samples=case.n_samples, **forward_kwargs(case))
+
+
+def test_sharded_render_single_rank_and_shard_layout():
+    """The C ABI's sharded render (ngf_comm_init / ngf_field_render_sharded / ngf_frame_allgather) on ONE GPU:
+    (a) world 1: the [R,4] frame equals the plain render, across more batches than frame buffers, device-resident and
+        through the host-buffer pipeline;
+    (b) the shard layout: for rank r of a pretend world of 3, the finalize kernel puts local ray l at the global row
+        ngf_shard_count's arithmetic names (the rows of the other ranks stay untouched); stitched together the three
+        ranks' rows give the whole frame.  (The exchange itself needs several processes: tests/test_gpu_multi.py.)"""
+    import ctypes as C
+    import ngf_b200
+    from ngf_b200 import _lib
+    from ngf_b200.render import shard_index
+    case = K.CASE_BY_NAME["tp_fog_c1"]
+    state, kw, occ, rays = K.build_inputs(case)
+    f = build_cuda_field(case, state, kw, occ)
+    ref = f(rays.cuda(), white_bg=True, N_samples=64, iteration=30001)
+    want = torch.cat([ref["rgb_map"], ref["depth_map"][:, None]], 1).cpu()
+    n = rays.shape[0]
+    comm = ngf_b200.FrameComm(f, n, block=96)
+    assert comm.world == 1 and comm.n_local == n
+    for k in range(5):
+        t = comm.submit(rays.cuda(), N_samples=64, white_bg=True, iteration=30001)
+        got = comm.result(t).clone()
+        comm.release(t)
+        assert (got.cpu() - want).abs().max() < 1e-5
+    out = [torch.zeros((n - 100, 4)).pin_memory() for _ in range(2)]
+    tk = [comm.submit_host(rays.pin_memory(), out[k % 2], first_row=100, N_samples=64, white_bg=True, iteration=30001)
+          for k in range(4)]
+    for t in tk:
+        comm.wait(t)
+    assert (out[0] - want[100:]).abs().max() < 1e-5 and (out[1] - want[100:]).abs().max() < 1e-5
+    comm.close()
+    # (b) three ranks driven from this one process on this one GPU (peers in the same process are addressed directly
+    # instead of through CUDA IPC): the complete exchange protocol — shard layout, strided copies / remote stores,
+    # arrived / freed flags, buffer reuse over 7 batches with 3 buffers.  Every wait kernel is enqueued after the work
+    # it waits for, so the single host thread cannot deadlock the device.
+    lib = _lib.load()
+    nb = int(lib.ngf_comm_handle_bytes())
+    fh = f._ensure_handle()
+    for mode in (_lib.COMM_COPY, _lib.COMM_STORE):
+        hs, blobs = [], b""
+        for r in range(3):
+            h = C.c_void_p()
+            _lib.check(lib.ngf_comm_init(r, 3, 0, n, 96, 3, mode, C.byref(h)))
+            assert lib.ngf_comm_local_rays(h) == shard_index(n, 96, r, 3).numel()
+            buf = C.create_string_buffer(nb)
+            _lib.check(lib.ngf_comm_export(h, buf))
+            hs.append(h)
+            blobs += bytes(buf.raw)
+        t = C.c_uint64()
+        mine = [rays[shard_index(n, 96, r, 3)].cuda().contiguous() for r in range(3)]
+        rc = lib.ngf_field_render_sharded(fh, hs[0], mine[0].data_ptr(), mine[0].shape[0], 6, 64, 1, 0, 0, None, C.byref(t))
+        assert rc == _lib.NGF_EINVAL and b"not connected" in lib.ngf_last_error()      # refuses rather than racing
+        for h in hs:
+            _lib.check(lib.ngf_comm_connect(h, blobs))
+        streams = [torch.cuda.Stream() for _ in range(3)]
+        for k in range(7):
+            tickets = []
+            for r in range(3):
+                _lib.check(lib.ngf_field_render_sharded(fh, hs[r], mine[r].data_ptr(), mine[r].shape[0], 6, 64, 1, 0, 0,
+                                                        C.c_void_p(streams[r].cuda_stream), C.byref(t)), "render_sharded")
+                tickets.append(int(t.value))
+            frames = []
+            for r in range(3):
+                p = C.c_void_p()
+                _lib.check(lib.ngf_frame_allgather(hs[r], tickets[r], C.c_void_p(streams[r].cuda_stream), C.byref(p)))
+                with torch.cuda.stream(streams[r]):
+                    frames.append(torch.as_tensor(ngf_b200.render._DevView(p.value, n, 4), device="cuda").clone())
+                _lib.check(lib.ngf_frame_release(hs[r], tickets[r], C.c_void_p(streams[r].cuda_stream)))
+            torch.cuda.synchronize()
+            for r in range(3):
+                assert (frames[r].cpu() - want).abs().max() < 1e-5, (mode, k, r)
+        for h in hs:
+            lib.ngf_comm_free(h)
+
+
+def test_camera_u8_host_path():
+    """ngf_field_render_camera_u8_host_async: evaluation_path's per-frame job (pose in, uint8 image out) equals the
+    fp32 camera render converted as main.py:116 does ((rgb * 255).astype('uint8')) byte for byte."""
+    case = K.CASE_BY_NAME["tp_fog_c1"]
+    state, kw, occ, _ = K.build_inputs(case)
+    f = build_cuda_field(case, state, kw, occ)
+    H, W = 48, 80
+    focal = K.synth.FOCAL_800 * 64 / 800
+    c2w = K.synth.look_at_c2w(*K.synth.pose_angles(4))
+    u8 = torch.zeros((H * W, 3), dtype=torch.uint8).pin_memory()
+    dep = torch.zeros((H * W,)).pin_memory()
+    rgb_h, dep_h = torch.empty((H * W, 3)).pin_memory(), torch.empty((H * W,)).pin_memory()
+    f.host_wait(f.render_camera_host_async(c2w, H, W, focal, rgb_h, dep_h, white_bg=True, N_samples=64, iteration=30001))
+    f.host_wait(f.render_camera_u8_host_async(c2w, H, W, focal, u8, dep, white_bg=True, N_samples=64, iteration=30001))
+    want = (rgb_h.numpy() * 255).astype("uint8")
+    # the two renders accumulate a ray's colour samples with fp32 atomics in arbitrary order: a value that sits on an
+    # integer boundary after * 255 may land on either side
+    diff = np.abs(u8.numpy().astype(np.int16) - want.astype(np.int16))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+    assert (dep - dep_h).abs().max() < 1e-5
+
+
+def test_weight_threshold_zero_keeps_every_sample():
+    """rayMarch_weight_thres = 0 (a constructor / checkpoint kwarg, FieldBase.py:46): the reference then shades every
+    sample with non-zero weight; the march's early-out must not drop them (its stop threshold follows the field's)."""
+    case = K.CASE_BY_NAME["tp_fog_c1"]
+    state, kw, occ, rays = K.build_inputs(case)
+    kw = dict(kw, rayMarch_weight_thres=0.0)
+    f = build_cuda_field(case, state, kw, occ)
+    out = f(rays.cuda(), white_bg=True, N_samples=64, iteration=30001)
+    spec = oracle_spec(case, state, kw, occ)
+    assert spec.weight_thres == 0.0
+    o_rgb, o_depth = R.render(spec, rays, white_bg=True, N_samples=64)
+    assert (out["rgb_map"].cpu() - o_rgb).abs().max() < RGB_TOL
+    assert (out["depth_map"].cpu() - o_depth).abs().max() < DEPTH_TOL
+    st = f.last_stats()
+    assert st["samples_colour"] >= spec.stats["n_active"] * 0.999
+
+
+def test_full_frame_c3_infoinv_properties():
+    """BASELINE config 3 (InfoInv, 800x800 rays, 192 samples) at full size: a 16 Ki-ray strided subset against the
+    oracle, halves vs whole, finiteness."""
+    case = K.Case("c3_hull", variant="infoinv", kind="hull", config="C2", n_samples=192)
+    state, kw, occ, rays = K.build_inputs(case)
+    f, rgb, depth = _render_cuda(case, state, kw, occ, rays, image_width=800)
+    assert rgb.shape == (640000, 3) and torch.isfinite(rgb).all() and torch.isfinite(depth).all()
+    assert float(rgb.min()) >= 0.0 and float(rgb.max()) <= 1.0
+    idx = torch.arange(0, 640000, 39)[:16384]
+    spec = oracle_spec(case, state, kw, occ)
+    o_rgb, o_depth = R.render(spec, rays[idx], white_bg=True, N_samples=192)
+    assert (rgb[idx] - o_rgb).abs().max() < RGB_TOL
+    assert (depth[idx] - o_depth).abs().max() < DEPTH_TOL
+    g = torch.Generator().manual_seed(7)
+    gt = (o_rgb + 0.02 * torch.randn(o_rgb.shape, generator=g)).clamp(0, 1)
+    assert abs(psnr(rgb[idx], gt) - psnr(o_rgb, gt)) < 0.05
+    half = 320000
+    a = f(rays[:half].cuda(), white_bg=True, N_samples=192, **forward_kwargs(case))
+    b = f(rays[half:].cuda(), white_bg=True, N_samples=192, **forward_kwargs(case))
+    assert (torch.cat([a["rgb_map"], b["rgb_map"]]).cpu() - rgb).abs().max() < 1e-5
