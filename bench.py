@@ -110,7 +110,9 @@ class ClockSampler:
 # workload
 # ---------------------------------------------------------------------------------------------------------------
 def shard_of_batch(synth, pose0: int, world: int, rank: int):
-    """Rays rank owns of the batch made of frames pose0 .. pose0+world-1 (interleaved BLOCK-ray blocks)."""
+    """Rays rank owns of the batch made of the frames of poses (pose0 + j) % N_POSES, j < world (interleaved BLOCK-ray
+    blocks).  Every N renders the same 16 poses equally often, so per-rank work is the same at every N (weak scaling)
+    while each of a rank's 16 batches is a different ray set."""
     if world == 1:
         return synth.config_rays("C2", pose0)
     g = torch.arange(world * RAYS_PER_FRAME)
@@ -119,7 +121,7 @@ def shard_of_batch(synth, pose0: int, world: int, rank: int):
     out = torch.empty((mine.numel(), 6))
     fidx = mine // RAYS_PER_FRAME
     for f in fidx.unique().tolist():
-        frames[f] = synth.config_rays("C2", pose0 + f)
+        frames[f] = synth.config_rays("C2", (pose0 + f) % N_POSES)
         sel = fidx == f
         out[sel] = frames[f][mine[sel] - f * RAYS_PER_FRAME]
     return out.contiguous()
@@ -210,7 +212,7 @@ def main():
                               gauge_start=0)
     synth.load_into(field, state, occ, ngf_b200.AlphaGridMask)
     assert field.nSamples == S, field.nSamples
-    host = [shard_of_batch(synth, p * world, world, rank).pin_memory() for p in range(N_POSES)]
+    host = [shard_of_batch(synth, p, world, rank).pin_memory() for p in range(N_POSES)]
     n_local = host[0].shape[0]
     dev_rays = [h.to(dev) for h in host]
     n_batch = world * RAYS_PER_FRAME
@@ -382,6 +384,26 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = n_batch * args.steps / e2e_s
 
+    # ---- the transport floor of that region: the same H2D and D2H copies alone (no kernels), all ranks at once
+    cp_in, cp_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    d_in = torch.empty_like(dev_rays[0])
+    d_out = torch.empty((n_local, 4), device=dev)
+    h_out = torch.empty((n_local, 4)).pin_memory()
+    def copies(n):
+        for i in range(n):
+            with torch.cuda.stream(cp_in):
+                d_in.copy_(host[i % N_POSES], non_blocking=True)
+            with torch.cuda.stream(cp_out):
+                h_out.copy_(d_out, non_blocking=True)
+    copies(3)
+    barrier()
+    n_cp = max(10, min(args.steps, 100))
+    t0 = time.perf_counter()
+    copies(n_cp)
+    barrier()
+    floor_s = max_over_ranks(time.perf_counter() - t0) / n_cp
+    e2e_floor = n_batch / floor_s
+
     # ---- second end-to-end figure: what evaluation_path needs (TriPlane/main.py:155-161) — a camera pose in, the
     # uint8 image out: rays generated on the device, uint8 conversion on the device, 1.92 MB D2H per frame
     e2e_cam = camera_e2e(ngf_b200, synth, field, dev, args.steps) if world == 1 else None
@@ -433,7 +455,10 @@ def main():
                    "arithmetic": "fp32 march / density / compositing; colour MLP fp16 operands with fp32 accumulation (tcgen05, TMEM)", "l2": f"inputs rotate over {N_POSES} poses ({N_POSES * n_local * 24 / 1e6:.0f} MB of rays per rank > 126 MB L2)",
                    "parallelism": "single GPU" if world == 1 else f"ray-sharded dp{world}, {BLOCK}-ray interleaved blocks, {coll}"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_local * 24, "d2h_bytes_per_step": d2h,
-                "api": e2e_api},
+                "api": e2e_api,
+                "transport_floor": {"value": e2e_floor, "unit": "rays/s", "frac_of_floor": e2e_value / e2e_floor,
+                                    "what": "the same pinned H2D (rays) and D2H (results) copies alone, no kernels, all ranks "
+                                            "concurrently: what the PCIe / host-memory path of this box allows"}},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": roofline,

@@ -167,6 +167,31 @@ int ngf_field_render_jitter(NgfField f, const float* rays_dev, int64_t n_rays, i
                             float* acc_dev, int32_t mlp_impl, void* stream);
 
 /*
+ * Backward pass of the training step (TriPlane/main.py:272-302: rgb_map = field(rays,
+ * is_train=True)['rgb_map'] -> loss -> loss.backward()).  Given dL/d(rgb_map) [R][3] it ADDS dL/d(parameter) into the
+ * caller's gradient buffers, which have the reference's own parameter layouts (feature planes [C][H][W], gauge planes
+ * [2][Hg][Wg], nn.Linear weights [out][in] and biases), i.e. the `.grad` tensors of the module's parameters.  The forward is
+ * not saved: the rays are re-marched with the same jitter (NULL = evaluation-time sampling) and the same sample decisions
+ * as ngf_field_render_jitter on the handle's current (packed) parameters, so call it before the parameters change.
+ * depth_map carries no gradient (it is computed under torch.no_grad(), FieldBase.py:304-306).  gauge[] may be NULL when
+ * the gauge is off; dens_l2 / dens_l3 are InfoInv's (density_decoder.mlp.{2,4}).  fp32 on CUDA cores; synchronises `stream`
+ * once (to size its workspace, NGF_TRAIN_MIB MiB at most, default 2048).
+ */
+typedef struct NgfFieldGrads {
+  float* plane[3];
+  float* gauge[3];
+  /* optional (all three or NULL): the feature-plane parameters themselves, fp32 [C][H][W] device pointers.  The forward
+   * of the colour MLP is then recomputed from the reference's fp32 features, so the ReLU masks of the backward are the
+   * reference's; with NULL the handle's fp16 appearance texels are used (hidden units within ~1e-3 of zero may flip). */
+  const float* plane_param[3];
+  float *rgb_basis, *rgb_l1_w, *rgb_l1_b, *rgb_l2_w, *rgb_l2_b, *rgb_l3_w, *rgb_l3_b;
+  float *dens_l1_w, *dens_l1_b, *dens_l2_w, *dens_l2_b, *dens_l3_w, *dens_l3_b;
+} NgfFieldGrads;
+int ngf_field_backward(NgfField f, const float* rays_dev, int64_t n_rays, int32_t ray_stride, int32_t n_samples,
+                       int32_t white_bg, const float* jitter_dev, const float* grad_rgb_dev, const NgfFieldGrads* grads,
+                       void* stream);
+
+/*
  * Same through HOST buffers: H2D of the rays, render, D2H of rgb/depth, chunked and overlapped on internal
  * streams; returns after the results are in rgb_host/depth_host.  This is the call the reference-facing
  * `renderer(rays_cpu, field, ...)` maps to when rays live on the CPU (main.py:64-65 does the H2D per chunk).

@@ -41,6 +41,14 @@ class NgfFieldDesc(C.Structure):
     ]
 
 
+class NgfFieldGrads(C.Structure):
+    _fields_ = [("plane", C.c_void_p * 3), ("gauge", C.c_void_p * 3), ("plane_param", C.c_void_p * 3),
+                ("rgb_basis", C.c_void_p), ("rgb_l1_w", C.c_void_p), ("rgb_l1_b", C.c_void_p), ("rgb_l2_w", C.c_void_p),
+                ("rgb_l2_b", C.c_void_p), ("rgb_l3_w", C.c_void_p), ("rgb_l3_b", C.c_void_p),
+                ("dens_l1_w", C.c_void_p), ("dens_l1_b", C.c_void_p), ("dens_l2_w", C.c_void_p), ("dens_l2_b", C.c_void_p),
+                ("dens_l3_w", C.c_void_p), ("dens_l3_b", C.c_void_p)]
+
+
 class NgfNeutexDesc(C.Structure):
     _fields_ = [("geometry", NgfLinear * 12), ("gauge", NgfLinear * 5), ("tex_block1", NgfLinear * 6),
                 ("tex_color1", NgfLinear), ("tex_block2", NgfLinear * 5), ("sample_num", C.c_int32),
@@ -70,6 +78,8 @@ SIGNATURES = {
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "ngf_field_render_jitter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "ngf_field_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                     C.c_void_p, C.POINTER(NgfFieldGrads), C.c_void_p]),
     "ngf_field_render_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
     "ngf_field_render_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,

@@ -92,6 +92,9 @@ static void free_all(NgfField_* h) {
   for (int i = 0; i < 3; ++i) cudaFree(h->dsum[i]);
   cudaFree(h->occ); cudaFree(h->occ2); cudaFree(h->occ_coarse);
   cudaFree(h->dmlp); cudaFree(h->w1p); cudaFree(h->w2p); cudaFree(h->tail);
+  cudaFree(h->raw_w); cudaFree(h->raw_dw);
+  ngf_train_free(h->train);
+  h->train = nullptr;
   cudaFree(h->acc_ws); cudaFree(h->counters); cudaFree(h->queue);
   free_chunks(h);
 }
@@ -318,6 +321,14 @@ static int pack_params(NgfField_* h, const NgfFieldDesc* d, bool allocate) {
     p[0] = b3[0];
     if (allocate) CU(dev_alloc(&h->dmlp, (size_t)kDmlpFloats));
     CU(cudaMemcpy(h->dmlp, m.data(), kDmlpFloats * sizeof(float), cudaMemcpyHostToDevice));
+    {
+      std::vector<float> raw;                       // nn.Linear layout, for the backward pass
+      raw.insert(raw.end(), w.begin(), w.end()); raw.insert(raw.end(), b.begin(), b.end());
+      raw.insert(raw.end(), w2.begin(), w2.end()); raw.insert(raw.end(), b2.begin(), b2.end());
+      raw.insert(raw.end(), w3.begin(), w3.end()); raw.insert(raw.end(), b3.begin(), b3.end());
+      if (allocate) CU(dev_alloc(&h->raw_dw, raw.size()));
+      CU(cudaMemcpy(h->raw_dw, raw.data(), raw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     f.dmlp = h->dmlp;
     memset(f.dw, 0, sizeof(f.dw));
     f.db = 0.f;
@@ -358,6 +369,15 @@ static int pack_params(NgfField_* h, const NgfFieldDesc* d, bool allocate) {
     CU(cudaMemcpy(h->w2p, w2p.data(), w2p.size() * sizeof(__half), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->tail, tail.data(), tail.size() * sizeof(float), cudaMemcpyHostToDevice));
     f.w1p = h->w1p; f.w2p = h->w2p; f.tail = h->tail;
+    {
+      std::vector<float> raw;                       // unfolded fp32 weights, for the backward pass
+      raw.insert(raw.end(), B.begin(), B.end()); raw.insert(raw.end(), W1.begin(), W1.end());
+      raw.insert(raw.end(), b1.begin(), b1.end()); raw.insert(raw.end(), W2.begin(), W2.end());
+      raw.insert(raw.end(), b2.begin(), b2.end()); raw.insert(raw.end(), W3.begin(), W3.end());
+      raw.insert(raw.end(), b3.begin(), b3.end());
+      if (allocate) CU(dev_alloc(&h->raw_w, raw.size()));
+      CU(cudaMemcpy(h->raw_w, raw.data(), raw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
   }
   if (allocate) {
     CU(cudaMalloc(reinterpret_cast<void**>(&h->counters), kCounterBytes));

@@ -43,6 +43,10 @@ struct NgfField_ {
   __half* w1p = nullptr;
   __half* w2p = nullptr;
   float* tail = nullptr;
+  // fp32 network weights in nn.Linear layout for the backward pass (ngf_train.cu)
+  float* raw_w = nullptr;             // [basis F*F | mlp.0 W 64*(F+15) | b 64 | mlp.2 W 64*64 | b 64 | mlp.4 W 3*64 | b 3]
+  float* raw_dw = nullptr;            // InfoInv density MLP [W1 32*72 | b1 32 | W2 32*32 | b2 32 | W3 32 | b3 1]
+  void* train = nullptr;              // TrainWs of ngf_train.cu (record list + activation workspace)
   // render workspace
   float* acc_ws = nullptr;
   long long acc_cap = 0;
@@ -88,6 +92,9 @@ struct ShardOut {
 cudaError_t launch_finalize_shard(const float* rgb, const float* acc, const float* depth, long long n_local,
                                   int white_bg, const ShardOut& so, cudaStream_t st);
 }  // namespace ngf
+
+// ngf_train.cu
+void ngf_train_free(void* train_ws);
 
 // ngf_abi.cu
 int ngf_set_error(int code, const char* fmt, ...);

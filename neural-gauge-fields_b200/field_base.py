@@ -4,9 +4,9 @@ render path executed by ``libngf_b200.so`` (hand-written sm_100a CUDA) through t
 ``include/ngf_b200.h``.
 
 There is deliberately no CPU implementation here: a field living on the CPU, a missing shared library or a
-non-Blackwell GPU raises.  ``is_train=True`` runs the reference's jittered sampling (FieldBase.py:128-130) as a
-forward-only render; there is no backward pass, so calling it with autograd enabled on a field
-whose parameters require gradients raises ``NotImplementedError`` instead of silently returning detached tensors.
+non-Blackwell GPU raises.  ``is_train=True`` runs the reference's jittered sampling (FieldBase.py:128-130); with autograd
+enabled the call is recorded as one ``torch.autograd.Function`` whose backward is ``ngf_field_backward`` (csrc/ngf_train.cu),
+so the reference's training step (TriPlane/main.py:272-302: forward, MSE, ``loss.backward()``, Adam) runs on these classes.
 """
 from __future__ import annotations
 
@@ -51,9 +51,38 @@ class AlphaGridMask(torch.nn.Module):
         return (xyz_sampled - self.aabb[0]) * self.invgridSize - 1
 
     def sample_alpha(self, xyz_sampled):
-        if self._owner is None:
-            raise RuntimeError("AlphaGridMask is not attached to a field (assign it to field.alphaMask first)")
-        return self._owner()._alpha_keep(xyz_sampled).float()
+        owner = self._owner() if self._owner is not None else None
+        if owner is None or owner.alphaMask is not self:
+            raise RuntimeError("this AlphaGridMask is not the mask of a live field (assign it to field.alphaMask first); "
+                               "a detached or replaced mask would answer from another mask's packed bits")
+        return owner._alpha_keep(xyz_sampled).float()
+
+
+class _RenderTrain(torch.autograd.Function):
+    """forward(is_train=True) as one autograd node: ngf_field_render_jitter forward, ngf_field_backward backward."""
+
+    @staticmethod
+    def forward(ctx, field, rays, jitter, white_bg, N_samples, image_width, *params):
+        with torch.no_grad():
+            out = field._forward(rays, white_bg, True, N_samples, image_width, jitter=jitter, _white_decided=True,
+                                 **field._train_fwd_kw)
+        ctx.field, ctx.white_bg, ctx.N_samples = field, white_bg, N_samples
+        ctx.save_for_backward(rays, jitter)
+        ctx.handle_sig = field._handle_sig
+        ctx.mark_non_differentiable(out['depth_map'])                     # FieldBase.py:304-306: under torch.no_grad()
+        return out['rgb_map'], out['depth_map']
+
+    @staticmethod
+    def backward(ctx, g_rgb, _g_depth):
+        field = ctx.field
+        rays, jitter = ctx.saved_tensors
+        if field._signature() != ctx.handle_sig:
+            raise RuntimeError("the field's parameters changed between forward(is_train=True) and backward(): the "
+                               "backward re-marches the rays on the packed parameters of the forward")
+        grads = field._backward(rays, jitter, ctx.white_bg, ctx.N_samples, g_rgb)
+        params = field._grad_parameters()
+        out = [g for g, p in zip(grads, params) if p is not None]
+        return (None, None, None, None, None, None, *out)
 
 
 class Base(torch.nn.Module):
@@ -108,6 +137,9 @@ class Base(torch.nn.Module):
         # nn.Module.__setattr__ would register an AlphaGridMask as a sub-module and bypass a property setter;
         # intercept it so the mask is attached to this field and the packed handle is refreshed.
         if name == "alphaMask":
+            old = self.__dict__.get("_alphaMask")
+            if old is not None and old is not value:
+                old._owner = None                       # a replaced mask must not answer from this field's packed bits
             object.__setattr__(self, "_alphaMask", value)
             if value is not None:
                 value._owner = weakref.ref(self)
@@ -228,6 +260,18 @@ class Base(torch.nn.Module):
     def _fill_desc(self, d: _lib.NgfFieldDesc, keep: list):
         raise NotImplementedError
 
+    def _shape_signature(self):
+        am = self.alphaMask
+        return ([tuple(p.shape) for p in self.parameters()],
+                None if am is None else tuple(am.alpha_volume.shape))
+
+    def invalidate(self):
+        """Tell the field that parameters or attributes were changed in a way the version counters cannot see (e.g.
+        ``plane.data.mul_()``, an in-place edit of ``aabb`` or of the mask volume): the next render re-packs."""
+        self._invalidate()
+
+    refresh = invalidate
+
     def _ensure_handle(self):
         self._require_cuda()
         sig = self._signature()
@@ -238,13 +282,25 @@ class Base(torch.nn.Module):
         keep: list = []
         self._fill_desc(d, keep)
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        shapes = self._shape_signature()
         torch.cuda.synchronize(self.device)
+        if self._handle is not None and shapes == getattr(self, "_handle_shapes", None):
+            # same shapes (an optimizer step, load_state_dict): refresh the packed shadows in place — allocations,
+            # streams and outstanding host-path tickets of the handle survive
+            _lib.check(lib.ngf_field_repack(self._handle, C.byref(d)), "ngf_field_repack")
+            self._handle_sig = sig
+            return self._handle
         self._free_handle()
         h = C.c_void_p()
         _lib.check(lib.ngf_field_pack(C.byref(d), dev_index, C.byref(h)), "ngf_field_pack")
         self._handle = h
         self._handle_sig = sig
+        self._handle_shapes = shapes
         return h
+
+    def _live_handle(self):
+        """The handle as it is (no staleness check): for waits, counters and timers, which must not re-pack."""
+        return self._handle if self._handle is not None else self._ensure_handle()
 
     def set_mlp_impl(self, name: str):
         """'tcgen05' (default) or 'simt' (CUDA-core cross-check of the same packed weights)."""
@@ -263,12 +319,62 @@ class Base(torch.nn.Module):
         the reference does (``torch.rand_like`` of a CPU ``[R,1]`` tensor, FieldBase.py:128-130) or passed in as
         ``jitter=`` ([R] or [R,1]); a non-white background is made white with probability 1/2 (FieldBase.py:299)."""
         if is_train and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("the B200 render path has no backward pass (SURVEY.md §8f row 3): call the "
-                                      "training-time forward under torch.no_grad()")
+            return self._forward_train(rays_chunk, white_bg, N_samples, image_width, **fwd_kw)
         with torch.no_grad():
             return self._forward(rays_chunk, white_bg, is_train, N_samples, image_width, **fwd_kw)
 
-    def _forward(self, rays_chunk, white_bg, is_train, N_samples, image_width, jitter=None, **fwd_kw):
+    def _grad_parameters(self):
+        """Parameters in the order of _lib.NgfFieldGrads: planes, gauge planes (or None), rgb_decoder, density head."""
+        raise NotImplementedError
+
+    def _forward_train(self, rays_chunk, white_bg, N_samples, image_width, jitter=None, **fwd_kw):
+        """The training-time forward under autograd (TriPlane/main.py:272): one autograd node whose backward is
+        ngf_field_backward."""
+        h = self._ensure_handle()
+        self._set_switches(_lib.load(), h, **fwd_kw)
+        rays = _f32c(rays_chunk.to(self.device))
+        R = rays.shape[0]
+        if jitter is None:
+            jitter = torch.rand_like(torch.empty((R, 1), dtype=torch.float32))          # CPU draw, as the reference
+        jitter = _f32c(jitter.reshape(-1).to(self.device))
+        white = bool(white_bg) or bool(torch.rand((1,)) < 0.5)                           # FieldBase.py:299
+        params = self._grad_parameters()
+        self._train_fwd_kw = dict(fwd_kw)               # per-call switches (iteration / infoinv), re-applied in the node
+        rgb, depth = _RenderTrain.apply(self, rays, jitter, white, int(N_samples), int(image_width),
+                                        *[p for p in params if p is not None])
+        return {'rgb_map': rgb, 'depth_map': depth}
+
+    def _backward(self, rays, jitter, white_bg, N_samples, grad_rgb):
+        """-> list of gradient tensors (or None) aligned with _grad_parameters()."""
+        lib = _lib.load()
+        h = self._live_handle()
+        params = self._grad_parameters()
+        grads = [None if (p is None or not p.requires_grad) else torch.zeros_like(p, dtype=torch.float32,
+                                                                                 memory_format=torch.contiguous_format)
+                 for p in params]
+        # the library adds into every buffer it is given; parameters that need no gradient get a scratch buffer
+        scratch = [g if g is not None else (None if p is None else torch.zeros_like(p, dtype=torch.float32))
+                   for g, p in zip(grads, params)]
+        ptr = lambda t: None if t is None else t.data_ptr()
+        G = _lib.NgfFieldGrads()
+        keep = []
+        for i in range(3):
+            G.plane[i] = ptr(scratch[i])
+            G.gauge[i] = ptr(scratch[3 + i])
+            keep.append(_f32c(params[i]))                       # the fp32 parameter: exact features for the ReLU masks
+            G.plane_param[i] = keep[-1].data_ptr()
+        (G.rgb_basis, G.rgb_l1_w, G.rgb_l1_b, G.rgb_l2_w, G.rgb_l2_b, G.rgb_l3_w, G.rgb_l3_b) = (ptr(t) for t in scratch[6:13])
+        dens = [ptr(t) for t in scratch[13:]] + [None] * 6
+        (G.dens_l1_w, G.dens_l1_b, G.dens_l2_w, G.dens_l2_b, G.dens_l3_w, G.dens_l3_b) = dens[:6]
+        g = _f32c(grad_rgb)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.ngf_field_backward(h, rays.data_ptr(), rays.shape[0], rays.shape[1], int(N_samples),
+                                              int(bool(white_bg)), jitter.data_ptr(), g.data_ptr(), C.byref(G),
+                                              _cuda_stream_ptr(self.device)), "ngf_field_backward")
+        return grads
+
+    def _forward(self, rays_chunk, white_bg, is_train, N_samples, image_width, jitter=None, _white_decided=False,
+                 **fwd_kw):
         h = self._ensure_handle()
         lib = _lib.load()
         self._set_switches(lib, h, **fwd_kw)
@@ -288,7 +394,8 @@ class Base(torch.nn.Module):
             jitter = _f32c(jitter.reshape(-1).to(self.device))
             if jitter.numel() != R:
                 raise ValueError(f"jitter must have one value per ray ({R}), got {jitter.numel()}")
-            white_bg = bool(white_bg) or bool(torch.rand((1,)) < 0.5)
+            if not _white_decided:
+                white_bg = bool(white_bg) or bool(torch.rand((1,)) < 0.5)
         with torch.cuda.device(self.device):
             if is_train:
                 _lib.check(lib.ngf_field_render_jitter(h, rays.data_ptr(), R, rays.shape[1], int(N_samples),
@@ -403,28 +510,25 @@ class Base(torch.nn.Module):
         return int(ticket.value)
 
     def host_wait(self, ticket: int):
-        _lib.check(_lib.load().ngf_field_host_wait(self._ensure_handle(), int(ticket)), "ngf_field_host_wait")
+        _lib.check(_lib.load().ngf_field_host_wait(self._live_handle(), int(ticket)), "ngf_field_host_wait")
 
     def last_stats(self) -> dict:
         """Counters of the last device-side render (forces a stream sync)."""
         st = _lib.NgfStats()
-        _lib.check(_lib.load().ngf_field_stats(self._ensure_handle(), C.byref(st), _cuda_stream_ptr(self.device)))
+        _lib.check(_lib.load().ngf_field_stats(self._live_handle(), C.byref(st), _cuda_stream_ptr(self.device)))
         return {k: int(getattr(st, k)) for k, _ in st._fields_}
 
     def kernel_timing(self, capacity: int):
         """Arm (capacity > 0) or disarm (0) CUDA-event timing of the march / colour kernels (ngf_field_timing_begin)."""
-        _lib.check(_lib.load().ngf_field_timing_begin(self._ensure_handle(), int(capacity)))
+        _lib.check(_lib.load().ngf_field_timing_begin(self._live_handle(), int(capacity)))
 
     def kernel_timing_read(self):
         """-> (march+colour pairs timed, march milliseconds, colour milliseconds) since the last read."""
         n, a, b = C.c_int32(), C.c_double(), C.c_double()
-        _lib.check(_lib.load().ngf_field_timing_read(self._ensure_handle(), C.byref(n), C.byref(a), C.byref(b)))
+        _lib.check(_lib.load().ngf_field_timing_read(self._live_handle(), C.byref(n), C.byref(a), C.byref(b)))
         return int(n.value), float(a.value), float(b.value)
 
     # ------------------------------------------------------------------ point-wise API parity
-    def _pts_call(self, fn_name, inputs, out_shapes, out_dtypes, *extra_before_out, extra_after=()):
-        raise NotImplementedError
-
     @torch.no_grad()
     def sample_ray(self, rays_o, rays_d, is_train=True, N_samples=-1, jitter=None):
         """Reference: Base.sample_ray (FieldBase.py:118-137).  -> (rays_pts [R,S,3], interpx [R,S],

@@ -55,6 +55,12 @@ class TriPlane(Base):
         d.dens_l1, d.dens_l2, d.dens_l3 = layers
         d.infoinv = 1
 
+    def _grad_parameters(self):
+        m, dm = self.rgb_decoder.mlp, self.density_decoder.mlp
+        return [self.plane_xy, self.plane_yz, self.plane_xz, None, None, None,
+                self.rgb_decoder.basis.weight, m[0].weight, m[0].bias, m[2].weight, m[2].bias, m[4].weight, m[4].bias,
+                dm[0].weight, dm[0].bias, dm[2].weight, dm[2].bias, dm[4].weight, dm[4].bias]
+
     def _set_switches(self, lib, h, infoinv=True, **_):
         _lib.check(lib.ngf_field_set_infoinv(h, int(bool(infoinv))))
 

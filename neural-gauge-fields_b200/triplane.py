@@ -63,6 +63,12 @@ class TriPlane(Base):
         d.dens_l1 = _lib.NgfLinear(w.data_ptr(), b.data_ptr(), 48, 1)
         d.infoinv = 0
 
+    def _grad_parameters(self):
+        m = self.rgb_decoder.mlp
+        return [self.plane_xy, self.plane_yz, self.plane_xz, self.gauge_xy, self.gauge_yz, self.gauge_xz,
+                self.rgb_decoder.basis.weight, m[0].weight, m[0].bias, m[2].weight, m[2].bias, m[4].weight, m[4].bias,
+                self.density_decoder.weight, self.density_decoder.bias]
+
     def _set_switches(self, lib, h, iteration=0, **_):
         # Field.py:58: the gauge offsets apply once iteration >= gauge_start (main.py:67 passes 30001 at eval)
         _lib.check(lib.ngf_field_set_gauge(h, int(iteration >= self.gauge_start)))
