@@ -121,6 +121,8 @@ typedef struct NgfStats {
   uint64_t samples_density; /* density evaluations: valid samples (bbox and alpha mask)    */
   uint64_t samples_colour;  /* colour-MLP evaluations: weight > weight_thres               */
   uint64_t mlp_tiles;       /* 128-sample colour-MLP tiles issued                          */
+  uint64_t direct_patches;  /* (32-sample group, plane) pairs whose taps did not fit a TMA patch and were gathered directly
+                               (of 12 per tile; TMA-staged colour kernel only) */
 } NgfStats;
 
 typedef struct NgfField_* NgfField;

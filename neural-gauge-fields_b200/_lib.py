@@ -63,7 +63,7 @@ class NgfCamera(C.Structure):
 
 class NgfStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("samples_in_box", C.c_uint64), ("samples_density", C.c_uint64),
-                ("samples_colour", C.c_uint64), ("mlp_tiles", C.c_uint64)]
+                ("samples_colour", C.c_uint64), ("mlp_tiles", C.c_uint64), ("direct_patches", C.c_uint64)]
 
 
 # name -> (restype, argtypes); every symbol include/ngf_b200.h declares

@@ -1,5 +1,6 @@
 // ngf_abi.cu — the C ABI of libngf_b200.so (include/ngf_b200.h): handle management, parameter packing, render
 // entry points.  Host code only; kernels live in ngf_kernels.cu.
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -92,7 +93,7 @@ static void free_all(NgfField_* h) {
   for (int i = 0; i < 3; ++i) cudaFree(h->dsum[i]);
   cudaFree(h->occ); cudaFree(h->occ2); cudaFree(h->occ_coarse);
   cudaFree(h->dmlp); cudaFree(h->w1p); cudaFree(h->w2p); cudaFree(h->tail);
-  cudaFree(h->raw_w); cudaFree(h->raw_dw);
+  cudaFree(h->raw_w); cudaFree(h->raw_dw); cudaFree(h->tmaps);
   ngf_train_free(h->train);
   h->train = nullptr;
   cudaFree(h->acc_ws); cudaFree(h->counters); cudaFree(h->queue);
@@ -169,6 +170,53 @@ static cudaError_t fetch(std::vector<float>& dst, const float* src, size_t n) {
 // (k/8)*rows*8 + r*8 + (k%8)   (in halves)
 static void put_kmajor(std::vector<__half>& dst, int rows, int r, int k, float v) {
   dst[(size_t)(k / 8) * rows * 8 + (size_t)r * 8 + (k % 8)] = __float2half_rn(v);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// Tensor maps over the channels-last fp16 appearance planes [H][W][48] with boxes of 48 channels x kBox x kBox texels
+// (ngf_colour_tma.cuh).  Failure is not an error: the colour kernel then keeps the direct gather.
+static void build_tensor_maps(NgfField_* h) {
+  h->dev.tmap = nullptr;
+  if (h->dev.variant != 0) return;
+  // opt-in: on the 800x800 / 256^2-plane workload only ~36 % of the (group, plane) taps fit a 5x5 patch (86 % would fit
+  // 8x8, which does not fit shared memory twice per SM), and the kernel is slower than the direct gather
+  const char* e = getenv("NGF_COLOUR_TMA");
+  if (!(e && e[0] == '1')) return;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return;
+  alignas(64) CUtensorMap maps[3];
+  for (int i = 0; i < 3; ++i) {
+    const PlaneDev& P = h->dev.plane[i];
+    const cuuint64_t dims[3] = {48, (cuuint64_t)P.W, (cuuint64_t)P.H};
+    const cuuint64_t strides[2] = {96, (cuuint64_t)P.W * 96};
+    const cuuint32_t box[3] = {48, 5, 5};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(P.app), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return;
+  }
+  if (!h->tmaps && cudaMalloc(&h->tmaps, sizeof(maps)) != cudaSuccess) { cudaGetLastError(); h->tmaps = nullptr; return; }
+  if (cudaMemcpy(h->tmaps, maps, sizeof(maps), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); return; }
+  h->dev.tmap = h->tmaps;
 }
 
 static int pack_params(NgfField_* h, const NgfFieldDesc* d, bool allocate) {
@@ -383,6 +431,7 @@ static int pack_params(NgfField_* h, const NgfFieldDesc* d, bool allocate) {
     CU(cudaMalloc(reinterpret_cast<void**>(&h->counters), kCounterBytes));
     CU(cudaMemset(h->counters, 0, kCounterBytes));
   }
+  build_tensor_maps(h);
   CU(cudaDeviceSynchronize());
   return NGF_OK;
 }
@@ -865,11 +914,12 @@ int ngf_field_set_infoinv(NgfField h, int32_t on) {
 int ngf_field_stats(NgfField h, NgfStats* out, void* stream) {
   if (!h || !out) return fail(NGF_EINVAL, "NULL argument");
   DeviceGuard g(h->device);
-  unsigned long long s[4];
+  unsigned long long s[5];
   CU(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
   CU(cudaMemcpy(s, h->counters + 2, sizeof(s), cudaMemcpyDeviceToHost));
   out->rays = 0;
   out->samples_in_box = s[0]; out->samples_density = s[1]; out->samples_colour = s[2]; out->mlp_tiles = s[3];
+  out->direct_patches = s[4];
   return NGF_OK;
 }
 

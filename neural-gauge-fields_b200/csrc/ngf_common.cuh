@@ -65,6 +65,9 @@ struct FieldDev {
   const __half* w1p;
   const __half* w2p;
   const float* tail;
+  // three 128-byte TMA tensor maps (device memory) over the appearance planes [H][W][48] fp16 with 48 x 5 x 5 boxes, or
+  // nullptr (InfoInv; driver without cuTensorMapEncodeTiled): ngf_colour_tma.cuh
+  const void* tmap;
 };
 
 // Pinhole camera for on-device ray generation (TriPlane/dataLoader/ray_utils.py:24-42,66-87 + blender.py:46-52)

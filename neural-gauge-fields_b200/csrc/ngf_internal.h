@@ -47,7 +47,7 @@ struct RenderArgs {
   unsigned int* queue_count;   // zero-initialised: colour work items appended so far
   QEntry* queue;               // [queue_cap] colour work items (march kernel -> colour kernel)
   unsigned int queue_cap;
-  unsigned long long* stats;   // [4]: samples_in_box, samples_density, samples_colour, mlp_tiles (accumulated)
+  unsigned long long* stats;   // [5]: samples_in_box, samples_density, samples_colour, mlp_tiles, direct_patches (accumulated)
   int n_tiles;
 };
 

@@ -19,7 +19,7 @@
 #include <cstdlib>
 
 #include "ngf_handle.h"
-#include "ngf_mlp.cuh"
+#include "ngf_colour_tma.cuh"
 
 namespace ngf {
 
@@ -302,7 +302,31 @@ cudaError_t launch_march(const FieldDev& f, const RenderArgs& a, int num_sms, cu
   return f.variant == 0 ? launch_march_t<0, false>(f, a, num_sms, st) : launch_march_t<1, false>(f, a, num_sms, st);
 }
 
+// TriPlane colour kernel with the TMA-staged gather (ngf_colour_tma.cuh)
+static cudaError_t launch_colour_tma(const FieldDev& f, const RenderArgs& a, int num_sms, cudaStream_t st) {
+  auto kern = ngf_colour_tma_kernel;
+  const size_t smem = TmaSmem::offEnd;
+  static PerDevice<int> occ_of;
+  bool fresh = false;
+  int& occ = *occ_of.get(&fresh);
+  if (fresh || occ == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { occ_of.retry(); return e; }
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    occ = blocks_per_sm(reinterpret_cast<const void*>(kern), kThreads, smem);
+    if (occ > 2) occ = 2;
+  }
+  long long grid = (long long)num_sms * occ;
+  long long worst = ((long long)a.queue_cap + kTileM - 1) / kTileM;
+  if (grid > worst) grid = worst;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, kThreads, smem, st>>>(f, a);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_colour(const FieldDev& f, const RenderArgs& a, int mlp_impl, int num_sms, cudaStream_t st) {
+  if (f.variant == 0 && mlp_impl == 0 && f.tmap) return launch_colour_tma(f, a, num_sms, st);
   if (f.variant == 0) return mlp_impl == 0 ? launch_colour_t<0, 0>(f, a, num_sms, st) : launch_colour_t<0, 1>(f, a, num_sms, st);
   return mlp_impl == 0 ? launch_colour_t<1, 0>(f, a, num_sms, st) : launch_colour_t<1, 1>(f, a, num_sms, st);
 }

@@ -257,6 +257,10 @@ __device__ __forceinline__ uint4 blend8h(const __half* __restrict__ base, int ch
 // ----------------------------------------------------------------------------------------------------------
 // q: the tile's 128 work items; A: the layer-1 operand; tapbuf: 12 KiB of scratch (TriPlane only); tid: 0..NT-1 within the
 // NT threads (256 or 384) that share the work; sync(): a barrier over exactly those threads.
+template <class L, int F>
+__device__ __forceinline__ void mlp_view_columns(const QEntry* __restrict__ q, uint8_t* A, int tid,
+                                                 const float* __restrict__ dir, int dir_stride, const CamDev* cam);
+
 template <int V, int NT, class Sync>
 __device__ __forceinline__ void mlp_gather_at(const FieldDev& f, const QEntry* __restrict__ q, uint8_t* A, TapsH* tapbuf,
                                               int tid, const float* __restrict__ dir, int dir_stride, const CamDev* cam,
@@ -354,7 +358,14 @@ __device__ __forceinline__ void mlp_gather_at(const FieldDev& f, const QEntry* _
       }
     }
   }
-  // view-direction columns F..F+15: [d(3), sin(d_k*2^j) (6), cos (6), 1]  (networks.py:27-29, 205-216)
+  mlp_view_columns<L, F>(q, A, tid, dir, dir_stride, cam);
+}
+
+// view-direction columns F..F+15 of the layer-1 operand: [d(3), sin(d_k*2^j) (6), cos (6), 1]  (networks.py:27-29, 205-216)
+template <class L, int F>
+__device__ __forceinline__ void mlp_view_columns(const QEntry* __restrict__ q, uint8_t* A, int tid,
+                                                 const float* __restrict__ dir, int dir_stride, const CamDev* cam) {
+  constexpr uint32_t head = 0;
   if (tid < kTileM) {
     const int m = tid;
     const QEntry& e = q[(head + m) & (kQueueCap - 1)];
@@ -404,17 +415,16 @@ __device__ __forceinline__ void mlp_gather(const FieldDev& f, uint8_t* smem, uin
                    [] { __syncthreads(); });
 }
 
-// ----------------------------------------------------------------------------------------------------------
-// One MLP tile.  All 256 threads call it with the same arguments; `phase` is the running mbarrier parity
-// (register, uniform).  Output: ATOMIC -> atomicAdd(out[id*3+c], w*rgb_c);  else out[id*3+c] = rgb_c.
-// The caller guarantees a __syncthreads() between the last write to the queue slots and this call; the function
-// ends with a __syncthreads().
-// ----------------------------------------------------------------------------------------------------------
-template <int V, int IMPL, bool ATOMIC>
-__device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint32_t head, uint32_t& phase,
-                                         const float* __restrict__ dir, int dir_stride, float* __restrict__ out,
-                                         const CamDev* cam = nullptr) {
-  using L = MlpSmem<V>;
+struct NoBetween {
+  __device__ __forceinline__ void operator()() const {}
+};
+
+// The layers of one MLP tile, after the layer-1 operand has been written to shared memory (layout L: MlpSmem<V> or the
+// TMA-staged colour kernel's).  `between` is called by every thread after the layer-1 MMAs have been issued and before
+// their completion is awaited (work that should hide under the tensor core, e.g. prefetching the next tile).
+template <class L, int IMPL, bool ATOMIC, class Between>
+__device__ __forceinline__ void mlp_layers(uint8_t* smem, uint32_t head, uint32_t& phase, float* __restrict__ out,
+                                           Between between) {
   constexpr int NKC = L::NKC;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = (warp & 3) * 32 + lane;        // TMEM lane == tile row handled by this thread
@@ -423,8 +433,6 @@ __device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint3
   const float* tail = reinterpret_cast<const float*>(smem + L::offTail);
   uint8_t* H = smem + L::offH;
   float acc[32];
-
-  mlp_gather<V>(f, smem, head, dir, dir_stride, cam);
 
   if (IMPL == 0) {
     fence_async_smem();
@@ -442,12 +450,14 @@ __device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint3
                  idesc, j > 0);
       umma_commit(&ctl->bar);
     }
+    between();
     mbar_wait(&ctl->bar, phase);
     phase ^= 1u;
     tc_fence_after();
     tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + chalf * 32, acc);
   } else {
     __syncthreads();
+    between();
     // CUDA-core layer 1 with the same fp16 operands
     const uint8_t* A = smem + L::offA;
     const uint8_t* W1 = smem + L::offW1;
@@ -565,6 +575,18 @@ __device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint3
     }
   }
   __syncthreads();
+}
+
+// One MLP tile.  All 256 threads call it with the same arguments; `phase` is the running mbarrier parity
+// (register, uniform).  Output: ATOMIC -> atomicAdd(out[id*3+c], w*rgb_c);  else out[id*3+c] = rgb_c.
+// The caller guarantees a __syncthreads() between the last write to the queue slots and this call; the function
+// ends with a __syncthreads().
+template <int V, int IMPL, bool ATOMIC>
+__device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint32_t head, uint32_t& phase,
+                                         const float* __restrict__ dir, int dir_stride, float* __restrict__ out,
+                                         const CamDev* cam = nullptr) {
+  mlp_gather<V>(f, smem, head, dir, dir_stride, cam);
+  mlp_layers<MlpSmem<V>, IMPL, ATOMIC>(smem, head, phase, out, NoBetween{});
 }
 
 }  // namespace ngf

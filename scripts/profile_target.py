@@ -47,8 +47,9 @@ else:
     else:
         synth.load_into(f, st, synth.occupancy_volume("hull"), ngf_b200.AlphaGridMask)
     fwd = dict(iteration=30001)
-rays = [synth.config_rays("C2", p).to(dev) for p in range(2)]
+# the bench's workload: 16 poses in rotation (246 MB of rays > L2), so a captured launch reads its rays from HBM
+rays = [synth.config_rays("C2", p).to(dev) for p in range(16)]
 for i in range(n):
-    f(rays[i % 2], white_bg=True, N_samples=192, image_width=800, **fwd)
+    f(rays[i % 16], white_bg=True, N_samples=192, image_width=800, **fwd)
 torch.cuda.synchronize()
 print(regime, f.last_stats())

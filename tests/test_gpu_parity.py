@@ -266,6 +266,19 @@ def test_render_split_into_ray_batches_by_queue_budget():
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
 
 
+def test_colour_kernel_with_tma_staged_gather():
+    """The opt-in TMA-staged colour kernel (NGF_COLOUR_TMA=1, csrc/ngf_colour_tma.cuh: cp.async.bulk.tensor boxes of plane
+    texels per 32-sample group, prefetched one tile ahead) against every TriPlane render golden."""
+    import subprocess
+    import sys
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NGF_COLOUR_TMA="1")
+    res = subprocess.run([sys.executable, os.path.join(root, "scripts", "check_colour_tma.py")], env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+
+
 @pytest.mark.parametrize("name", [c.name for c in K.TRAIN_CASES])
 def test_train_forward_matches_reference_golden(name):
     """forward(is_train=True), forward only: jittered sampling (FieldBase.py:128-130) and the background coin
