@@ -529,7 +529,13 @@ int ngf_render_dev(NgfField h, const float* rays, long long n_rays, int ray_stri
   if (per > n_rays) per = n_rays;
   long long want = per * S;
   if (want > 0xfffffff0ll) { per = 0xfffffff0ll / S / unit * unit; want = per * S; }
-  int rc = ensure_queue(queue, queue_cap, want, st);
+  // InfoInv: the three-phase march keeps 192 bytes of state per ray (+ 64) behind the queue, in the same allocation
+  static int ii_phased = -1;
+  // opt-in (NGF_INFOINV_PHASED=1): parity-green but slower on B200 than the in-march MLP — 10 rounds x 4 grid barriers of
+  // ~12 us each and a per-lane MLP that is latency-bound even at full lane occupancy (profiles/r02_infoinv_phased_trace.txt)
+  if (ii_phased < 0) { const char* e = getenv("NGF_INFOINV_PHASED"); ii_phased = e && e[0] == '1' ? 1 : 0; }
+  const long long ii_items = (h->dev.variant == 1 && ii_phased) ? per * 6 + 2 : 0;      // in 32-byte queue items
+  int rc = ensure_queue(queue, queue_cap, want + ii_items, st);
   if (rc) return rc;
   for (long long s0 = 0; s0 < n_rays; s0 += per) {
     const long long n = (n_rays - s0) < per ? (n_rays - s0) : per;
@@ -552,6 +558,7 @@ int ngf_render_dev(NgfField h, const float* rays, long long n_rays, int ray_stri
     a.queue_count = counters + 1;
     a.queue = *queue;
     a.queue_cap = (unsigned int)(n * S < want ? n * S : want);
+    a.ii_ws = ii_items ? static_cast<void*>(*queue + want) : nullptr;
     a.stats = reinterpret_cast<unsigned long long*>(counters + 2);
     CU(cudaMemsetAsync(counters, 0, s0 == 0 ? kCounterBytes : 8, st));   // first batch also clears the statistics
     const bool timed = h->ev_used + 3 <= (int)h->ev.size();

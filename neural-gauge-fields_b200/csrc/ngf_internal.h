@@ -47,6 +47,7 @@ struct RenderArgs {
   unsigned int* queue_count;   // zero-initialised: colour work items appended so far
   QEntry* queue;               // [queue_cap] colour work items (march kernel -> colour kernel)
   unsigned int queue_cap;
+  void* ii_ws;                 // InfoInv: workspace of the three-phase march (ngf_infoinv_march.cuh), 192 B per ray + 64 B
   unsigned long long* stats;   // [5]: samples_in_box, samples_density, samples_colour, mlp_tiles, direct_patches (accumulated)
   int n_tiles;
 };

@@ -20,6 +20,7 @@
 
 #include "ngf_handle.h"
 #include "ngf_colour_tma.cuh"
+#include "ngf_infoinv_march.cuh"
 
 namespace ngf {
 
@@ -297,7 +298,40 @@ static cudaError_t launch_colour_t(const FieldDev& f, const RenderArgs& a, int n
   return cudaGetLastError();
 }
 
+// InfoInv: three-phase cooperative march (ngf_infoinv_march.cuh).  a.ii_ws: 192 bytes per ray + 64.
+template <bool JIT>
+static cudaError_t launch_infoinv_march_t(const FieldDev& f, const RenderArgs& a, int num_sms, cudaStream_t st) {
+  auto kern = ngf_infoinv_march_kernel<JIT>;
+  const size_t smem = ((kDmlpFloats * 4 + 127) / 128) * 128;
+  static PerDevice<int> occ_of;
+  bool fresh = false;
+  int& occ = *occ_of.get(&fresh);
+  if (fresh || occ == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { occ_of.retry(); return e; }
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kIiThreads, smem);
+    if (e != cudaSuccess || n < 1) { occ_of.retry(); return e != cudaSuccess ? e : cudaErrorLaunchOutOfResources; }
+    occ = n;
+  }
+  uint8_t* base = static_cast<uint8_t*>(a.ii_ws);
+  const size_t R = (size_t)a.n_rays;
+  IiWs ws;
+  ws.counts = reinterpret_cast<unsigned int*>(base);
+  ws.ray = reinterpret_cast<IiRay*>(base + 64);
+  ws.sample = reinterpret_cast<IiSample*>(base + 64 + R * 32);
+  ws.list[0] = reinterpret_cast<int*>(base + 64 + R * 160);
+  ws.list[1] = ws.list[0] + R;
+  ws.hit = ws.list[1] + R;
+  dim3 grid((unsigned)(num_sms * occ)), block(kIiThreads);
+  void* args[] = {const_cast<FieldDev*>(&f), const_cast<RenderArgs*>(&a), &ws};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), grid, block, args, smem, st);
+  NGF_COUNT_LAUNCH();
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 cudaError_t launch_march(const FieldDev& f, const RenderArgs& a, int num_sms, cudaStream_t st) {
+  if (f.variant == 1 && a.ii_ws) return a.jitter ? launch_infoinv_march_t<true>(f, a, num_sms, st) : launch_infoinv_march_t<false>(f, a, num_sms, st);
   if (a.jitter) return f.variant == 0 ? launch_march_t<0, true>(f, a, num_sms, st) : launch_march_t<1, true>(f, a, num_sms, st);
   return f.variant == 0 ? launch_march_t<0, false>(f, a, num_sms, st) : launch_march_t<1, false>(f, a, num_sms, st);
 }

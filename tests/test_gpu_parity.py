@@ -279,6 +279,18 @@ def test_colour_kernel_with_tma_staged_gather():
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
 
 
+def test_infoinv_phased_march():
+    """The opt-in three-phase cooperative march of the InfoInv field (NGF_INFOINV_PHASED=1) against the InfoInv goldens."""
+    import subprocess
+    import sys
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NGF_INFOINV_PHASED="1")
+    res = subprocess.run([sys.executable, os.path.join(root, "scripts", "check_infoinv_phased.py")], env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+
+
 @pytest.mark.parametrize("name", [c.name for c in K.TRAIN_CASES])
 def test_train_forward_matches_reference_golden(name):
     """forward(is_train=True), forward only: jittered sampling (FieldBase.py:128-130) and the background coin
