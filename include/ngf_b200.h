@@ -364,7 +364,7 @@ int ngf_comm_wait(NgfComm c, uint64_t ticket);
  * NeuTex.forward (model/model.py:27-59) = cube_ray_generation (model/renderer.py:79-141) -> GeometryMlpDecoder
  * (model/decoder.py:201-237) -> GaugeTransform (model/gauge_fields.py:8-74) -> TextureMlpDecoder
  * (model/decoder.py:11-121) -> ray_march / simple_tone_map (model/renderer.py:4-11,176-247), as called per 1024-ray
- * chunk by test.py:108-114 through Model.test (model/model.py:362-373).  primitive_type = 'square'.
+ * chunk by test.py:108-114 through Model.test (model/model.py:362-373).  primitive_type 'square' or 'sphere'.
  * ===================================================================================================== */
 typedef struct NgfNeutexDesc {
   NgfLinear geometry[12];   /* net_geometry_decoder.block.{0,2,...,22}: 63->256, 10 x 256->256, 256->1          */
@@ -376,6 +376,9 @@ typedef struct NgfNeutexDesc {
   float jitter;             /* 0.05, hard-coded at model/model.py:30                                             */
   const float* texture;     /* TextureMlpDecoder.cubemap_ after load_square: [h][w][c] fp32 in [0,1], or NULL    */
   int32_t tex_h, tex_w, tex_c;
+  int32_t primitive;        /* opt.primitive_type: 0 = 'square' (gauge 128->2, uv = tanh, tex_block1[0] 42->256),
+                               1 = 'sphere' (gauge 128->3, uv = normalize, tex_block1[0] 63->256; gauge_fields.py:53-56,71-74,
+                               model.py:22); the sphere's edited-texture (cube map) branch is not built */
 } NgfNeutexDesc;
 
 typedef struct NgfNeutex_* NgfNeutex;

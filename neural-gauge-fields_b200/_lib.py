@@ -53,7 +53,7 @@ class NgfNeutexDesc(C.Structure):
     _fields_ = [("geometry", NgfLinear * 12), ("gauge", NgfLinear * 5), ("tex_block1", NgfLinear * 6),
                 ("tex_color1", NgfLinear), ("tex_block2", NgfLinear * 5), ("sample_num", C.c_int32),
                 ("jitter", C.c_float), ("texture", C.c_void_p), ("tex_h", C.c_int32), ("tex_w", C.c_int32),
-                ("tex_c", C.c_int32)]
+                ("tex_c", C.c_int32), ("primitive", C.c_int32)]
 
 
 class NgfCamera(C.Structure):

@@ -692,15 +692,31 @@ __global__ void __launch_bounds__(kThreads, 1) ntx_mlp_kernel(const __grid_const
         mark_done();
         signal_a();
       }
-      float uvr[2] = {0.f, 0.f};
-      stage_head(kHeadGauge, 256, kHeadGaugeB, 2);
-      wait_acc();
-      epilogue_head<128, 0, false, 2>(hw, taddr, A, row, ch, uvr);
-      mark_done();
-      combine(uvr, 2);
-      float uv[2] = {tanhf(uvr[0] + hw[kHwBias]), tanhf(uvr[1] + hw[kHwBias + 1])};
-      // ---- texture block1: [uv, PE(uv,10)] -> 256 -> 5 x 256 (LeakyReLU 0.2); color1 256 -> 3 softplus   (decoder.py:56-78)
-      write_encoding<2, 10, 6, false, false, false>(A, row, ch, uv);
+      float uvr[3] = {0.f, 0.f, 0.f}, uv[3];
+      if (net.sphere) {
+        // sphere primitive: 3 outputs, uv = F.normalize(out) = out / max(|out|, 1e-12)   (gauge_fields.py:71-74)
+        stage_head(kHeadGauge, 384, kHeadGaugeB, 3);
+        wait_acc();
+        epilogue_head<128, 0, false, 3>(hw, taddr, A, row, ch, uvr);
+        mark_done();
+        combine(uvr, 3);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) uvr[k] += hw[kHwBias + k];
+        const float nrm = fmaxf(sqrtf(uvr[0] * uvr[0] + uvr[1] * uvr[1] + uvr[2] * uvr[2]), 1e-12f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) uv[k] = uvr[k] / nrm;
+        // ---- texture block1: [uv3, PE(uv3,10)] (63) -> 256 -> ...   (model.py:22: uv_dim 3)
+        write_encoding<3, 10, 8, false, false, false>(A, row, ch, uv);
+      } else {
+        stage_head(kHeadGauge, 256, kHeadGaugeB, 2);
+        wait_acc();
+        epilogue_head<128, 0, false, 2>(hw, taddr, A, row, ch, uvr);
+        mark_done();
+        combine(uvr, 2);
+        uv[0] = tanhf(uvr[0] + hw[kHwBias]); uv[1] = tanhf(uvr[1] + hw[kHwBias + 1]); uv[2] = 0.f;
+        // ---- texture block1: [uv, PE(uv,10)] -> 256 -> 5 x 256 (LeakyReLU 0.2); color1 256 -> 3 softplus   (decoder.py:56-78)
+        write_encoding<2, 10, 6, false, false, false>(A, row, ch, uv);
+      }
       write_encoding<3, 6, 6, false, false, true>(smem + offA2, row, ch, dir);
       signal_a();
       for (int r = 0; r < 5; ++r) {
@@ -788,20 +804,20 @@ __device__ __forceinline__ RaySetup ray_setup(const RenderArgsN& a, long long ra
   return r;
 }
 
-// seg_i = dt + dt*jitter*(U_i - 0.5) (renderer.py:111-118); dt = 2/64, dt*jitter is a Python double cast to fp32
-__device__ __forceinline__ float seg_len(float dj, float u) { return __fadd_rn(0.03125f, __fmul_rn(dj, __fsub_rn(u, 0.5f))); }
+// seg_i = dt + dt*jitter*(U_i - 0.5) (renderer.py:111-118); dt = 2/S and dt*jitter are Python doubles cast to fp32
+__device__ __forceinline__ float seg_len(float dt, float dj, float u) { return __fadd_rn(dt, __fmul_rn(dj, __fsub_rn(u, 0.5f))); }
 
 template <bool EMIT>
-__device__ __forceinline__ unsigned long long walk_ray(const RenderArgsN& a, const RaySetup& r, long long ray, float dj,
-                                                       float4* dst) {
+__device__ __forceinline__ unsigned long long walk_ray(const RenderArgsN& a, const RaySetup& r, long long ray, int S, float dt,
+                                                       float dj, float4* dst) {
   unsigned long long mask = 0ull;
   double run = 0.0;
   float e_prev = __fadd_rn(r.t, 0.f);
   int n = 0;
 #pragma unroll 4
-  for (int i = 0; i < kS; ++i) {
-    const float u = a.noise ? __ldg(a.noise + ray * kS + i) : 0.5f;
-    run += (double)seg_len(dj, u);
+  for (int i = 0; i < S; ++i) {
+    const float u = a.noise ? __ldg(a.noise + ray * S + i) : 0.5f;
+    run += (double)seg_len(dt, dj, u);
     const float e = __fadd_rn(r.t, (float)run);
     const float mid = __fmul_rn(__fadd_rn(e_prev, e), 0.5f);
     e_prev = e;
@@ -825,12 +841,13 @@ __global__ void __launch_bounds__(128) ntx_raygen_kernel(const __grid_constant__
   const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool live = ray < a.n_rays;
-  const float dj = (float)(0.03125 * (double)net.jitter);
+  const float dj = net.dj, dt = net.dt;
+  const int S = net.S;
   RaySetup r{};
   unsigned long long mask = 0ull;
   if (live) {
     r = ray_setup(a, ray);
-    mask = walk_ray<false>(a, r, ray, dj, nullptr);
+    mask = walk_ray<false>(a, r, ray, S, dt, dj, nullptr);
     a.valid_mask[ray] = mask;
   }
   // warp prefix sum of the per-ray counts, one atomic per warp
@@ -845,7 +862,7 @@ __global__ void __launch_bounds__(128) ntx_raygen_kernel(const __grid_constant__
   unsigned int base = 0;
   if (lane == 31 && total > 0) base = atomicAdd(a.counters, (unsigned int)total);
   base = __shfl_sync(0xffffffffu, base, 31);
-  if (cnt > 0) walk_ray<true>(a, r, ray, dj, a.work + base + (incl - cnt));
+  if (cnt > 0) walk_ray<true>(a, r, ray, S, dt, dj, a.work + base + (incl - cnt));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -855,14 +872,15 @@ __global__ void __launch_bounds__(128) ntx_march_kernel(const __grid_constant__ 
                                                         const __grid_constant__ RenderArgsN a) {
   const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (ray >= a.n_rays) return;
-  const float dj = (float)(0.03125 * (double)net.jitter);
+  const float dj = net.dj, dt = net.dt;
+  const int S = net.S;
   const unsigned long long mask = a.valid_mask[ray];
   double T = 1.0;                           // torch.cumprod on the CPU accumulates in double
   float col[3] = {0.f, 0.f, 0.f};
-  for (int i = 0; i < kS; ++i) {
+  for (int i = 0; i < S; ++i) {
     if (!((mask >> i) & 1ull)) continue;    // sigma * 0 -> opacity 0 -> weight 0, transmittance factor 1 + 1e-10 == 1.f
-    const float u = a.noise ? __ldg(a.noise + ray * kS + i) : 0.5f;
-    const float seg = seg_len(dj, u);
+    const float u = a.noise ? __ldg(a.noise + ray * S + i) : 0.5f;
+    const float seg = seg_len(dt, dj, u);
     const float4 s = a.sample_out[ray * kS + i];
     const float op = __fsub_rn(1.f, expf(-__fmul_rn(s.x, seg)));
     const float w = __fmul_rn(op, (float)T);

@@ -15,7 +15,7 @@
 namespace ngf {
 namespace ntx {
 
-constexpr int kS = 64;                 // samples per ray (dtu_test.sh: --sample_num 64); the kernels are built for it
+constexpr int kS = 64;                 // sample slots per ray in the workspaces (the in-cube mask is 64 bits): sample_num <= 64
 constexpr int kRows = 256;             // work items per MLP tile: two M=128 tcgen05 tiles sharing every weight chunk
 constexpr int kWorkerThreads = 512;    // two threads per tile row (TMEM lane): each owns half of the layer's columns
 constexpr int kWorkerWarps = kWorkerThreads / 32;
@@ -34,9 +34,9 @@ constexpr int kTraceWords = 25 * 4 + 64;   // NGF_NTX_DBG=4: per-layer stamps + 
 constexpr int kTraceLayer = 5;
 constexpr int kNumLayers = 25;         // MMA layers per tile: geometry 11, gauge 4, texture block1 6, block2 4
 
-// geometry head [256] | gauge head [2][128] | color1 [3][256] | block2 head [3][256] | biases 1 + 2 + 3 + 3
-constexpr int kHeadGeo = 0, kHeadGauge = 256, kHeadC1 = 512, kHeadB2 = 1280, kHeadGeoB = 2048, kHeadGaugeB = 2049,
-              kHeadC1B = 2051, kHeadB2B = 2054, kHeadFloats = 2060;
+// geometry head [256] | gauge head [2 or 3][128] | color1 [3][256] | block2 head [3][256] | biases 1 + 3 + 3 + 3
+constexpr int kHeadGeo = 0, kHeadGauge = 256, kHeadC1 = 768, kHeadB2 = 1536, kHeadGeoB = 2304, kHeadGaugeB = 2305,
+              kHeadC1B = 2308, kHeadB2B = 2311, kHeadFloats = 2316;
 
 struct LayerDesc {
   int K;                // K of the main A operand (multiple of 16)
@@ -63,6 +63,9 @@ struct NetDev {
   const float* texture;   // [h][w][c] edited texture or nullptr
   int tex_h, tex_w, tex_c;
   float jitter;
+  int S;                  // opt.sample_num (1..64; dtu_test.sh: 64)
+  float dt, dj;           // fp32(2 / S) and fp32((2 / S) * jitter): the Python doubles of renderer.py:111-118 as torch casts them
+  int sphere;             // 1: primitive_type 'sphere' (gauge_fields.py:55-56,71-74): 3 gauge outputs, uv = normalize(.)
   int dbg;                // NGF_NTX_DBG (profiling experiments only): 2 = skip MMA issue, 4 = record a timeline,
                           //          8 = skip the weight copies (ring stages are released without data)
   long long* trace;       // dbg & 4: [25 layers][4] clock64 stamps of CTA 0's first tile (a_ready seen, MMAs issued,

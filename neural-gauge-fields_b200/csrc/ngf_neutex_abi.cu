@@ -119,17 +119,23 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
   if (!out) return ngf_set_error(NGF_EINVAL, "out is NULL");
   *out = nullptr;
   if (!d) return ngf_set_error(NGF_EINVAL, "desc is NULL");
-  if (d->sample_num != kS) return ngf_set_error(NGF_EUNSUPPORTED, "sample_num=%d (kernels are built for %d)", d->sample_num, kS);
+  if (d->sample_num < 1 || d->sample_num > kS)
+    return ngf_set_error(NGF_EUNSUPPORTED, "sample_num=%d (1..%d: the in-cube mask of a ray is a 64-bit word)", d->sample_num, kS);
   int rc;
   for (int i = 0; i < 12; ++i) {
     const int in_dim = i == 0 ? 63 : 256, out_dim = i == 11 ? 1 : 256;
     if ((rc = check_lin(d->geometry[i], in_dim, out_dim, "geometry", i))) return rc;
   }
-  const int gi[5] = {63, 64, 128, 128, 128}, go[5] = {64, 128, 128, 128, 2};
+  if (d->primitive != 0 && d->primitive != 1) return ngf_set_error(NGF_EINVAL, "primitive=%d (0 square, 1 sphere)", d->primitive);
+  const int sphere = d->primitive;
+  if (sphere && d->texture)
+    return ngf_set_error(NGF_EUNSUPPORTED, "the edited-texture branch of the sphere primitive samples a cube map "
+                         "(decoder.py:96-98); only the square primitive's texture swap is built");
+  const int gi[5] = {63, 64, 128, 128, 128}, go[5] = {64, 128, 128, 128, sphere ? 3 : 2};
   for (int i = 0; i < 5; ++i)
     if ((rc = check_lin(d->gauge[i], gi[i], go[i], "gauge", i))) return rc;
   for (int i = 0; i < 6; ++i)
-    if ((rc = check_lin(d->tex_block1[i], i == 0 ? 42 : 256, 256, "tex_block1", i))) return rc;
+    if ((rc = check_lin(d->tex_block1[i], i == 0 ? (sphere ? 63 : 42) : 256, 256, "tex_block1", i))) return rc;
   if ((rc = check_lin(d->tex_color1, 256, 3, "tex_color1", 0))) return rc;
   for (int i = 0; i < 5; ++i)
     if ((rc = check_lin(d->tex_block2[i], i == 0 ? 295 : 256, i == 4 ? 3 : 256, "tex_block2", i))) return rc;
@@ -189,7 +195,7 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
   if (!rc) rc = head(d->geometry[11], kHeadGeo, kHeadGeoB);
   for (int i = 0; i < 4 && !rc; ++i) rc = add(d->gauge[i], i < 2 ? 64 : 128, 0, true);
   if (!rc) rc = head(d->gauge[4], kHeadGauge, kHeadGaugeB);
-  for (int i = 0; i < 6 && !rc; ++i) rc = add(d->tex_block1[i], i == 0 ? 48 : 256, 0, false);
+  for (int i = 0; i < 6 && !rc; ++i) rc = add(d->tex_block1[i], i == 0 ? (sphere ? 64 : 48) : 256, 0, false);
   if (!rc) rc = head(d->tex_color1, kHeadC1, kHeadC1B);
   for (int i = 0; i < 4 && !rc; ++i) rc = add(d->tex_block2[i], 256, i == 0 ? 48 : 0, false);
   if (!rc) rc = head(d->tex_block2[4], kHeadB2, kHeadB2B);
@@ -234,6 +240,10 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
   h->net.wstream = h->wstream; h->net.heads = h->heads;
   h->net.texture = h->texture; h->net.tex_h = d->tex_h; h->net.tex_w = d->tex_w; h->net.tex_c = d->tex_c;
   h->net.jitter = d->jitter;
+  h->net.S = d->sample_num;
+  h->net.dt = (float)(2.0 / d->sample_num);
+  h->net.dj = (float)((2.0 / d->sample_num) * (double)d->jitter);
+  h->net.sphere = sphere;
   { const char* e = getenv("NGF_NTX_DBG"); h->net.dbg = e ? atoi(e) : 0; }
   h->net.trace = nullptr;
   if (h->net.dbg & 4) {
@@ -281,7 +291,7 @@ static int ntx_render_dev(NgfNeutex_* h, const float* campos, const float* raydi
     const long long n = (n_rays - s0) < per ? (n_rays - s0) : per;
     RenderArgsN a{};
     a.campos = campos; a.raydir = raydir + s0 * 3; a.background = background;
-    a.noise = noise ? noise + s0 * kS : nullptr;
+    a.noise = noise ? noise + s0 * h->net.S : nullptr;
     a.n_rays = n;
     a.work = h->work; a.counters = h->counters; a.valid_mask = h->valid_mask; a.sample_out = h->sample_out;
     a.color = color + s0 * 3; a.transmittance = trans + s0;
@@ -344,7 +354,7 @@ int ngf_neutex_render_host(NgfNeutex h, const float* campos_host, const float* r
     NtxChunk& c = h->chunk[ci];
     cudaStreamWaitEvent(copy, done[ci], 0);               // buffers of this slot free again
     cudaMemcpyAsync(c.raydir, raydir_host + s * 3, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, copy);
-    if (noise_host) cudaMemcpyAsync(c.noise, noise_host + s * kS, (size_t)n * kS * sizeof(float), cudaMemcpyHostToDevice, copy);
+    if (noise_host) cudaMemcpyAsync(c.noise, noise_host + s * h->net.S, (size_t)n * h->net.S * sizeof(float), cudaMemcpyHostToDevice, copy);
     cudaEventRecord(up[ci], copy);
     cudaStreamWaitEvent(run, up[ci], 0);
     rc = ntx_render_dev(h, h->cam_bg, c.raydir, background_host ? h->cam_bg + 3 : nullptr, noise_host ? c.noise : nullptr, n,

@@ -1,5 +1,5 @@
 """Drop-in for the render path of the reference's ``UV-Mapping/model/model.py`` ``NeuTex`` module
-(``primitive_type='square'``), executing on hand-written sm_100a CUDA through ``libngf_b200.so``.
+(``primitive_type`` 'square' or 'sphere'), executing on hand-written sm_100a CUDA through ``libngf_b200.so``.
 
 Sub-modules keep the reference's names and parameter shapes so ``state_dict`` round-trips with ``strict=False``
 (the reference's own ``load_networks`` uses ``strict=False``, model/model.py:215-230):
@@ -39,7 +39,7 @@ class GeometryMlpDecoder(nn.Module):
 
 
 class GaugeNetwork(nn.Module):
-    """Parameters of gauge_fields.py:8-35 (63 -> 64 -> 128 -> 128 -> 128 -> 2)."""
+    """Parameters of gauge_fields.py:8-35 (63 -> 64 -> 128 -> 128 -> 128 -> 2 | 3)."""
 
     def __init__(self, input_dim=3, output_dim=2, mid_size=64, hidden_size=128, num_layers=2):
         super().__init__()
@@ -50,22 +50,25 @@ class GaugeNetwork(nn.Module):
 
 
 class GaugeTransform(nn.Module):
+    """gauge_fields.py:49-74: 'square' -> 2 outputs, uv = tanh; 'sphere' -> 3 outputs, uv = normalize."""
+
     def __init__(self, primitive_type="square"):
         super().__init__()
-        if primitive_type != "square":
-            raise NotImplementedError("only primitive_type='square' (uv = tanh) is built")
-        self.output_dim = 2
-        self.encoder = GaugeNetwork(3, 2)
+        if primitive_type not in ("square", "sphere"):
+            raise Exception("Unknown primitive type {}".format(primitive_type))          # as gauge_fields.py:57-58
+        self.primitive_type = primitive_type
+        self.output_dim = 2 if primitive_type == "square" else 3
+        self.encoder = GaugeNetwork(3, self.output_dim)
 
 
 class TextureMlpDecoder(nn.Module):
     """Parameters of decoder.py:11-36 (42 -> 256 -> 5 x 256; color1 256 -> 3; 295 -> 256 -> 3 x 256 -> 3)."""
 
-    def __init__(self, width=256, layers=(5, 3)):
+    def __init__(self, width=256, layers=(5, 3), uv_dim=2):
         super().__init__()
-        # Linear at even Sequential indices, as in the reference
+        # Linear at even Sequential indices, as in the reference; input = [uv, PE(uv, 10)] (uv_dim * 21)
         mods = []
-        for i, o in [(42, width)] + [(width, width)] * layers[0]:
+        for i, o in [(uv_dim * 21, width)] + [(width, width)] * layers[0]:
             mods += [nn.Linear(i, o), nn.LeakyReLU(0.2)]
         self.block1 = nn.Sequential(*mods)
         self.color1 = nn.Linear(width, 3)
@@ -84,11 +87,10 @@ class NeuTex(nn.Module):
     def __init__(self, opt=None, device="cuda"):
         super().__init__()
         self.opt = opt if opt is not None else SimpleNamespace(sample_num=64, primitive_type="square", target_texture="None")
-        if getattr(self.opt, "primitive_type", "square") != "square":
-            raise NotImplementedError("only primitive_type='square' is built")
+        prim = getattr(self.opt, "primitive_type", "square")
         self.net_geometry_decoder = GeometryMlpDecoder(pos_freqs=10, hidden_size=256, num_layers=10)
-        self.gauge_transform = GaugeTransform("square")
-        self.net_texture = TextureMlpDecoder()
+        self.gauge_transform = GaugeTransform(prim)
+        self.net_texture = TextureMlpDecoder(uv_dim=2 if prim == "square" else 3)          # model.py:22
         self._handle = None
         self._handle_sig = None
         self.to(device)
@@ -156,6 +158,7 @@ class NeuTex(nn.Module):
             d.tex_block2[i] = lin(m)
         d.sample_num = int(getattr(self.opt, "sample_num", 64))
         d.jitter = 0.05                                                   # model.py:30
+        d.primitive = 0 if self.gauge_transform.primitive_type == "square" else 1
         tex = self.net_texture.cubemap_
         if tex is not None:
             t = tex.to(dev).float().contiguous()

@@ -221,9 +221,11 @@ NEUTEX_LAYERS = {
 }
 
 
-def neutex_state(seed: int = 0, gain: float = 1.0) -> Dict[str, torch.Tensor]:
-    """state_dict (reference NeuTex parameter names, primitive_type='square') with xavier-uniform weights like the
-    reference's init_seq / init_weights (util.py:390-425) and small random biases."""
+def neutex_state(seed: int = 0, gain: float = 1.0, primitive: str = "square") -> Dict[str, torch.Tensor]:
+    """state_dict (reference NeuTex parameter names) with xavier-uniform weights like the reference's init_seq /
+    init_weights (util.py:390-425) and small random biases.  ``primitive='sphere'``: the gauge network ends in 3 outputs
+    (gauge_fields.py:55-56) and the texture network starts from [uv3, PE(uv3, 10)] = 63 inputs (model.py:22); those two
+    layers are drawn from their own generator so the 'square' state of the same seed is unchanged."""
     g = torch.Generator().manual_seed(seed)
     st: Dict[str, torch.Tensor] = {}
 
@@ -246,6 +248,12 @@ def neutex_state(seed: int = 0, gain: float = 1.0) -> Dict[str, torch.Tensor]:
     lin(f"{enc}.last_linear", 2, 128, 1.0)
     # a denser object in the middle of the cube so rays see structure: bias the density head
     st["net_geometry_decoder.block.22.bias"] = torch.tensor([1.5])
+    if primitive == "sphere":
+        g = torch.Generator().manual_seed(seed + 1000)
+        lin(f"{enc}.last_linear", 3, 128, 1.0)
+        lin("net_texture.block1.0", 256, 63, leaky)
+    elif primitive != "square":
+        raise ValueError(primitive)
     return {k: v.float().contiguous() for k, v in st.items()}
 
 

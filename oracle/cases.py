@@ -170,6 +170,8 @@ class NeutexCase:
     seed: int = 0
     gain: float = 1.0
     noise_seed: int = 11
+    sample_num: int = 64                 # opt.sample_num
+    primitive: str = "square"          # 'sphere': 3-d unit-vector uv (gauge_fields.py:55-56,71-74)
 
 
 NEUTEX_CASES = [
@@ -178,20 +180,22 @@ NEUTEX_CASES = [
     NeutexCase("neutex_nobg", pose=9, background=None, max_rays=777, noise_seed=4),
     NeutexCase("neutex_texture_rgb", pose=3, texture_channels=3, max_rays=1024),
     NeutexCase("neutex_texture_rgba", pose=7, texture_channels=4, max_rays=1024, background=(0.2, 0.4, 0.6)),
+    NeutexCase("neutex_sphere", pose=2, max_rays=1024, seed=3, primitive="sphere"),
+    NeutexCase("neutex_s48", pose=6, max_rays=768, seed=1, sample_num=48, noise_seed=9),
 ]
 NEUTEX_BY_NAME = {c.name: c for c in NEUTEX_CASES}
 
 
 @functools.lru_cache(maxsize=4)
-def _neutex_state(seed, gain):
-    return synth.neutex_state(seed, gain)
+def _neutex_state(seed, gain, primitive="square"):
+    return synth.neutex_state(seed, gain, primitive)
 
 
 def build_neutex_inputs(case: NeutexCase):
     """-> (state_dict, texture or None, campos [1,3], raydir [1,R,3], background [1,3] or None, noise [1,R,64])."""
-    state = _neutex_state(case.seed, case.gain)
+    state = _neutex_state(case.seed, case.gain, case.primitive)
     tex = synth.neutex_texture(channels=case.texture_channels) if case.texture_channels else None
     campos, raydir = synth.neutex_camera(case.pose, max_rays=case.max_rays)
     bg = None if case.background is None else torch.tensor([case.background], dtype=torch.float32)
-    noise = synth.neutex_noise(raydir.shape[1], seed=case.noise_seed)
+    noise = synth.neutex_noise(raydir.shape[1], samples=case.sample_num, seed=case.noise_seed)
     return state, tex, campos, raydir, bg, noise

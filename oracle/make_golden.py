@@ -170,9 +170,9 @@ def build_reference_neutex(case: K.NeutexCase):
     pkg = ref_loader.uvmapping_model()
     state, tex, campos, raydir, bg, noise = K.build_neutex_inputs(case)
     geo = ref_loader.quiet(pkg.decoder.GeometryMlpDecoder, pos_freqs=10, hidden_size=256, num_layers=10)
-    gt = pkg.gauge_fields.GaugeTransform("square")
-    texnet = ref_loader.quiet(pkg.decoder.TextureMlpDecoder, 3, 10, 6, uv_dim=2, layers=[5, 3], width=256, clamp=False,
-                              primitive_type="square", target_texture="None")
+    gt = pkg.gauge_fields.GaugeTransform(case.primitive)
+    texnet = ref_loader.quiet(pkg.decoder.TextureMlpDecoder, 3, 10, 6, uv_dim=2 if case.primitive == "square" else 3,
+                              layers=[5, 3], width=256, clamp=False, primitive_type=case.primitive, target_texture="None")
     for mod, prefix in ((geo, "net_geometry_decoder"), (gt, "gauge_transform"), (texnet, "net_texture")):
         mod.load_state_dict({k[len(prefix) + 1:]: v for k, v in state.items() if k.startswith(prefix + ".")}, strict=True)
     if tex is not None:
@@ -191,7 +191,7 @@ def make_neutex(case: K.NeutexCase) -> str:
         real_rand = torch.rand
         torch.rand = lambda *a, **k: nz.clone()
         try:
-            pos, seg, valid, _ = ren.cube_ray_generation(campos, rd, 64, jitter=0.05)
+            pos, seg, valid, _ = ren.cube_ray_generation(campos, rd, case.sample_num, jitter=0.05)
         finally:
             torch.rand = real_rand
         density = geo(pos)["density"][..., None]

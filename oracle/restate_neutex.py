@@ -75,7 +75,8 @@ def geometry(spec: NeuTexSpec, pts: torch.Tensor) -> torch.Tensor:
 
 
 def gauge(spec: NeuTexSpec, pts: torch.Tensor) -> torch.Tensor:
-    """-> uv [N,R,S,2] = tanh(GaugeNetwork([p, PE(p,10)]))."""
+    """-> uv [N,R,S,2] = tanh(GaugeNetwork([p, PE(p,10)])) for the square primitive, [N,R,S,3] = normalize(...) for the
+    sphere (gauge_fields.py:60-74); the primitive is read off the last layer's width."""
     st, e = spec.state, "gauge_transform.encoder"
     shape = pts.shape
     x = pts.reshape(shape[0], -1, 3)
@@ -84,7 +85,9 @@ def gauge(spec: NeuTexSpec, pts: torch.Tensor) -> torch.Tensor:
     for i in range(2):
         x = torch.relu(F.linear(x, st[f"{e}.linear_list.{i}.weight"], st[f"{e}.linear_list.{i}.bias"]))
     x = F.linear(x, st[f"{e}.last_linear.weight"], st[f"{e}.last_linear.bias"])
-    return torch.tanh(x.reshape(shape[:-1] + (2,)))
+    out_dim = st[f"{e}.last_linear.weight"].shape[0]
+    x = x.reshape(shape[:-1] + (out_dim,))
+    return torch.tanh(x) if out_dim == 2 else F.normalize(x, dim=-1)
 
 
 def sample_square(square: torch.Tensor, uv: torch.Tensor) -> torch.Tensor:

@@ -12,9 +12,12 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
-def _build(state, tex):
+def _build(state, tex, sample_num=64):
     import ngf_b200
-    m = ngf_b200.NeuTex(device="cuda")
+    from types import SimpleNamespace
+    sphere = state["gauge_transform.encoder.last_linear.weight"].shape[0] == 3
+    opt = SimpleNamespace(sample_num=sample_num, primitive_type="sphere" if sphere else "square", target_texture="None")
+    m = ngf_b200.NeuTex(opt, device="cuda")
     m.load_state_dict(state, strict=True)
     m.set_texture(tex)
     return m
@@ -25,7 +28,7 @@ def test_neutex_matches_reference_golden(name):
     case = K.NEUTEX_BY_NAME[name]
     gold = load_golden(name)
     state, tex, campos, raydir, bg, noise = K.build_neutex_inputs(case)
-    m = _build(state, tex)
+    m = _build(state, tex, case.sample_num)
     out = m(campos.cuda(), raydir.cuda(), None if bg is None else bg.cuda(), noise=noise.cuda())
     torch.cuda.synchronize()
     e_c = np.abs(out["color"].cpu().numpy() - gold["color"]).max()
