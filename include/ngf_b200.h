@@ -193,6 +193,12 @@ int ngf_field_backward(NgfField f, const float* rays_dev, int64_t n_rays, int32_
                        int32_t white_bg, const float* jitter_dev, const float* grad_rgb_dev, const NgfFieldGrads* grads,
                        void* stream);
 
+/* One Adam step (torch.optim.Adam without weight decay / amsgrad, the optimiser of TriPlane/main.py:237,300-302) over a flat
+ * fp32 parameter in one pass: exp_avg / exp_avg_sq are the optimiser state, `step` the 1-based step count.  The feature
+ * planes are 50 MB of parameters; torch's unfused step makes ~10 passes over them. */
+int ngf_adam_step(float* param_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n, double lr,
+                  double beta1, double beta2, double eps, int64_t step, void* stream);
+
 /*
  * Same through HOST buffers: H2D of the rays, render, D2H of rgb/depth, chunked and overlapped on internal
  * streams; returns after the results are in rgb_host/depth_host.  This is the call the reference-facing
@@ -290,6 +296,12 @@ int ngf_field_sigma_world(NgfField f, const float* pts_dev, int64_t n, int32_t u
  */
 int ngf_frame_post(const float* rgb_dev, const float* gt_dev, int64_t n_values, uint8_t* u8_dev, double* sse_dev,
                    void* stream);
+
+/* The depth image evaluation() writes next to every frame (TriPlane/main.py:102,168 -> visualize_depth_numpy,
+ * utils.py:32-47, with minmax = near_far): x = nan_to_num(depth); x = (x - min) / (max - min + 1e-8);
+ * cv2.applyColorMap((255 * x).astype(uint8), cv2.COLORMAP_JET) -> bgr_dev [n][3] uint8 (B, G, R as OpenCV returns). */
+int ngf_depth_colormap(const float* depth_dev, int64_t n, double min_depth, double max_depth, uint8_t* bgr_dev,
+                       void* stream);
 
 /*
  * Multi-GPU helpers (the reference has no distributed code).  Rays of a frame are dealt to

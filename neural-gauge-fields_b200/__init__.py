@@ -16,6 +16,7 @@ from .field_base import AlphaGridMask, Base  # noqa: F401
 from .triplane import TriPlane  # noqa: F401
 from .infoinv import TriPlane as InfoInvTriPlane  # noqa: F401
 from .neutex import NeuTex  # noqa: F401
-from .render import FrameComm, ShardedFrameRenderer, frame_post, renderer, render_frames, render_frame_sharded, shard_rays, unshard_frame  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
+from .render import FrameComm, ShardedFrameRenderer, frame_post, renderer, render_rays, render_frames, render_frame_sharded, shard_rays, unshard_frame, visualize_depth  # noqa: F401
 
 __version__ = "0.1.0"

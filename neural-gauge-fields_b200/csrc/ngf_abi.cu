@@ -1045,6 +1045,19 @@ int ngf_frame_post(const float* rgb_dev, const float* gt_dev, int64_t n_values, 
   return NGF_OK;
 }
 
+int ngf_depth_colormap(const float* depth_dev, int64_t n, double min_depth, double max_depth, uint8_t* bgr_dev,
+                       void* stream) {
+  if (!depth_dev || !bgr_dev) return fail(NGF_EINVAL, "NULL pointer");
+  if (n < 0) return fail(NGF_EINVAL, "negative count");
+  int dev = 0, sms = 148;
+  CU(cudaGetDevice(&dev));
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // numpy casts the Python scalars mi and (ma - mi + 1e-8) to the array's fp32
+  CU(launch_depth_colormap(depth_dev, n, (float)min_depth, (float)(max_depth - min_depth + 1e-8), bgr_dev, sms,
+                           reinterpret_cast<cudaStream_t>(stream)));
+  return NGF_OK;
+}
+
 int64_t ngf_shard_count(int64_t n_rays, int32_t block, int32_t rank, int32_t world) {
   if (n_rays < 0 || block < 1 || world < 1 || rank < 0 || rank >= world) return -1;
   const long long per_cycle = (long long)block * world;

@@ -82,6 +82,9 @@ cudaError_t launch_pack_dsum(const float* dens, long long hw, int DC, const floa
 cudaError_t launch_frame_post(const float* rgb, const float* gt, long long n, uint8_t* u8, double* sse, int num_sms,
                               cudaStream_t st);
 
+cudaError_t launch_depth_colormap(const float* depth, long long n, float mi, float den, uint8_t* bgr, int num_sms,
+                                  cudaStream_t st);
+
 // ray sharding
 cudaError_t launch_shard_gather(const float* src, long long n_rays, int width, int block, int rank, int world,
                                 float* dst, cudaStream_t st);

@@ -718,6 +718,42 @@ cudaError_t launch_frame_post(const float* rgb, const float* gt, long long n, ui
   return cudaGetLastError();
 }
 
+// Depth visualisation of evaluation() (TriPlane/main.py:102 -> utils.py:32-47 visualize_depth_numpy with minmax = near_far):
+//   x = nan_to_num(depth); x = (x - mi) / (ma - mi + 1e-8); u8 = (255 * x).astype(uint8); cv2.applyColorMap(u8, COLORMAP_JET)
+// in numpy's fp32 arithmetic (the Python scalars are cast to fp32), the float -> uint8 cast truncating like the host's.
+#include "ngf_jet_lut.h"
+__constant__ unsigned char c_jet_lut[256 * 3];
+__global__ void ngf_depth_colormap_kernel(const float* __restrict__ depth, long long n, float mi, float den,
+                                          uint8_t* __restrict__ bgr) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float x = depth[i];
+    if (isnan(x)) x = 0.f;
+    else if (isinf(x)) x = x > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
+    const float v = __fmul_rn(255.f, __fdiv_rn(__fsub_rn(x, mi), den));
+    const int idx = (int)v & 255;                          // cvttss2si + low byte, as numpy's astype(uint8) on the host
+    bgr[i * 3 + 0] = c_jet_lut[idx * 3 + 0];
+    bgr[i * 3 + 1] = c_jet_lut[idx * 3 + 1];
+    bgr[i * 3 + 2] = c_jet_lut[idx * 3 + 2];
+  }
+}
+
+cudaError_t launch_depth_colormap(const float* depth, long long n, float mi, float den, uint8_t* bgr, int num_sms,
+                                  cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  static PerDevice<int> lut_done;
+  bool fresh = false;
+  lut_done.get(&fresh);
+  if (fresh) {
+    cudaError_t e = cudaMemcpyToSymbol(c_jet_lut, kJetLutBgr, sizeof(kJetLutBgr));
+    if (e != cudaSuccess) { lut_done.retry(); return e; }
+  }
+  long long blocks = (n + 255) / 256;
+  if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+  ngf_depth_colormap_kernel<<<(unsigned)blocks, 256, 0, st>>>(depth, n, mi, den, bgr);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
 // ==========================================================================================================
 // Ray sharding: ray g belongs to rank (g / block) % world, local index
 // (g / (block*world)) * block + g % block.

@@ -24,6 +24,7 @@
 //                             gauge planes (compute_gauge backward, Field.py:53-75).
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -560,7 +561,40 @@ __global__ void ngf_bwd_dscatter_kernel(const __grid_constant__ FieldDev f, cons
 
 unsigned grid_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
+// One Adam step over a flat fp32 parameter (torch.optim.Adam, no weight decay, no amsgrad; TriPlane/main.py:237,300-302):
+//   m = b1 m + (1 - b1) g ; v = b2 v + (1 - b2) g^2 ; p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+// in torch's order of operations (lerp for m, addcmul for v, addcdiv for p), one pass over the four arrays.
+__global__ void ngf_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, long long n, float b1, float b2, float one_minus_b2, float step_size,
+                                float bc2_sqrt, float eps) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = m[i] + (gi - m[i]) * (1.f - b1);               // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * b2 + one_minus_b2 * gi * gi;            // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);                          // param.addcdiv_(exp_avg, denom, value=-step_size)
+  }
+}
+
 }  // namespace
+
+extern "C" int ngf_adam_step(float* param_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n,
+                             double lr, double beta1, double beta2, double eps, int64_t step, void* stream) {
+  if (!param_dev || !grad_dev || !exp_avg_dev || !exp_avg_sq_dev) return ngf_set_error(NGF_EINVAL, "NULL pointer");
+  if (n < 0 || step < 1) return ngf_set_error(NGF_EINVAL, "n=%lld step=%lld", (long long)n, (long long)step);
+  if (n == 0) return NGF_OK;
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ngf_adam_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      param_dev, grad_dev, exp_avg_dev, exp_avg_sq_dev, n, (float)beta1, (float)beta2, (float)(1.0 - beta2), (float)(lr / bc1),
+      (float)sqrt(bc2), (float)eps);
+  count_launch();
+  CU(cudaGetLastError());
+  return NGF_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // C ABI

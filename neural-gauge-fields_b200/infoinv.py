@@ -88,6 +88,15 @@ class TriPlane(Base):
         self._apply_alpha_kw(infoinv=infoinv)
         return self._rgb(xy, yz, xz, view_sampled)
 
+    # upstream TensoRF names listed by BASELINE.json's north_star (see triplane.py)
+    def compute_densityfeature(self, xyz_sampled, infoinv=True):
+        xy, yz, xz = self.transform(xyz_sampled)
+        return self.compute_density(xy, yz, xz, infoinv)
+
+    def compute_appfeature(self, xyz_sampled, viewdirs, infoinv=True):
+        xy, yz, xz = self.transform(xyz_sampled)
+        return self.compute_rgb(xy, yz, xz, viewdirs, infoinv)
+
     # Reference: InfoInv/models/Field.py:107-110
     def density_L1(self):
         return torch.mean(torch.abs(self.plane_xy)) + torch.mean(torch.abs(self.plane_yz)) \

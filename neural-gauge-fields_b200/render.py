@@ -23,6 +23,9 @@ def renderer(rays, field, chunk=4096, N_samples=-1, white_bg=True, is_train=Fals
     return out['rgb_map'], out['depth_map']
 
 
+render_rays = renderer          # the upstream TensoRF-style name BASELINE.json's north_star uses for the same call
+
+
 @torch.no_grad()
 def render_frames(frames, field, N_samples=-1, white_bg=True, image_width=0, depth=2, **fwd_kw):
     """Render a sequence of frames whose rays live in pinned CPU memory, as the reference's ``evaluation`` loop does
@@ -70,6 +73,23 @@ def frame_post(rgb_map, gt_rgb=None, want_u8=True):
     if sse is not None:
         psnr = -10.0 * math.log(float(sse.item()) / n) / math.log(10.0)
     return u8, psnr
+
+
+@torch.no_grad()
+def visualize_depth(depth_map, minmax=None):
+    """Device-side ``visualize_depth_numpy`` (TriPlane/utils.py:32-47; evaluation() calls it with near_far, main.py:102):
+    depth [H, W] CUDA fp32 -> (uint8 [H, W, 3] in OpenCV's B, G, R order, [mi, ma])."""
+    d = depth_map.contiguous().float()
+    if minmax is None:
+        x = torch.nan_to_num(d)
+        mi, ma = float(x[x > 0].min()), float(x.max())
+    else:
+        mi, ma = float(minmax[0]), float(minmax[1])
+    out = torch.empty(tuple(d.shape) + (3,), dtype=torch.uint8, device=d.device)
+    with torch.cuda.device(d.device):
+        _lib.check(_lib.load().ngf_depth_colormap(d.data_ptr(), d.numel(), mi, ma, out.data_ptr(), _cuda_stream_ptr(d.device)),
+                   "ngf_depth_colormap")
+    return out, [mi, ma]
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -93,6 +93,18 @@ class TriPlane(Base):
     def compute_rgb(self, xy, yz, xz, view_sampled):
         return self._rgb(xy, yz, xz, view_sampled)
 
+    # Names of the upstream TensoRF API that BASELINE.json's north_star lists; this reference renamed them
+    # (compute_density / compute_rgb, which already include feature2density and the rgb decoder).
+    def compute_densityfeature(self, xyz_sampled, iteration=30001):
+        """xyz_sampled: normalised coordinates [N,3] -> density [N] (compute_gauge + compute_density, Field.py:53-91)."""
+        xy, yz, xz = self.compute_gauge(xyz_sampled, iteration)
+        return self.compute_density(xy, yz, xz)
+
+    def compute_appfeature(self, xyz_sampled, viewdirs, iteration=30001):
+        """xyz_sampled [N,3] normalised, viewdirs [N,3] -> rgb [N,3] (compute_gauge + compute_rgb, Field.py:53-75,93-105)."""
+        xy, yz, xz = self.compute_gauge(xyz_sampled, iteration)
+        return self.compute_rgb(xy, yz, xz, viewdirs)
+
     # Reference: Field.py:108-114
     @torch.no_grad()
     def up_sampling(self, res):
