@@ -406,7 +406,12 @@ def main():
 
     # ---- second end-to-end figure: what evaluation_path needs (TriPlane/main.py:155-161) — a camera pose in, the
     # uint8 image out: rays generated on the device, uint8 conversion on the device, 1.92 MB D2H per frame
-    e2e_cam = camera_e2e(ngf_b200, synth, field, dev, args.steps) if world == 1 else None
+    if world == 1:
+        e2e_cam = camera_e2e(ngf_b200, synth, field, dev, args.steps)
+    elif sharded.comm is not None:
+        e2e_cam = camera_e2e_sharded(synth, sharded.comm, rank, world, args.steps, barrier, max_over_ranks)
+    else:
+        e2e_cam = None
 
     # ---- roofline of the dominant kernel, from CUDA events around each kernel of the pair (measured live above)
     pk = peaks()
@@ -553,6 +558,39 @@ def camera_e2e(ngf_b200, synth, field, dev, steps):
                    "out, 3 frames in flight"}
 
 
+def camera_e2e_sharded(synth, comm, rank, world, steps, barrier, max_over_ranks):
+    """The same job for a ray-sharded batch of `world` frames per step (ngf_field_render_sharded_camera_u8_host_async): every
+    rank gets the batch's poses (48 B per frame) from pinned host memory, renders its interleaved blocks with rays generated in
+    the march kernel, the rows are exchanged over peer memory and every rank downloads ONE gathered frame as uint8."""
+    steps = max(10, min(steps, 1000))
+    batches = [torch.stack([synth.look_at_c2w(*synth.pose_angles((p + j) % N_POSES)) for j in range(world)]).contiguous().pin_memory()
+               for p in range(N_POSES)]
+    u8_h = [torch.empty((RAYS_PER_FRAME, 3), dtype=torch.uint8).pin_memory() for _ in range(3)]
+    pend = []
+    def step(i):
+        pend.append(comm.submit_camera_host(batches[i % N_POSES], H, W, synth.FOCAL_800, u8_h[i % 3], first_row=rank * RAYS_PER_FRAME,
+                                            N_samples=S, white_bg=True, iteration=30001))
+        if len(pend) > 2:
+            comm.wait(pend.pop(0))
+    def drain():
+        while pend:
+            comm.wait(pend.pop(0))
+    for i in range(3):
+        step(i)
+    drain()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    drain()
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    return {"value": world * RAYS_PER_FRAME * steps / dt, "unit": "rays/s", "h2d_bytes_per_step": world * 48,
+            "d2h_bytes_per_step": RAYS_PER_FRAME * 3, "steps": steps,
+            "api": "ngf_field_render_sharded_camera_u8_host_async (C ABI): the batch's poses in, rays generated in the march "
+                   "kernel, peer-memory all-gather, one gathered frame per rank out as uint8, 3 batches in flight"}
+
+
 def dense_regime(ngf_b200, synth, dev, pk, dev_rays):
     """Same frame, fog field without alpha mask and weight threshold -1: every sample inside the box runs the colour
     MLP (SURVEY.md §8d "dense-MLP microbench").  Reports the tensor roofline of the same kernel."""
@@ -656,12 +694,13 @@ def infoinv_config(ngf_b200, synth, dev, pk, dev_rays, host, args):
 
 
 def neutex_config(ngf_b200, synth, dev, pk, args):
-    """BASELINE configs[3]: UV-Mapping NeuTex render, 600x800 rays x 64 samples, random-init networks of the reference's
-    shapes, synthetic DTU-like camera, explicit jitter noise."""
+    """BASELINE configs[3]: UV-Mapping NeuTex test render of DTU scan83, camera 33 (the cameras ship with the reference and
+    are kept in neural-gauge-fields_b200/data/scan83_cameras.npz), 600x800 rays x 64 samples, random-init networks of the
+    reference's shapes (no checkpoint exists offline), explicit jitter noise."""
     m = ngf_b200.NeuTex(device=dev)
     nstate = synth.neutex_state(0)
     m.load_state_dict(nstate)
-    campos, raydir = synth.neutex_camera(0)
+    campos, raydir = synth.scan83_camera(33)              # the real DTU scan83 centre camera (data/dtu.py:113-114,119-182)
     R = raydir.shape[1]
     noise = synth.neutex_noise(R)
     bg = torch.ones(1, 3)
@@ -681,7 +720,7 @@ def neutex_config(ngf_b200, synth, dev, pk, args):
     t0 = time.perf_counter()
     m.render_host(campos, h_rd, bg, h_nz)
     e2e_s = time.perf_counter() - t0
-    res = {"workload": "UV-Mapping NeuTex, 600x800 rays x 64 samples/ray, square primitive, jitter 0.05 (BASELINE configs[3])",
+    res = {"workload": "UV-Mapping NeuTex, DTU scan83 camera 33, 600x800 rays x 64 samples/ray, square primitive, jitter 0.05 (BASELINE configs[3])",
            "rays_per_s": R / (total_ms * 1e-3), "ms_per_frame": total_ms, "raygen_ms": a_ms / k, "mlp_kernel_ms": b_ms / k,
            "march_ms": c_ms / k, "in_cube_samples_per_ray": nv / R,
            "e2e": {"value": R / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": R * (3 + 64) * 4, "d2h_bytes_per_step": R * 16,

@@ -370,6 +370,20 @@ int ngf_field_render_sharded_host_async(NgfField f, NgfComm c, const float* rays
                                         int32_t mlp_impl, float* frame_host, int64_t first_row, int64_t n_rows,
                                         uint64_t* ticket);
 int ngf_comm_wait(NgfComm c, uint64_t ticket);
+/* Camera batches (evaluation_path's per-frame job, TriPlane/main.py:155-161, for a ray-sharded batch of frames): the batch is
+ * n_frames (<= 64) frames of one pinhole model (`camera`: intrinsics and image size; its c2w is ignored) with one pose each,
+ * poses [n_frames][12] = row-major [3][4] camera-to-world; n_frames * width * height must be the comm's n_rays.  Rays are
+ * generated in the march kernel from the pixel index, so a step's input is 48 bytes per frame.
+ *   ngf_field_render_sharded_camera                 device-resident: as ngf_field_render_sharded (ticket for
+ *                                                   ngf_frame_allgather / ngf_frame_release), poses in device memory
+ *   ngf_field_render_sharded_camera_u8_host_async   poses from host memory in; rows [first_row, first_row + n_rows) of the
+ *                                                   gathered batch out as uint8 rgb [n_rows][3] ((rgb * 255) truncated,
+ *                                                   main.py:116); wait with ngf_comm_wait */
+int ngf_field_render_sharded_camera(NgfField f, NgfComm c, const NgfCamera* camera, const float* poses_dev, int32_t n_frames,
+                                    int32_t n_samples, int32_t white_bg, int32_t mlp_impl, void* stream, uint64_t* ticket);
+int ngf_field_render_sharded_camera_u8_host_async(NgfField f, NgfComm c, const NgfCamera* camera, const float* poses_host,
+                                                  int32_t n_frames, int32_t n_samples, int32_t white_bg, int32_t mlp_impl,
+                                                  uint8_t* u8_host, int64_t first_row, int64_t n_rows, uint64_t* ticket);
 
 /* =====================================================================================================
  * UV-Mapping (NeuTex) render path.  Reference (paths relative to /root/reference/UV-Mapping):

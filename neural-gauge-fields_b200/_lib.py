@@ -145,6 +145,11 @@ SIGNATURES = {
                                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
                                                       C.POINTER(C.c_uint64)]),
     "ngf_comm_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "ngf_field_render_sharded_camera": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(NgfCamera), C.c_void_p, C.c_int32, C.c_int32,
+                                                  C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "ngf_field_render_sharded_camera_u8_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(NgfCamera), C.c_void_p,
+                                                                C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                                                C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]),
 }
 
 _lib = None

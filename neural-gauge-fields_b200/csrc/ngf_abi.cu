@@ -815,6 +815,7 @@ static int check_camera(const NgfCamera* c, CamDev* out) {
   out->fx = c->fx; out->fy = c->fy; out->cx = c->cx; out->cy = c->cy;
   out->W = c->width; out->H = c->height;
   out->base = 0;
+  out->poses = nullptr; out->shard_block = 1; out->shard_rank = 0; out->shard_world = 1;
   return NGF_OK;
 }
 

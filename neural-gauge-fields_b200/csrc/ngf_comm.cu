@@ -40,6 +40,7 @@ namespace {
 constexpr int kMaxWorld = 16;
 constexpr int kMaxSlots = 4;
 constexpr int kCommStreams = 2;
+constexpr int kMaxFrames = 64;                // frames per camera batch
 constexpr size_t kFlagBytes = 4096;           // arrived [kMaxSlots][kMaxWorld] u32 @0, freed [kMaxSlots][kMaxWorld] u32 @1024
 
 struct CommBlob {                             // what ranks exchange (ngf_comm_export / ngf_comm_connect)
@@ -83,6 +84,16 @@ __global__ void ngf_comm_wait_kernel(const __grid_constant__ PeerList pl, uint32
   }
 }
 
+// rows [first, first + n) of a gathered [.][4] frame -> uint8 rgb, (rgb * 255) truncated (TriPlane/main.py:116)
+__global__ void ngf_frame4_u8_kernel(const float4* __restrict__ frame, long long first, long long n, uint8_t* __restrict__ u8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = frame[first + i];
+    u8[i * 3 + 0] = (uint8_t)__fmul_rn(v.x, 255.f);
+    u8[i * 3 + 1] = (uint8_t)__fmul_rn(v.y, 255.f);
+    u8[i * 3 + 2] = (uint8_t)__fmul_rn(v.z, 255.f);
+  }
+}
+
 }  // namespace
 
 struct NgfComm_ {
@@ -105,6 +116,9 @@ struct NgfComm_ {
     cudaEvent_t ev_consumed = nullptr;        // the consumer has finished reading the frame buffer
     cudaEvent_t ev_done = nullptr;            // host path: results are in the caller's host buffer
     float* rays = nullptr;                    // host path staging
+    float* poses = nullptr;                   // camera path: [kMaxFrames][12] c2w of the batch's frames
+    uint8_t* u8 = nullptr;                    // camera path: uint8 image rows on their way to the host
+    long long u8_cap = 0;
     unsigned long long ticket = 0;            // ticket occupying the slot (0 = none)
     bool released = true;
   } slot[kMaxSlots];
@@ -141,7 +155,7 @@ void comm_destroy(NgfComm_* c) {
     for (auto& e : s.ev_sent) if (e) cudaEventDestroy(e);
     if (s.ev_consumed) cudaEventDestroy(s.ev_consumed);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
-    cudaFree(s.rays);
+    cudaFree(s.rays); cudaFree(s.poses); cudaFree(s.u8);
   }
   if (c->s_in) cudaStreamDestroy(c->s_in);
   if (c->s_comp) cudaStreamDestroy(c->s_comp);
@@ -206,7 +220,8 @@ int check_err(const NgfComm_* c) {
 
 // Steps 2-3 of a sharded frame on stream `st`: render my rays into frame order of slot s, then hand the rows to the peers.
 int render_and_push(NgfField f, NgfComm_* c, int s, unsigned long long k, const float* rays_dev, long long n_local,
-                    int ray_stride, int n_samples, int white_bg, int tile_w, int mlp_impl, cudaStream_t st) {
+                    int ray_stride, int n_samples, int white_bg, int tile_w, int mlp_impl, cudaStream_t st,
+                    const CamDev* cam = nullptr) {
   NgfComm_::Slot& sl = c->slot[s];
   // my rows of slot s may be overwritten once (a) the local consumer of step k - n_slots has released the buffer and
   // (b) the copies that pushed them to the peers have finished reading them
@@ -222,7 +237,7 @@ int render_and_push(NgfField f, NgfComm_* c, int s, unsigned long long k, const 
     for (int d = 1; d < c->world; ++d) so.dst[so.n_dst++] = c->frame((c->rank + d) % c->world, s);
   }
   int rc = ngf_render_dev(f, rays_dev, n_local, ray_stride, n_samples, white_bg, tile_w, c->rgb, c->depth, c->acc,
-                          c->counters, &c->queue, &c->queue_cap, mlp_impl, st, nullptr, nullptr, &so);
+                          c->counters, &c->queue, &c->queue_cap, mlp_impl, st, cam, nullptr, &so);
   if (rc) return rc;
   if (c->mode == NGF_COMM_STORE && c->world > 1) {
     PeerList pl{};
@@ -507,6 +522,102 @@ int ngf_field_render_sharded_host_async(NgfField f, NgfComm c, const float* rays
   PeerList pl{};
   for (int d = 1; d < c->world; ++d) pl.p[pl.n++] = c->freed((c->rank + d) % c->world, s, c->rank);
   if ((rc = launch_signal(pl, (uint32_t)(k + 1), c->s_out))) return rc;
+  CU(cudaEventRecord(sl.ev_done, c->s_out));
+  sl.ticket = k + 1;
+  sl.released = true;
+  c->next_step = k + 1;
+  *ticket = k + 1;
+  return NGF_OK;
+}
+
+// Camera batches: the batch is n_frames frames of one pinhole camera model (intrinsics of `camera`, one pose each), rays are
+// generated inside the march kernel from the pixel index.  poses: [n_frames][12] row-major [3][4] camera-to-world.
+static int camera_batch(NgfComm_* c, const NgfCamera* camera, int n_frames, int rank_check, CamDev* out) {
+  if (!camera) return ngf_set_error(NGF_EINVAL, "camera is NULL");
+  if (n_frames < 1 || n_frames > kMaxFrames) return ngf_set_error(NGF_EINVAL, "n_frames=%d (1..%d)", n_frames, kMaxFrames);
+  if (camera->width < 1 || camera->height < 1 || !(camera->fx != 0.f) || !(camera->fy != 0.f))
+    return ngf_set_error(NGF_EINVAL, "bad camera");
+  if ((long long)n_frames * camera->width * camera->height != c->n_rays)
+    return ngf_set_error(NGF_EINVAL, "%d frames of %dx%d pixels are not the comm's %lld-ray batch", n_frames, camera->width,
+                         camera->height, c->n_rays);
+  (void)rank_check;
+  CamDev cam{};
+  memcpy(cam.c2w, camera->c2w, sizeof(cam.c2w));
+  cam.fx = camera->fx; cam.fy = camera->fy; cam.cx = camera->cx; cam.cy = camera->cy;
+  cam.W = camera->width; cam.H = camera->height;
+  cam.base = 0;
+  cam.shard_block = c->block; cam.shard_rank = c->rank; cam.shard_world = c->world;
+  *out = cam;
+  return NGF_OK;
+}
+
+int ngf_field_render_sharded_camera(NgfField f, NgfComm c, const NgfCamera* camera, const float* poses_dev, int32_t n_frames,
+                                    int32_t n_samples, int32_t white_bg, int32_t mlp_impl, void* stream, uint64_t* ticket) {
+  if (!ticket || !poses_dev) return ngf_set_error(NGF_EINVAL, "NULL argument");
+  int s = 0;
+  unsigned long long k = 0;
+  int rc = begin_step(f, c, c ? c->n_local : 0, mlp_impl, &s, &k);
+  if (rc) return rc;
+  CamDev cam{};
+  if ((rc = camera_batch(c, camera, n_frames, c->rank, &cam))) return rc;
+  cam.poses = poses_dev;
+  Guard g(c->device);
+  const int tile_w = (c->block % (4 * cam.W) == 0) ? cam.W : 0;       // whole 4-row groups per block: 8x4-pixel warp tiles
+  rc = render_and_push(f, c, s, k, nullptr, c->n_local, 6, n_samples, white_bg, tile_w, mlp_impl,
+                       reinterpret_cast<cudaStream_t>(stream), &cam);
+  if (rc) return rc;
+  c->slot[s].ticket = k + 1;
+  c->slot[s].released = false;
+  c->next_step = k + 1;
+  *ticket = k + 1;
+  return NGF_OK;
+}
+
+int ngf_field_render_sharded_camera_u8_host_async(NgfField f, NgfComm c, const NgfCamera* camera, const float* poses_host,
+                                                  int32_t n_frames, int32_t n_samples, int32_t white_bg, int32_t mlp_impl,
+                                                  uint8_t* u8_host, int64_t first_row, int64_t n_rows, uint64_t* ticket) {
+  if (!ticket || !poses_host) return ngf_set_error(NGF_EINVAL, "NULL argument");
+  int s = 0;
+  unsigned long long k = 0;
+  int rc = begin_step(f, c, c ? c->n_local : 0, mlp_impl, &s, &k);
+  if (rc) return rc;
+  CamDev cam{};
+  if ((rc = camera_batch(c, camera, n_frames, c->rank, &cam))) return rc;
+  if (first_row < 0 || n_rows < 0 || first_row + n_rows > c->n_rays || (n_rows > 0 && !u8_host))
+    return ngf_set_error(NGF_EINVAL, "rows [%lld, %lld) of a %lld-ray batch", (long long)first_row, (long long)(first_row + n_rows), c->n_rays);
+  Guard g(c->device);
+  NgfComm_::Slot& sl = c->slot[s];
+  if (!sl.poses) CU(cudaMalloc(reinterpret_cast<void**>(&sl.poses), kMaxFrames * 12 * sizeof(float)));
+  if (sl.u8_cap < n_rows) {
+    CU(cudaStreamSynchronize(c->s_out));
+    cudaFree(sl.u8);
+    sl.u8 = nullptr; sl.u8_cap = 0;
+    CU(cudaMalloc(reinterpret_cast<void**>(&sl.u8), (size_t)(n_rows > 0 ? n_rows : 1) * 3));
+    sl.u8_cap = n_rows;
+  }
+  // upload the poses: the slot's pose buffer is free once the render that read it (step k - n_slots) is done
+  CU(cudaStreamWaitEvent(c->s_in, sl.ev_rendered, 0));
+  CU(cudaMemcpyAsync(sl.poses, poses_host, (size_t)n_frames * 12 * sizeof(float), cudaMemcpyHostToDevice, c->s_in));
+  CU(cudaEventRecord(sl.ev_in, c->s_in));
+  CU(cudaStreamWaitEvent(c->s_comp, sl.ev_in, 0));
+  cam.poses = sl.poses;
+  const int tile_w = (c->block % (4 * cam.W) == 0) ? cam.W : 0;
+  rc = render_and_push(f, c, s, k, nullptr, c->n_local, 6, n_samples, white_bg, tile_w, mlp_impl, c->s_comp, &cam);
+  if (rc) return rc;
+  CU(cudaStreamWaitEvent(c->s_out, sl.ev_rendered, 0));
+  if ((rc = launch_wait(c, local_flags(c, s, true), (uint32_t)(k + 1), c->s_out))) return rc;
+  if (n_rows > 0) {
+    long long blocks = (n_rows + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    ngf_frame4_u8_kernel<<<(unsigned)blocks, 256, 0, c->s_out>>>(c->frame(c->rank, s), first_row, n_rows, sl.u8);
+    count_launch();
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(sl.ev_consumed, c->s_out));          // the frame buffer has been read: peers may overwrite it
+  PeerList pl{};
+  for (int d = 1; d < c->world; ++d) pl.p[pl.n++] = c->freed((c->rank + d) % c->world, s, c->rank);
+  if ((rc = launch_signal(pl, (uint32_t)(k + 1), c->s_out))) return rc;
+  if (n_rows > 0) CU(cudaMemcpyAsync(u8_host, sl.u8, (size_t)n_rows * 3, cudaMemcpyDeviceToHost, c->s_out));
   CU(cudaEventRecord(sl.ev_done, c->s_out));
   sl.ticket = k + 1;
   sl.released = true;

@@ -76,12 +76,23 @@ struct CamDev {
   float fx, fy, cx, cy;
   int W, H;
   long long base;                 // pixel index of local ray 0 (frames rendered in row blocks)
+  // ray-sharded batches of several frames (ngf_comm.cu): local ray l is ray ((l / block) * world + rank) * block + l % block
+  // of the batch, which is pixel g % (W*H) of frame g / (W*H); every frame has its own pose, poses[frame][12].
+  const float* poses;             // nullptr: one frame, pose c2w
+  int shard_block, shard_rank, shard_world;
 };
 
 // Ray of pixel `ray` (row-major): camera-space direction ((i+0.5-cx)/fx, (j+0.5-cy)/fy, 1), normalised
 // (blender.py:52), rotated by c2w[:3,:3] (get_rays: directions @ c2w[:3,:3].T); origin = c2w[:3,3].
 __device__ __forceinline__ void camera_ray(const CamDev& c, long long ray, float o[3], float d[3]) {
   ray += c.base;
+  const float* c2w = c.c2w;
+  if (c.poses) {
+    const long long g = ((ray / c.shard_block) * c.shard_world + c.shard_rank) * c.shard_block + ray % c.shard_block;
+    const long long per = (long long)c.W * c.H, frame = g / per;
+    c2w = c.poses + frame * 12;
+    ray = g - frame * per;
+  }
   const int j = (int)(ray / c.W), i = (int)(ray - (long long)j * c.W);
   const float x = __fdiv_rn(__fsub_rn(__fadd_rn((float)i, 0.5f), c.cx), c.fx);
   const float y = __fdiv_rn(__fsub_rn(__fadd_rn((float)j, 0.5f), c.cy), c.fy);
@@ -89,8 +100,8 @@ __device__ __forceinline__ void camera_ray(const CamDev& c, long long ray, float
   const float dx = __fdiv_rn(x, nrm), dy = __fdiv_rn(y, nrm), dz = __fdiv_rn(1.f, nrm);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    d[k] = __fadd_rn(__fadd_rn(__fmul_rn(dx, c.c2w[4 * k]), __fmul_rn(dy, c.c2w[4 * k + 1])), __fmul_rn(dz, c.c2w[4 * k + 2]));
-    o[k] = c.c2w[4 * k + 3];
+    d[k] = __fadd_rn(__fadd_rn(__fmul_rn(dx, c2w[4 * k]), __fmul_rn(dy, c2w[4 * k + 1])), __fmul_rn(dz, c2w[4 * k + 2]));
+    o[k] = c2w[4 * k + 3];
   }
 }
 

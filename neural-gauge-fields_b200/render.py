@@ -291,6 +291,52 @@ class FrameComm:
     def wait(self, ticket: int):
         _lib.check(_lib.load().ngf_comm_wait(self._h, int(ticket)), "ngf_comm_wait")
 
+    def _poses(self, poses):
+        p = torch.as_tensor(poses, dtype=torch.float32).reshape(-1, 12)
+        return p.contiguous()
+
+    @torch.no_grad()
+    def submit_camera(self, poses, H, W, focal, center=None, N_samples=-1, white_bg=True, **fwd_kw):
+        """A batch of ``len(poses)`` camera frames (poses [F,3,4] camera-to-world, one pinhole model), this rank's rays
+        generated in the march kernel (ngf_field_render_sharded_camera).  -> ticket for result() / release()."""
+        import ctypes as C
+        if not fwd_kw and hasattr(self.field, "gauge_start"):
+            fwd_kw = {"iteration": 30001}
+        fh = self._field_handle(fwd_kw)
+        p = self._poses(poses).to(self.field.device)
+        cam = self.field._camera(p[0].cpu(), H, W, focal, center)
+        t = C.c_uint64()
+        with torch.cuda.device(self.field.device):
+            _lib.check(_lib.load().ngf_field_render_sharded_camera(fh, self._h, C.byref(cam), p.data_ptr(), p.shape[0], int(N_samples),
+                                                                   int(bool(white_bg)), self.field._mlp_impl,
+                                                                   _cuda_stream_ptr(self.field.device), C.byref(t)),
+                       "ngf_field_render_sharded_camera")
+        self._keep_poses = p
+        return int(t.value)
+
+    @torch.no_grad()
+    def submit_camera_host(self, poses_host, H, W, focal, u8_host, first_row=0, n_rows=None, center=None, N_samples=-1,
+                           white_bg=True, **fwd_kw):
+        """Host pipeline of a camera batch (ngf_field_render_sharded_camera_u8_host_async): poses [F,3,4] (pinned CPU fp32) in,
+        rows [first_row, first_row + n_rows) of the gathered batch out as uint8 rgb in the pinned ``u8_host``; -> ticket for
+        ``wait``."""
+        import ctypes as C
+        if not fwd_kw and hasattr(self.field, "gauge_start"):
+            fwd_kw = {"iteration": 30001}
+        fh = self._field_handle(fwd_kw)
+        if poses_host.device.type != "cpu" or poses_host.dtype != torch.float32 or not poses_host.is_contiguous():
+            raise ValueError("poses_host must be a contiguous fp32 CPU tensor [F, 3, 4]")
+        if u8_host.device.type != "cpu" or u8_host.dtype != torch.uint8 or not u8_host.is_contiguous():
+            raise ValueError("u8_host must be a contiguous uint8 CPU tensor")
+        n_frames = poses_host.numel() // 12
+        n_rows = u8_host.shape[0] if n_rows is None else int(n_rows)
+        cam = self.field._camera(poses_host.reshape(-1, 12)[0], H, W, focal, center)
+        t = C.c_uint64()
+        _lib.check(_lib.load().ngf_field_render_sharded_camera_u8_host_async(
+            fh, self._h, C.byref(cam), poses_host.data_ptr(), n_frames, int(N_samples), int(bool(white_bg)), self.field._mlp_impl,
+            u8_host.data_ptr(), int(first_row), n_rows, C.byref(t)), "ngf_field_render_sharded_camera_u8_host_async")
+        return int(t.value)
+
 
 class ShardedFrameRenderer:
     """Ray-sharded multi-GPU rendering, one all-gather of the rendered batch per step, overlapped with the next batch.

@@ -275,6 +275,27 @@ def neutex_camera(pose: int = 0, H: int = NEUTEX_H, W: int = NEUTEX_W, radius: f
     return c2w[:, 3].reshape(1, 3).contiguous(), d.contiguous()
 
 
+def scan83_camera(view: int = 33, max_rays: int = 0):
+    """The real DTU scan83 camera ``view`` as DtuDataset.get_item builds it for a full-image test render (data/dtu.py:119-182
+    with no_crop: integer pixel coordinates, get_rays_dir dtu.py:27-37): -> campos [1,3], raydir [1, 600*800, 3].  The 64
+    cameras ship with the reference (trainData/in_cam*.npy) and are kept in data/scan83_cameras.npz; 33 is the reference's
+    centre camera (dtu.py:113-114)."""
+    import os
+    import numpy as np
+    c = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "scan83_cameras.npz"))
+    focal, princpt, rot = c["focal"][view], c["princpt"][view], c["extrinsics"][view][0:3, 0:3]
+    px, py = np.meshgrid(np.arange(NEUTEX_W).astype(np.float32), np.arange(NEUTEX_H).astype(np.float32))
+    x = (px - princpt[0]) / focal[0]
+    y = (py - princpt[1]) / focal[1]
+    dirs = np.stack([x, y, np.ones_like(x)], axis=-1)
+    dirs = np.sum(rot[None, None, :, :] * dirs[..., None], axis=-2)
+    dirs = dirs / (np.linalg.norm(dirs, axis=-1, keepdims=True) + 1e-5)
+    d = torch.from_numpy(np.reshape(dirs, (-1, 3))).float().reshape(1, -1, 3)
+    if max_rays and d.shape[1] > max_rays:
+        d = d[:, :: d.shape[1] // max_rays][:, :max_rays]
+    return torch.from_numpy(c["campos"][view]).float().reshape(1, 3).contiguous(), d.contiguous()
+
+
 def neutex_noise(n_rays: int, samples: int = NEUTEX_SAMPLES, seed: int = 11) -> torch.Tensor:
     """The U[0,1) jitter tensor cube_ray_generation draws with torch.rand (renderer.py:113-118), made explicit so
     both implementations consume the same numbers."""

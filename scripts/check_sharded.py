@@ -89,6 +89,32 @@ for mode in ("nccl", "copy", "store"):
             report.append(f"{mode} host buffer {k}: rgb {e_rgb:.2e} depth {e_dep:.2e} {'ok' if good else 'MISMATCH'}")
         dist.barrier()
         sr.comm.close()
+# camera batches through the host pipeline: `world` frames per batch, every rank downloads its own frame as uint8
+H, W = 48, 80
+focal = K.synth.FOCAL_800 * 64 / 800
+poses = torch.stack([K.synth.look_at_c2w(*K.synth.pose_angles(p)) for p in range(4, 4 + world)]).contiguous()
+per = H * W
+o = f.render_camera(poses[rank], H, W, focal, white_bg=True, N_samples=64, iteration=30001)
+want = (o["rgb_map"].cpu().numpy() * 255).astype("uint8")
+for mode in ("copy", "store"):
+    comm = ngf_b200.FrameComm(f, world * per, block=4 * W, mode=mode)
+    u8 = [torch.zeros((per, 3), dtype=torch.uint8).pin_memory() for _ in range(3)]
+    ph = poses.pin_memory()
+    tickets = []
+    for k in range(6):
+        tickets.append(comm.submit_camera_host(ph, H, W, focal, u8[k % 3], first_row=rank * per, N_samples=64, white_bg=True,
+                                               iteration=30001))
+        if len(tickets) > 2:
+            comm.wait(tickets.pop(0))
+    for t in tickets:
+        comm.wait(t)
+    for k, b in enumerate(u8):
+        d = np.abs(b.numpy().astype(np.int16) - want.astype(np.int16))
+        good = d.max() <= 1 and (d > 0).mean() < 1e-3
+        ok &= bool(good)
+        report.append(f"{mode} camera u8 buffer {k}: max diff {int(d.max())} {'ok' if good else 'MISMATCH'}")
+    dist.barrier()
+    comm.close()
 print(f"rank {rank}/{world}: " + "; ".join(report) + f" => {'OK' if ok else 'MISMATCH'}", flush=True)
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

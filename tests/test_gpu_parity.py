@@ -637,3 +637,80 @@ def test_tensorf_style_aliases():
     assert torch.equal(f.compute_appfeature(xyz, d), f.compute_rgb(xy, yz, xz, d))
     a, b = ngf_b200.render_rays(rays.cuda(), f, N_samples=64), ngf_b200.renderer(rays.cuda(), f, N_samples=64)
     assert float((a[0] - b[0]).abs().max()) < 1e-5 and torch.equal(a[1], b[1])
+
+
+def test_sharded_camera_batches():
+    """Ray-sharded batches of camera frames (ngf_field_render_sharded_camera[_u8_host_async]): rays generated in the march
+    kernel from (frame, pixel) of the rank's interleaved blocks.  (a) one rank, 2-frame batch, device-resident and host-u8
+    paths against ngf_field_render_camera of each frame; (b) three ranks driven from this process on one GPU, 3-frame batch:
+    every rank's gathered batch equals the per-frame renders."""
+    import ctypes as C
+    import ngf_b200
+    from ngf_b200 import _lib
+    case = K.CASE_BY_NAME["tp_fog_c1"]
+    state, kw, occ, _ = K.build_inputs(case)
+    f = build_cuda_field(case, state, kw, occ)
+    H, W = 48, 80
+    focal = K.synth.FOCAL_800 * 64 / 800
+    poses = torch.stack([K.synth.look_at_c2w(*K.synth.pose_angles(p)) for p in (4, 9, 13)])      # [3, 3, 4]
+    per = H * W
+    ref = []
+    for p in poses:
+        o = f.render_camera(p, H, W, focal, white_bg=True, N_samples=64, iteration=30001)
+        ref.append(torch.cat([o["rgb_map"], o["depth_map"][:, None]], 1))
+    ref = torch.cat(ref).cpu()                                                                  # [3*per, 4]
+    # (a) world 1, two frames
+    comm = ngf_b200.FrameComm(f, 2 * per, block=4 * W)
+    for k in range(4):
+        t = comm.submit_camera(poses[:2], H, W, focal, N_samples=64, white_bg=True, iteration=30001)
+        got = comm.result(t).clone()
+        comm.release(t)
+        assert (got.cpu() - ref[:2 * per]).abs().max() < 1e-5
+    u8 = [torch.zeros((per, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    ph = poses[:2].contiguous().pin_memory()
+    tk = [comm.submit_camera_host(ph, H, W, focal, u8[k % 2], first_row=per, N_samples=64, white_bg=True, iteration=30001)
+          for k in range(4)]
+    for t in tk:
+        comm.wait(t)
+    want = (ref[per:2 * per, :3].numpy() * 255).astype("uint8")
+    for b in u8:
+        d = np.abs(b.numpy().astype(np.int16) - want.astype(np.int16))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3          # fp32 atomics order: values on an integer boundary may flip
+    comm.close()
+    # (b) three ranks in this process
+    lib = _lib.load()
+    nb = int(lib.ngf_comm_handle_bytes())
+    fh = f._ensure_handle()
+    n = 3 * per
+    hs, blobs = [], b""
+    for r in range(3):
+        h = C.c_void_p()
+        _lib.check(lib.ngf_comm_init(r, 3, 0, n, 4 * W, 3, _lib.COMM_COPY, C.byref(h)))
+        buf = C.create_string_buffer(nb)
+        _lib.check(lib.ngf_comm_export(h, buf))
+        hs.append(h)
+        blobs += bytes(buf.raw)
+    for h in hs:
+        _lib.check(lib.ngf_comm_connect(h, blobs))
+    cam = f._camera(poses[0], H, W, focal)
+    pd = poses.reshape(3, 12).cuda().contiguous()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    t = C.c_uint64()
+    for k in range(4):
+        tickets = []
+        for r in range(3):
+            _lib.check(lib.ngf_field_render_sharded_camera(fh, hs[r], C.byref(cam), pd.data_ptr(), 3, 64, 1, 0,
+                                                           C.c_void_p(streams[r].cuda_stream), C.byref(t)), "sharded_camera")
+            tickets.append(int(t.value))
+        frames = []
+        for r in range(3):
+            p = C.c_void_p()
+            _lib.check(lib.ngf_frame_allgather(hs[r], tickets[r], C.c_void_p(streams[r].cuda_stream), C.byref(p)))
+            with torch.cuda.stream(streams[r]):
+                frames.append(torch.as_tensor(ngf_b200.render._DevView(p.value, n, 4), device="cuda").clone())
+            _lib.check(lib.ngf_frame_release(hs[r], tickets[r], C.c_void_p(streams[r].cuda_stream)))
+        torch.cuda.synchronize()
+        for r in range(3):
+            assert (frames[r].cpu() - ref).abs().max() < 1e-5, (k, r)
+    for h in hs:
+        lib.ngf_comm_free(h)
