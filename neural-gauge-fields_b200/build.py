@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libngf_b200.so")
 SOURCES = ["ngf_kernels.cu", "ngf_abi.cu", "ngf_comm.cu", "ngf_train.cu", "ngf_neutex.cu", "ngf_neutex_abi.cu"]
-HEADERS = ["ngf_common.cuh", "ngf_mlp.cuh", "ngf_internal.h", "ngf_handle.h", "ngf_queue.h", "ngf_colour_tma.cuh", "ngf_infoinv_march.cuh", "ngf_jet_lut.h", "ngf_neutex.cuh", os.path.join("..", "..", "include", "ngf_b200.h")]
+HEADERS = ["ngf_common.cuh", "ngf_mlp.cuh", "ngf_internal.h", "ngf_handle.h", "ngf_queue.h", "ngf_colour_tma.cuh", "ngf_infoinv_march.cuh", "ngf_infoinv_tc.cuh", "ngf_jet_lut.h", "ngf_neutex.cuh", os.path.join("..", "..", "include", "ngf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 

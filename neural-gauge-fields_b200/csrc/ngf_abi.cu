@@ -93,7 +93,7 @@ static void free_all(NgfField_* h) {
   for (int i = 0; i < 3; ++i) cudaFree(h->dsum[i]);
   cudaFree(h->occ); cudaFree(h->occ2); cudaFree(h->occ_coarse);
   cudaFree(h->dmlp); cudaFree(h->w1p); cudaFree(h->w2p); cudaFree(h->tail);
-  cudaFree(h->raw_w); cudaFree(h->raw_dw); cudaFree(h->tmaps);
+  cudaFree(h->raw_w); cudaFree(h->raw_dw); cudaFree(h->tmaps); cudaFree(h->ii_w); cudaFree(h->ii_tail);
   ngf_train_free(h->train);
   h->train = nullptr;
   cudaFree(h->acc_ws); cudaFree(h->counters); cudaFree(h->queue);
@@ -346,6 +346,7 @@ static int pack_params(NgfField_* h, const NgfFieldDesc* d, bool allocate) {
     memcpy(f.dw, w.data(), 48 * sizeof(float));
     f.db = b[0];
     f.dmlp = nullptr;
+    f.ii_w = nullptr; f.ii_tail = nullptr;
     float* w_dev = nullptr;
     CU(dev_alloc(&w_dev, (size_t)48));
     cudaError_t e = cudaMemcpy(w_dev, w.data(), 48 * sizeof(float), cudaMemcpyHostToDevice);
@@ -376,6 +377,31 @@ static int pack_params(NgfField_* h, const NgfFieldDesc* d, bool allocate) {
       raw.insert(raw.end(), w3.begin(), w3.end()); raw.insert(raw.end(), b3.begin(), b3.end());
       if (allocate) CU(dev_alloc(&h->raw_dw, raw.size()));
       CU(cudaMemcpy(h->raw_dw, raw.data(), raw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    {
+      // split fp16 operands of the tensor-core density MLP: x = hi + lo, hi = rn16(x), lo = rn16(x - hi); the biases ride
+      // in a constant-one K column (layer 1: column 72 of 80, layer 2: column 32 of 48)
+      std::vector<__half> iw((size_t)2 * 32 * 80 + (size_t)2 * 32 * 48, __float2half_rn(0.f));
+      auto put = [&](size_t base_hi, size_t base_lo, int r, int k, float v) {
+        const __half hi = __float2half_rn(v);
+        const size_t o = (size_t)(k / 8) * 32 * 8 + (size_t)r * 8 + (k % 8);
+        iw[base_hi + o] = hi;
+        iw[base_lo + o] = __float2half_rn(v - __half2float(hi));
+      };
+      const size_t o1h = 0, o1l = 32 * 80, o2h = 2 * 32 * 80, o2l = 2 * 32 * 80 + 32 * 48;
+      for (int r = 0; r < 32; ++r) {
+        for (int k = 0; k < 72; ++k) put(o1h, o1l, r, k, w[(size_t)r * 72 + k]);
+        put(o1h, o1l, r, 72, b[r]);
+        for (int k = 0; k < 32; ++k) put(o2h, o2l, r, k, w2[(size_t)r * 32 + k]);
+        put(o2h, o2l, r, 32, b2[r]);
+      }
+      std::vector<float> tl(36, 0.f);
+      memcpy(tl.data(), w3.data(), 32 * 4);
+      tl[32] = b3[0];
+      if (allocate) { CU(dev_alloc(&h->ii_w, iw.size())); CU(dev_alloc(&h->ii_tail, tl.size())); }
+      CU(cudaMemcpy(h->ii_w, iw.data(), iw.size() * sizeof(__half), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(h->ii_tail, tl.data(), tl.size() * sizeof(float), cudaMemcpyHostToDevice));
+      f.ii_w = h->ii_w; f.ii_tail = h->ii_tail;
     }
     f.dmlp = h->dmlp;
     memset(f.dw, 0, sizeof(f.dw));
@@ -530,11 +556,26 @@ int ngf_render_dev(NgfField h, const float* rays, long long n_rays, int ray_stri
   long long want = per * S;
   if (want > 0xfffffff0ll) { per = 0xfffffff0ll / S / unit * unit; want = per * S; }
   // InfoInv: the three-phase march keeps 192 bytes of state per ray (+ 64) behind the queue, in the same allocation
+  // InfoInv, opt-in (NGF_INFOINV_TC=1): the march as find / tensor-core density / composite (ngf_infoinv_tc.cuh), with one
+  // 32-byte record per kept sample (worst case n * S, like the queue) + 4 bytes per ray behind the queue, in the same
+  // allocation: queue and records share the budget.  Parity-green, but it evaluates every kept sample of a ray (13.2 per ray
+  // on the hull field against 3.3 with the in-march early-out) and the fp32 density gather costs as much per sample as the
+  // colour gather: 1.92 ms per frame against 0.77.  Default: the in-march per-lane MLP.
+  static int ii_tc = -1;
+  if (ii_tc < 0) { const char* e = getenv("NGF_INFOINV_TC"); ii_tc = e && e[0] == '1' ? 1 : 0; }
+  const bool use_tc = h->dev.variant == 1 && ii_tc && !getenv("NGF_INFOINV_PHASED");
+  if (use_tc) {
+    per = per / 2 / unit * unit;
+    if (per < unit) per = unit;
+    if (per > n_rays) per = n_rays;
+    want = per * S;
+  }
   static int ii_phased = -1;
   // opt-in (NGF_INFOINV_PHASED=1): parity-green but slower on B200 than the in-march MLP — 10 rounds x 4 grid barriers of
   // ~12 us each and a per-lane MLP that is latency-bound even at full lane occupancy (profiles/r02_infoinv_phased_trace.txt)
   if (ii_phased < 0) { const char* e = getenv("NGF_INFOINV_PHASED"); ii_phased = e && e[0] == '1' ? 1 : 0; }
-  const long long ii_items = (h->dev.variant == 1 && ii_phased) ? per * 6 + 2 : 0;      // in 32-byte queue items
+  const long long ii_items = use_tc ? per * S + per / 8 + 4                               // in 32-byte queue items
+                                    : (h->dev.variant == 1 && ii_phased) ? per * 6 + 2 : 0;
   int rc = ensure_queue(queue, queue_cap, want + ii_items, st);
   if (rc) return rc;
   for (long long s0 = 0; s0 < n_rays; s0 += per) {
@@ -559,6 +600,7 @@ int ngf_render_dev(NgfField h, const float* rays, long long n_rays, int ray_stri
     a.queue = *queue;
     a.queue_cap = (unsigned int)(n * S < want ? n * S : want);
     a.ii_ws = ii_items ? static_cast<void*>(*queue + want) : nullptr;
+    a.ii_tc = use_tc ? 1 : 0;
     a.stats = reinterpret_cast<unsigned long long*>(counters + 2);
     CU(cudaMemsetAsync(counters, 0, s0 == 0 ? kCounterBytes : 8, st));   // first batch also clears the statistics
     const bool timed = h->ev_used + 3 <= (int)h->ev.size();

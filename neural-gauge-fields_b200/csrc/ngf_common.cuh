@@ -68,6 +68,10 @@ struct FieldDev {
   // three 128-byte TMA tensor maps (device memory) over the appearance planes [H][W][48] fp16 with 48 x 5 x 5 boxes, or
   // nullptr (InfoInv; driver without cuTensorMapEncodeTiled): ngf_colour_tma.cuh
   const void* tmap;
+  // InfoInv density MLP for the tensor-core march (ngf_infoinv_tc.cuh): split fp16 weights in tcgen05 K-major order
+  // [W1 hi | W1 lo] ([32 x 80], column 72 = b1) [W2 hi | W2 lo] ([32 x 48], column 32 = b2), and fp32 [w3 32][b3]
+  const __half* ii_w;
+  const float* ii_tail;
 };
 
 // Pinhole camera for on-device ray generation (TriPlane/dataLoader/ray_utils.py:24-42,66-87 + blender.py:46-52)

@@ -44,6 +44,8 @@ struct NgfField_ {
   __half* w2p = nullptr;
   float* tail = nullptr;
   // fp32 network weights in nn.Linear layout for the backward pass (ngf_train.cu)
+  __half* ii_w = nullptr;             // InfoInv: split fp16 density MLP (ngf_infoinv_tc.cuh)
+  float* ii_tail = nullptr;
   void* tmaps = nullptr;              // 3 CUtensorMap objects in device memory (TriPlane appearance planes)
   float* raw_w = nullptr;             // [basis F*F | mlp.0 W 64*(F+15) | b 64 | mlp.2 W 64*64 | b 64 | mlp.4 W 3*64 | b 3]
   float* raw_dw = nullptr;            // InfoInv density MLP [W1 32*72 | b1 32 | W2 32*32 | b2 32 | W3 32 | b3 1]

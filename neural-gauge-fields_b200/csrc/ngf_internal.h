@@ -47,7 +47,9 @@ struct RenderArgs {
   unsigned int* queue_count;   // zero-initialised: colour work items appended so far
   QEntry* queue;               // [queue_cap] colour work items (march kernel -> colour kernel)
   unsigned int queue_cap;
-  void* ii_ws;                 // InfoInv: workspace of the three-phase march (ngf_infoinv_march.cuh), 192 B per ray + 64 B
+  void* ii_ws;                 // InfoInv: workspace of the tensor-core march (ngf_infoinv_tc.cuh: 64 B + 4 B per ray + 32 B per
+                               // sample slot) or of the opt-in three-phase march (ngf_infoinv_march.cuh: 192 B per ray + 64 B)
+  int ii_tc;                   // 1: ii_ws is laid out for the tensor-core march
   unsigned long long* stats;   // [5]: samples_in_box, samples_density, samples_colour, mlp_tiles, direct_patches (accumulated)
   int n_tiles;
 };

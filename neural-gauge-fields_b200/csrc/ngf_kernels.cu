@@ -21,6 +21,7 @@
 #include "ngf_handle.h"
 #include "ngf_colour_tma.cuh"
 #include "ngf_infoinv_march.cuh"
+#include "ngf_infoinv_tc.cuh"
 
 namespace ngf {
 
@@ -330,7 +331,58 @@ static cudaError_t launch_infoinv_march_t(const FieldDev& f, const RenderArgs& a
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+// InfoInv: find / tensor-core density / composite (ngf_infoinv_tc.cuh)
+template <bool JIT>
+static cudaError_t launch_infoinv_tc_t(const FieldDev& f, const RenderArgs& a, int num_sms, cudaStream_t st) {
+  uint8_t* base = static_cast<uint8_t*>(a.ii_ws);
+  IiTcWs ws;
+  ws.counts = reinterpret_cast<unsigned int*>(base);
+  ws.head = reinterpret_cast<int*>(base + 64);
+  const size_t head_bytes = (((size_t)a.n_rays * 4 + 63) / 64) * 64;
+  ws.entry = reinterpret_cast<IiEntry*>(base + 64 + head_bytes);
+  ws.cap = (unsigned int)((long long)a.n_rays * a.S < 0xfffffff0ll ? (long long)a.n_rays * a.S : 0xfffffff0ll);
+  cudaError_t e = cudaMemsetAsync(ws.counts, 0, 64, st);
+  if (e != cudaSuccess) return e;
+  {
+    auto kern = ngf_ii_find_kernel<JIT>;
+    long long want = ((long long)a.n_tiles + 7) / 8, grid = (long long)num_sms * 3;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, 256, 0, st>>>(f, a, ws);
+    NGF_COUNT_LAUNCH();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  {
+    auto kern = ngf_ii_density_kernel;
+    const size_t smem = IiSmem::offEnd;
+    static PerDevice<int> configured;
+    bool fresh = false;
+    configured.get(&fresh);
+    if (fresh) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { configured.retry(); return e; }
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+    long long grid = (long long)num_sms * 2, worst = ((long long)ws.cap + kTileM - 1) / kTileM;
+    if (grid > worst) grid = worst;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(f, ws, a.stats);
+    NGF_COUNT_LAUNCH();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  {
+    long long grid = (a.n_rays + 255) / 256;
+    if (grid > (long long)num_sms * 8) grid = (long long)num_sms * 8;
+    ngf_ii_composite_kernel<<<(unsigned)grid, 256, 0, st>>>(f, a, ws);
+    NGF_COUNT_LAUNCH();
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
 cudaError_t launch_march(const FieldDev& f, const RenderArgs& a, int num_sms, cudaStream_t st) {
+  if (f.variant == 1 && a.ii_ws && a.ii_tc)
+    return a.jitter ? launch_infoinv_tc_t<true>(f, a, num_sms, st) : launch_infoinv_tc_t<false>(f, a, num_sms, st);
   if (f.variant == 1 && a.ii_ws) return a.jitter ? launch_infoinv_march_t<true>(f, a, num_sms, st) : launch_infoinv_march_t<false>(f, a, num_sms, st);
   if (a.jitter) return f.variant == 0 ? launch_march_t<0, true>(f, a, num_sms, st) : launch_march_t<1, true>(f, a, num_sms, st);
   return f.variant == 0 ? launch_march_t<0, false>(f, a, num_sms, st) : launch_march_t<1, false>(f, a, num_sms, st);

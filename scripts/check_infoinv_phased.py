@@ -1,13 +1,14 @@
-"""Run with NGF_INFOINV_PHASED=1: the InfoInv march then runs as the three-phase cooperative kernel
-(csrc/ngf_infoinv_march.cuh: find samples / density MLP per lane / composite, in rounds).  Every InfoInv golden (render and
-training-time forward) must still match, bit for bit in depth and sample counts with the default march."""
+"""Run with NGF_INFOINV_PHASED=1 or NGF_INFOINV_TC=1: the InfoInv march then runs as the three-phase cooperative kernel
+(csrc/ngf_infoinv_march.cuh: find samples / density MLP per lane / composite, in rounds) or as find / tensor-core density /
+composite (csrc/ngf_infoinv_tc.cuh: split-fp16 tcgen05 MMAs).  Every InfoInv golden (render and training-time forward) must
+still match."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from oracle import cases as K
 from helpers import build_cuda_field, forward_kwargs, load_golden
-assert os.environ.get("NGF_INFOINV_PHASED") == "1"
+assert os.environ.get("NGF_INFOINV_PHASED") == "1" or os.environ.get("NGF_INFOINV_TC") == "1"
 ok = True
 for case in list(K.CASES) + list(K.TRAIN_CASES):
     if case.variant != "infoinv":

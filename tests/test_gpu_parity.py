@@ -291,13 +291,15 @@ def test_colour_kernel_with_tma_staged_gather():
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
 
 
-def test_infoinv_phased_march():
-    """The opt-in three-phase cooperative march of the InfoInv field (NGF_INFOINV_PHASED=1) against the InfoInv goldens."""
+@pytest.mark.parametrize("switch", ["NGF_INFOINV_PHASED", "NGF_INFOINV_TC"])
+def test_infoinv_alternative_marches(switch):
+    """The two opt-in marches of the InfoInv field against the InfoInv goldens: the three-phase cooperative kernel
+    (NGF_INFOINV_PHASED=1) and find / tensor-core density (split-fp16 tcgen05 MMAs) / composite (NGF_INFOINV_TC=1)."""
     import subprocess
     import sys
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, NGF_INFOINV_PHASED="1")
+    env = dict(os.environ, **{switch: "1"})
     res = subprocess.run([sys.executable, os.path.join(root, "scripts", "check_infoinv_phased.py")], env=env,
                          capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
