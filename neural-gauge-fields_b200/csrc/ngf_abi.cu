@@ -687,8 +687,11 @@ static int host_enqueue(NgfField h, const float* rays_host, long long n_rays, in
     CU(cudaStreamWaitEvent(c.stream, c.ev_out, 0));      // ... and the slot's result buffers must have been downloaded
     CamDev cam_chunk{};
     if (cam) { cam_chunk = *cam; cam_chunk.base = s; }
+    // slots i and i + kHostComp run on the same compute stream, one after the other: they share one colour queue and one
+    // set of counters (the queue is sized for the worst case of a chunk, n * S items)
+    HostChunk& qs = h->chunk[ci % kHostComp];
     int rc = ngf_render_dev(h, cam ? nullptr : c.rays, n, ray_stride, n_samples, white_bg, img ? tile_w : 0, c.rgb, c.depth,
-                        c.acc, c.counters, &c.queue, &c.queue_cap, mlp_impl, c.stream, cam ? &cam_chunk : nullptr);
+                        c.acc, qs.counters, &qs.queue, &qs.queue_cap, mlp_impl, c.stream, cam ? &cam_chunk : nullptr);
     if (rc) return rc;
     if (u8_host) CU(launch_frame_post(c.rgb, nullptr, n * 3, c.u8, nullptr, h->num_sms, c.stream));   // main.py:116
     CU(cudaEventRecord(c.ev_comp, c.stream));

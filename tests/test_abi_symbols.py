@@ -55,6 +55,18 @@ def test_argument_validation_without_gpu(lib):
     d.plane_c, d.density_c = 32, 8
     assert lib.ngf_field_pack(C.byref(d), 0, C.byref(h)) == L.NGF_EUNSUPPORTED
     assert lib.ngf_field_render(None, None, 0, 6, 0, 1, 0, None, None, None, 0, None) == L.NGF_EINVAL
+    # round-2 entry points: argument errors are reported before any CUDA call
+    assert lib.ngf_field_backward(None, None, 0, 6, 0, 1, None, None, None, None) == L.NGF_EINVAL
+    assert lib.ngf_adam_step(None, None, None, None, 4, 1e-3, 0.9, 0.99, 1e-8, 1, None) == L.NGF_EINVAL
+    assert lib.ngf_depth_colormap(None, 4, 2.0, 6.0, None, None) == L.NGF_EINVAL
+    comm = C.c_void_p()
+    assert lib.ngf_comm_init(5, 2, 0, 1000, 64, 3, L.COMM_COPY, C.byref(comm)) == L.NGF_EINVAL      # rank outside the world
+    assert lib.ngf_comm_init(0, 2, 0, 1000, 64, 9, L.COMM_COPY, C.byref(comm)) == L.NGF_EINVAL      # too many frame buffers
+    assert lib.ngf_comm_init(0, 2, 0, 1000, 64, 3, 7, C.byref(comm)) == L.NGF_EINVAL                # unknown exchange mode
+    assert lib.ngf_comm_handle_bytes() == 128 and lib.ngf_comm_local_rays(None) == -1
+    assert lib.ngf_frame_allgather(None, 1, None, None) == L.NGF_EINVAL
+    t = C.c_uint64()
+    assert lib.ngf_field_render_sharded(None, None, None, 0, 6, 0, 1, 0, 0, None, C.byref(t)) == L.NGF_EINVAL
     assert lib.ngf_shard_count(10, 0, 0, 1) == -1
     assert lib.ngf_shard_count(100, 8, 1, 4) == 24         # blocks 1, 5, 9
     assert lib.ngf_shard_count(100, 8, 0, 4) == 24 + 4     # blocks 0, 4, 8 + the 4-ray tail block 12
