@@ -265,6 +265,8 @@ int ngf_field_timing_read(NgfField f, int32_t* n_launches, double* march_ms, dou
  *  ngf_field_sample_ray : Base.sample_ray, eval branch (FieldBase.py:118-137): pts [R][S][3], t [R][S],
  *                         inside [R][S] (uint8 0/1).
  *  ngf_field_alpha_keep : AlphaGridMask.sample_alpha(...) > 0 (FieldBase.py:33-37): world pts [N][3] -> uint8.
+ *  ngf_field_alpha_value: AlphaGridMask.sample_alpha(...) itself: the trilinear value of the {0,1} volume -> fp32 [N]
+ *                         (1 everywhere when the field has no mask).
  *  ngf_field_gauge      : Base.normalize_coord is NOT applied: in = normalised xyz [N][3];
  *                         out xy/yz/xz [N][2] each = TriPlane.compute_gauge (Field.py:53-75) or
  *                         InfoInv transform (InfoInv/models/Field.py:43-50).
@@ -279,6 +281,7 @@ int ngf_field_sample_ray(NgfField f, const float* rays_dev, int64_t n_rays, int3
 int ngf_field_sample_ray_jitter(NgfField f, const float* rays_dev, int64_t n_rays, int32_t ray_stride, int32_t n_samples,
                                 const float* jitter_dev, float* pts_dev, float* t_dev, uint8_t* inside_dev, void* stream);
 int ngf_field_alpha_keep(NgfField f, const float* pts_dev, int64_t n, uint8_t* keep_dev, void* stream);
+int ngf_field_alpha_value(NgfField f, const float* pts_dev, int64_t n, float* value_dev, void* stream);
 int ngf_field_gauge(NgfField f, const float* xyz_norm_dev, int64_t n, int32_t gauge_on, float* xy_dev,
                     float* yz_dev, float* xz_dev, void* stream);
 int ngf_field_density(NgfField f, const float* xy_dev, const float* yz_dev, const float* xz_dev, int64_t n,

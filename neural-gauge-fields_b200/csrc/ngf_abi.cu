@@ -1040,6 +1040,13 @@ int ngf_field_alpha_keep(NgfField h, const float* pts_dev, int64_t n, uint8_t* k
   return NGF_OK;
 }
 
+int ngf_field_alpha_value(NgfField h, const float* pts_dev, int64_t n, float* value_dev, void* stream) {
+  NGF_POINTWISE_PROLOGUE();
+  if (!pts_dev || !value_dev) return fail(NGF_EINVAL, "NULL pointer");
+  CU(launch_alpha_value(h->dev, pts_dev, n, value_dev, st));
+  return NGF_OK;
+}
+
 int ngf_field_gauge(NgfField h, const float* xyz_norm_dev, int64_t n, int32_t gauge_on, float* xy_dev,
                     float* yz_dev, float* xz_dev, void* stream) {
   NGF_POINTWISE_PROLOGUE();

@@ -61,6 +61,7 @@ cudaError_t launch_finalize(float* rgb, const float* acc, long long n_rays, int 
 cudaError_t launch_sample_ray(const FieldDev& f, const float* rays, long long n_rays, int stride, int S,
                               const float* jitter, float* pts, float* t, uint8_t* inside, cudaStream_t st);
 cudaError_t launch_alpha_keep(const FieldDev& f, const float* pts, long long n, uint8_t* keep, cudaStream_t st);
+cudaError_t launch_alpha_value(const FieldDev& f, const float* pts, long long n, float* out, cudaStream_t st);
 cudaError_t launch_gauge(const FieldDev& f, const float* xyz, long long n, int gauge_on, float* xy, float* yz,
                          float* xz, cudaStream_t st);
 cudaError_t launch_density(const FieldDev& f, const float* xy, const float* yz, const float* xz, long long n,

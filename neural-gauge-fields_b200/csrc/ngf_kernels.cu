@@ -485,6 +485,41 @@ __global__ void ngf_alpha_keep_kernel(const __grid_constant__ FieldDev f, const 
   keep[i] = (!f.has_occ || occ_keep(f, p)) ? 1 : 0;
 }
 
+// AlphaGridMask.sample_alpha(pts) itself (FieldBase.py:33-37): the trilinear value of the {0,1} volume
+// (grid_sample, align_corners=True, zeros padding) — sum of the corner weights of the set corners, in ATen's order of
+// operations for the weights ((x1 - ix) * (y1 - iy) * (z1 - iz) ...).
+__global__ void ngf_alpha_value_kernel(const __grid_constant__ FieldDev f, const float* __restrict__ pts, long long n,
+                                       float* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = 1.f;
+  if (f.has_occ) {
+    const int dims[3] = {f.occ_w, f.occ_h, f.occ_d};
+    float fi[3], fl[3];
+    int i0[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float q = __fsub_rn(__fmul_rn(__fsub_rn(pts[i * 3 + k], f.occ_lo[k]), f.occ_inv[k]), 1.f);
+      fi[k] = __fmul_rn(__fmul_rn(__fadd_rn(q, 1.f), 0.5f), (float)(dims[k] - 1));
+      fl[k] = floorf(fi[k]);
+      i0[k] = (int)fminf(fmaxf(fl[k], -2.f), (float)dims[k] + 1.f);
+    }
+    // ATen grid_sampler_3d: tnw = (ix_bse - ix) * (iy_bse - iy) * (iz_bse - iz) etc. with ix_bse = floor(ix) + 1
+    const float wx[2] = {__fsub_rn(__fadd_rn(fl[0], 1.f), fi[0]), __fsub_rn(fi[0], fl[0])};
+    const float wy[2] = {__fsub_rn(__fadd_rn(fl[1], 1.f), fi[1]), __fsub_rn(fi[1], fl[1])};
+    const float wz[2] = {__fsub_rn(__fadd_rn(fl[2], 1.f), fi[2]), __fsub_rn(fi[2], fl[2])};
+    v = 0.f;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx)
+          if (occ_bit(f, i0[0] + dx, i0[1] + dy, i0[2] + dz)) v = __fadd_rn(v, __fmul_rn(__fmul_rn(wx[dx], wy[dy]), wz[dz]));
+  }
+  out[i] = v;
+}
+
 // compute_gauge (Field.py:53-75) / transform (InfoInv Field.py:43-50) on normalised coordinates
 __global__ void ngf_gauge_kernel(const __grid_constant__ FieldDev f, const float* __restrict__ xyz, long long n,
                                  int gauge_on, float* __restrict__ xy, float* __restrict__ yz,
@@ -600,6 +635,12 @@ cudaError_t launch_sample_ray(const FieldDev& f, const float* rays, long long n_
 cudaError_t launch_alpha_keep(const FieldDev& f, const float* pts, long long n, uint8_t* keep, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   ngf_alpha_keep_kernel<<<blocks_for(n, 256), 256, 0, st>>>(f, pts, n, keep);
+  NGF_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+cudaError_t launch_alpha_value(const FieldDev& f, const float* pts, long long n, float* out, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  ngf_alpha_value_kernel<<<blocks_for(n, 256), 256, 0, st>>>(f, pts, n, out);
   NGF_COUNT_LAUNCH();
   return cudaGetLastError();
 }

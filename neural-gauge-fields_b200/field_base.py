@@ -33,8 +33,8 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 class AlphaGridMask(torch.nn.Module):
     """Binary occupancy volume with its own box (reference: FieldBase.py:22-40).  ``sample_alpha`` answers through
-    the owning field's packed bit grid; it returns 1.0 / 0.0 where the reference returns the trilinear value — every
-    caller only tests ``> 0`` (FieldBase.py:145,239,264)."""
+    the owning field's packed bit grid (ngf_field_alpha_value): the trilinear value of the {0,1} volume, as the
+    reference's ``F.grid_sample`` returns it."""
 
     def __init__(self, device, aabb, alpha_volume):
         super().__init__()
@@ -55,7 +55,7 @@ class AlphaGridMask(torch.nn.Module):
         if owner is None or owner.alphaMask is not self:
             raise RuntimeError("this AlphaGridMask is not the mask of a live field (assign it to field.alphaMask first); "
                                "a detached or replaced mask would answer from another mask's packed bits")
-        return owner._alpha_keep(xyz_sampled).float()
+        return owner._alpha_value(xyz_sampled)
 
 
 class _RenderTrain(torch.autograd.Function):
@@ -566,6 +566,16 @@ class Base(torch.nn.Module):
             _lib.check(_lib.load().ngf_field_alpha_keep(h, pts.data_ptr(), pts.shape[0], keep.data_ptr(),
                                                         _cuda_stream_ptr(self.device)))
         return keep.bool()
+
+    @torch.no_grad()
+    def _alpha_value(self, xyz):
+        h = self._ensure_handle()
+        pts = _f32c(xyz.to(self.device)).view(-1, 3)
+        out = torch.empty((pts.shape[0],), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().ngf_field_alpha_value(h, pts.data_ptr(), pts.shape[0], out.data_ptr(),
+                                                         _cuda_stream_ptr(self.device)))
+        return out.view(xyz.shape[:-1])
 
     @torch.no_grad()
     def _coords(self, valid_xyz, gauge_on: bool):

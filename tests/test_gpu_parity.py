@@ -103,8 +103,14 @@ def test_pointwise_api_matches_reference_golden(variant):
         assert np.abs(a.cpu().numpy() - gold[k]).max() < 1e-6
     assert np.abs(sigma.cpu().numpy() - gold["sigma"]).max() <= 2e-5 * max(1.0, np.abs(gold["sigma"]).max())
     assert np.abs(rgb.cpu().numpy() - gold["rgb"]).max() < RGB_TOL
-    keep = f.alphaMask.sample_alpha(world.cuda()) > 0
-    assert np.array_equal(keep.cpu().numpy(), gold["alpha_keep"])          # bit-exact: integer decision
+    val = f.alphaMask.sample_alpha(world.cuda())
+    assert np.array_equal((val > 0).cpu().numpy(), gold["alpha_keep"])     # bit-exact: integer decision
+    # and the value itself is grid_sample's trilinear value of the {0,1} volume (FieldBase.py:33-37), not a 0/1 flag
+    spec = oracle_spec(case, state, kw, occ)
+    lo, inv = spec.alpha_aabb[0], 1.0 / (spec.alpha_aabb[1] - spec.alpha_aabb[0]) * 2
+    want = torch.nn.functional.grid_sample(spec.alpha_volume, ((world - lo) * inv - 1).view(1, -1, 1, 1, 3),
+                                           align_corners=True).view(-1)
+    assert (val.cpu() - want).abs().max() < 1e-5 and float(((want > 0) & (want < 1)).float().mean()) > 0.01
     alpha = f.compute_alpha(world.cuda(), f.stepSize)
     assert np.abs(alpha.cpu().numpy() - gold["alpha"]).max() < 2e-5
     pts, t, inside = f.sample_ray(rays[:64, :3].cuda(), rays[:64, 3:6].cuda(), is_train=False, N_samples=48)
