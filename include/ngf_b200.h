@@ -430,6 +430,16 @@ int ngf_neutex_render(NgfNeutex h, const float* campos_dev, const float* raydir_
  * are in color_host / transmittance_host. */
 int ngf_neutex_render_host(NgfNeutex h, const float* campos_host, const float* raydir_host, const float* background_host,
                            const float* noise_host, int64_t n_rays, float* color_host, float* transmittance_host);
+/* Arithmetic of the three MLP stacks: 0 (default) = tcgen05 tensor cores, fp16 operands / fp32 accumulation with the
+ * gauge network and the first geometry layer in split fp16; 1 = plain fp32 on the CUDA cores from the unpacked
+ * parameters (several times slower; the fall-back for checkpoints whose activations leave fp16's range or precision).
+ * The environment variable NGF_NTX_FP32=1 selects 1 at pack time. */
+int ngf_neutex_set_precision(NgfNeutex h, int32_t mode);
+/* Evaluate n_points seeded random in-cube points with random unit view directions through BOTH arithmetic paths and
+ * report, in report[4] (host): max |sigma_tc - sigma_fp32| / (1 + |sigma_fp32|), max |rgb_tc - rgb_fp32|, the mean of
+ * that rgb deviation, and max |rgb_fp32|.  What a caller runs after loading a trained checkpoint to decide whether the
+ * fp16 path is good enough for it.  Synchronous; overwrites the per-sample workspace of the last render. */
+int ngf_neutex_self_check(NgfNeutex h, int32_t n_points, uint64_t seed, float* report, void* stream);
 /* In-cube samples the last render evaluated (synchronises `stream`). */
 int ngf_neutex_last_valid_samples(NgfNeutex h, uint64_t* n_valid, void* stream);
 /* Per-sample view of the last render (tests): (sigma, r, g, b) of samples [first_sample, first_sample+n) — defined only

@@ -943,6 +943,103 @@ cudaError_t launch_neutex_mlp(const NetDev& net, const RenderArgsN& a, int num_s
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// fp32 reference evaluation (one warp per in-cube sample): the same networks as ntx_mlp_kernel, from the unpacked fp32
+// parameters, every layer a plain dot product per output.  ~30x slower than the tensor-core kernel; used by
+// ngf_neutex_self_check and as the NGF_NTX_FP32 / ngf_neutex_set_precision fallback for networks whose fp16 evaluation
+// leaves the 1e-3 image budget (ill-conditioned trained weights).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kRefWarps = 8, kRefWidth = 320;
+__device__ __forceinline__ void ref_dense(const RawNet& raw, int l, const float* __restrict__ x, float* __restrict__ y, int act,
+                                          int lane) {
+  const int in = raw.in[l], out = raw.out[l];
+  for (int n = lane; n < out; n += 32) {
+    const float* w = raw.w[l] + (size_t)n * in;
+    float acc = __ldg(raw.b[l] + n);
+    for (int k = 0; k < in; ++k) acc = fmaf(__ldg(w + k), x[k], acc);
+    y[n] = act == 1 ? fmaxf(acc, 0.f) : act == 2 ? (acc > 0.f ? acc : 0.2f * acc) : acc;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void ref_encode(const float* v, int dims, int freqs, float* out, int lane) {
+  // [x, sin(x_d 2^f) (d-major), cos(same)]   (util.py:427-438)
+  for (int i = lane; i < dims; i += 32) out[i] = v[i];
+  for (int i = lane; i < dims * freqs; i += 32) {
+    const float a = v[i / freqs] * (float)(1 << (i % freqs));
+    out[dims + i] = sinf(a);
+    out[dims + dims * freqs + i] = cosf(a);
+  }
+  __syncwarp();
+}
+__global__ void __launch_bounds__(kRefWarps * 32) ntx_ref_kernel(const __grid_constant__ NetDev net,
+                                                                 const __grid_constant__ RawNet raw,
+                                                                 const __grid_constant__ RenderArgsN a) {
+  __shared__ float buf[kRefWarps][2][kRefWidth];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned count = a.counters[0];
+  float* x = buf[warp][0];
+  float* y = buf[warp][1];
+  for (unsigned item = blockIdx.x * kRefWarps + warp; item < count; item += gridDim.x * kRefWarps) {
+    const float4 e = a.work[item];
+    const int id = __float_as_int(e.x);
+    const float p[3] = {e.y, e.z, e.w};
+    const float* rd = a.raydir + (size_t)(id >> 6) * 3;
+    const float dir[3] = {rd[0], rd[1], rd[2]};
+    // geometry
+    ref_encode(p, 3, 10, x, lane);
+    for (int l = 0; l < 11; ++l) { ref_dense(raw, l, x, y, 1, lane); float* t = x; x = y; y = t; }
+    ref_dense(raw, 11, x, y, 0, lane);
+    const float sigma = softplus_t(y[0]);
+    __syncwarp();
+    // gauge
+    ref_encode(p, 3, 10, x, lane);
+    for (int l = 12; l < 16; ++l) { ref_dense(raw, l, x, y, 1, lane); float* t = x; x = y; y = t; }
+    ref_dense(raw, 16, x, y, 0, lane);
+    float uv[3];
+    if (net.sphere) {
+      const float nrm = fmaxf(sqrtf(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]), 1e-12f);
+      uv[0] = y[0] / nrm; uv[1] = y[1] / nrm; uv[2] = y[2] / nrm;
+    } else {
+      uv[0] = tanhf(y[0]); uv[1] = tanhf(y[1]); uv[2] = 0.f;
+    }
+    __syncwarp();
+    // texture block1, color1
+    ref_encode(uv, net.sphere ? 3 : 2, 10, x, lane);
+    for (int l = 17; l < 23; ++l) { ref_dense(raw, l, x, y, 2, lane); float* t = x; x = y; y = t; }
+    ref_dense(raw, 23, x, y, 0, lane);                    // color1: x = h (256), y = 3
+    const float c1[3] = {softplus_t(y[0]), softplus_t(y[1]), softplus_t(y[2])};
+    __syncwarp();
+    // block2: [h, d, PE(d, 6)] (295)
+    ref_encode(dir, 3, 6, x + 256, lane);
+    for (int l = 24; l < 28; ++l) { ref_dense(raw, l, x, y, 2, lane); float* t = x; x = y; y = t; }
+    ref_dense(raw, 28, x, y, 0, lane);
+    if (lane == 0) {
+      float rgb[3] = {c1[0] + y[0], c1[1] + y[1], c1[2] + y[2]};
+      if (net.texture == nullptr) {
+        for (int k = 0; k < 3; ++k) rgb[k] = fmaxf(rgb[k], 0.f);
+      } else {
+        float m = 0.f;
+        for (int k = 0; k < 3; ++k) m += fminf(fmaxf(rgb[k] * 8.f, 0.f), 1.f);
+        m = m / 3.f;
+        float tx[3];
+        sample_texture(net, uv[0], uv[1], tx);
+        for (int k = 0; k < 3; ++k) rgb[k] = tx[k] * m;
+      }
+      a.sample_out[id] = make_float4(sigma, rgb[0], rgb[1], rgb[2]);
+    }
+    __syncwarp();
+  }
+}
+
+cudaError_t launch_neutex_ref(const NetDev& net, const RawNet& raw, const RenderArgsN& a, cudaStream_t st) {
+  long long worst = (a.n_rays * kS + kRefWarps - 1) / kRefWarps;
+  long long grid = worst < 148 * 8 ? worst : 148 * 8;
+  if (grid < 1) grid = 1;
+  ntx_ref_kernel<<<(unsigned)grid, kRefWarps * 32, 0, st>>>(net, raw, a);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_neutex_march(const NetDev& net, const RenderArgsN& a, cudaStream_t st) {
   if (a.n_rays <= 0) return cudaSuccess;
   ntx_march_kernel<<<(unsigned)((a.n_rays + 127) / 128), 128, 0, st>>>(net, a);

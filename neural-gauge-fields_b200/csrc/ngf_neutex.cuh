@@ -86,6 +86,15 @@ struct RenderArgsN {
   float* transmittance;    // [R]
 };
 
+// fp32 CUDA-core evaluation of the three networks from the unpacked parameters (fallback / self-check): raw = every layer's
+// W [out][in] then b [out], in NgfNeutexDesc order (geometry 12, gauge 5, tex_block1 6, tex_color1, tex_block2 5)
+struct RawNet {
+  const float* w[29];
+  const float* b[29];
+  int in[29], out[29];
+};
+cudaError_t launch_neutex_ref(const NetDev& net, const RawNet& raw, const RenderArgsN& a, cudaStream_t st);
+
 cudaError_t launch_neutex_raygen(const NetDev& net, const RenderArgsN& a, cudaStream_t st);
 cudaError_t launch_neutex_mlp(const NetDev& net, const RenderArgsN& a, int num_sms, cudaStream_t st);
 cudaError_t launch_neutex_march(const NetDev& net, const RenderArgsN& a, cudaStream_t st);

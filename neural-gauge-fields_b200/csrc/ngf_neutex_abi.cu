@@ -44,6 +44,9 @@ struct NgfNeutex_ {
   unsigned long long* valid_mask = nullptr;
   unsigned int* counters = nullptr;          // [0] work count, [1] spare, [2..3] u64 valid-sample total
   float* cam_bg = nullptr;                   // [6]: campos, background (host path)
+  float* rawbuf = nullptr;                   // unpacked fp32 parameters (fp32 fallback / self-check)
+  RawNet raw{};
+  int precision = 0;                         // 0: tcgen05 fp16 / split fp16 (ntx_mlp_kernel), 1: fp32 CUDA cores (ntx_ref_kernel)
   NtxChunk chunk[2];
   long long chunk_cap = 0;
   std::vector<cudaEvent_t> ev;               // 4 per timed render: raygen | mlp | march
@@ -68,6 +71,7 @@ static void ntx_free_all(NgfNeutex_* h) {
   ntx_free_chunks(h);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   cudaFree(h->wstream); cudaFree(h->heads); cudaFree(h->texture); cudaFree(h->counters); cudaFree(h->cam_bg);
+  cudaFree(h->rawbuf);
 }
 
 struct Guard {
@@ -155,7 +159,15 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
   int cg = 1;
   { const char* ce = getenv("NGF_NTX_CG"); if (ce && atoi(ce) == 2 && h->num_sms >= 2) cg = 2; }
   std::vector<uint8_t> wp[2];
-  std::vector<float> heads(kHeadFloats, 0.f), W, B, Wb;
+  std::vector<float> heads(kHeadFloats, 0.f), W, B, Wb, rawv;
+  std::vector<size_t> raw_off;
+  std::vector<int> raw_in, raw_out;
+  auto keep_raw = [&](const NgfLinear& l) {
+    raw_off.push_back(rawv.size());
+    raw_in.push_back(l.in_dim); raw_out.push_back(l.out_dim);
+    rawv.insert(rawv.end(), W.begin(), W.begin() + (size_t)l.out_dim * l.in_dim);
+    rawv.insert(rawv.end(), B.begin(), B.begin() + l.out_dim);
+  };
   int li = 0;
   // The bias is accumulated by the tensor core: the view-direction operand carries two constant-one columns
   // (kOnesCol, kOnesCol + 1 = columns 7 and 8 of its third K=16 slice) and the weights hold (bias_hi, bias_lo) there.
@@ -163,6 +175,7 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
   auto add = [&](const NgfLinear& l, int K, int Kext, bool split) -> int {
     if (fetch(W, l.w, (size_t)l.out_dim * l.in_dim) != cudaSuccess || fetch(B, l.b, l.out_dim) != cudaSuccess)
       return ngf_set_error(NGF_ECUDA, "cannot read layer %d parameters: %s", li, cudaGetErrorString(cudaGetLastError()));
+    keep_raw(l);
     LayerDesc& L = h->net.layer[li++];
     const int N = l.out_dim;
     const bool merged = Kext > 0;
@@ -186,6 +199,7 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
   auto head = [&](const NgfLinear& l, int w_off, int b_off) -> int {
     if (fetch(W, l.w, (size_t)l.out_dim * l.in_dim) != cudaSuccess || fetch(B, l.b, l.out_dim) != cudaSuccess)
       return ngf_set_error(NGF_ECUDA, "cannot read head parameters: %s", cudaGetErrorString(cudaGetLastError()));
+    keep_raw(l);
     memcpy(heads.data() + w_off, W.data(), W.size() * sizeof(float));
     memcpy(heads.data() + b_off, B.data(), B.size() * sizeof(float));
     return NGF_OK;
@@ -228,6 +242,16 @@ int ngf_neutex_pack(const NgfNeutexDesc* d, int device, NgfNeutex* out) {
   if (e == cudaSuccess) e = cudaMemcpy(h->heads, heads.data(), heads.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->counters), 64);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->cam_bg), 6 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->rawbuf), rawv.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(h->rawbuf, rawv.data(), rawv.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && raw_off.size() == 29) {
+    for (int l = 0; l < 29; ++l) {
+      h->raw.w[l] = h->rawbuf + raw_off[l];
+      h->raw.b[l] = h->raw.w[l] + (size_t)raw_in[l] * raw_out[l];
+      h->raw.in[l] = raw_in[l]; h->raw.out[l] = raw_out[l];
+    }
+  }
+  { const char* pe = getenv("NGF_NTX_FP32"); h->precision = pe && pe[0] == '1' ? 1 : 0; }
   if (e == cudaSuccess && d->texture) {
     const size_t n = (size_t)d->tex_h * d->tex_w * d->tex_c;
     e = cudaMalloc(reinterpret_cast<void**>(&h->texture), n * sizeof(float));
@@ -300,7 +324,8 @@ static int ntx_render_dev(NgfNeutex_* h, const float* campos, const float* raydi
     if (timed) CUN(cudaEventRecord(h->ev[h->ev_used], st));
     CUN(launch_neutex_raygen(h->net, a, st));
     if (timed) CUN(cudaEventRecord(h->ev[h->ev_used + 1], st));
-    CUN(launch_neutex_mlp(h->net, a, h->num_sms, st));
+    if (h->precision == 1) CUN(launch_neutex_ref(h->net, h->raw, a, st));
+    else CUN(launch_neutex_mlp(h->net, a, h->num_sms, st));
     if (timed) CUN(cudaEventRecord(h->ev[h->ev_used + 2], st));
     CUN(launch_neutex_march(h->net, a, st));
     if (timed) {
@@ -368,6 +393,72 @@ int ngf_neutex_render_host(NgfNeutex h, const float* campos_host, const float* r
   if (rc) return rc;
   CUN(e1);
   CUN(e2);
+  return NGF_OK;
+}
+
+int ngf_neutex_set_precision(NgfNeutex h, int32_t mode) {
+  if (!h) return ngf_set_error(NGF_EINVAL, "handle is NULL");
+  if (mode != 0 && mode != 1) return ngf_set_error(NGF_EINVAL, "mode=%d (0 tensor cores, 1 fp32)", mode);
+  h->precision = mode;
+  return NGF_OK;
+}
+
+// Evaluate n_points random in-cube points (and unit view directions) through the tensor-core kernel and through the fp32
+// reference kernel and report how far they are apart.
+int ngf_neutex_self_check(NgfNeutex h, int32_t n_points, uint64_t seed, float* report, void* stream) {
+  if (!h || !report) return ngf_set_error(NGF_EINVAL, "NULL argument");
+  if (n_points < 1 || n_points > (1 << 20)) return ngf_set_error(NGF_EINVAL, "n_points=%d", n_points);
+  Guard g(h->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = ntx_ensure_ws(h, n_points, st);
+  if (rc) return rc;
+  std::vector<float4> work((size_t)n_points);
+  std::vector<float> dirs((size_t)n_points * 3);
+  uint64_t x = seed * 6364136223846793005ull + 1442695040888963407ull;
+  auto uni = [&]() { x = x * 6364136223846793005ull + 1442695040888963407ull; return (float)((x >> 40) & 0xFFFFFF) / 16777216.f; };
+  for (int i = 0; i < n_points; ++i) {
+    const int id = i * kS;
+    float4 w;
+    memcpy(&w.x, &id, 4);
+    w.y = uni() * 1.98f - 0.99f; w.z = uni() * 1.98f - 0.99f; w.w = uni() * 1.98f - 0.99f;
+    work[i] = w;
+    float d[3] = {uni() * 2.f - 1.f, uni() * 2.f - 1.f, uni() * 2.f - 1.f};
+    const float n = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) + 1e-5f;
+    for (int k = 0; k < 3; ++k) dirs[(size_t)i * 3 + k] = d[k] / n;
+  }
+  float* dirs_dev = nullptr;
+  CUN(cudaMalloc(reinterpret_cast<void**>(&dirs_dev), dirs.size() * sizeof(float)));
+  cudaError_t e = cudaMemcpyAsync(dirs_dev, dirs.data(), dirs.size() * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->work, work.data(), work.size() * sizeof(float4), cudaMemcpyHostToDevice, st);
+  const unsigned int cnt[2] = {(unsigned)n_points, 0u};
+  std::vector<float4> out_tc((size_t)n_points), out_ref((size_t)n_points);
+  RenderArgsN a{};
+  a.raydir = dirs_dev; a.n_rays = n_points;
+  a.work = h->work; a.counters = h->counters; a.valid_mask = h->valid_mask; a.sample_out = h->sample_out;
+  for (int pass = 0; pass < 2 && e == cudaSuccess; ++pass) {
+    e = cudaMemcpyAsync(h->counters, cnt, sizeof(cnt), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = pass == 0 ? launch_neutex_mlp(h->net, a, h->num_sms, st) : launch_neutex_ref(h->net, h->raw, a, st);
+    // sample_out is indexed by sample id = point * 64
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(pass == 0 ? out_tc.data() : out_ref.data(), sizeof(float4), h->sample_out, sizeof(float4) * kS,
+                            sizeof(float4), (size_t)n_points, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  }
+  cudaFree(dirs_dev);
+  if (e != cudaSuccess) { cudaGetLastError(); return ngf_set_error(NGF_ECUDA, "ngf_neutex_self_check: %s", cudaGetErrorString(e)); }
+  double max_sig = 0.0, max_rgb = 0.0, mean_rgb = 0.0, max_ref_rgb = 0.0;
+  for (int i = 0; i < n_points; ++i) {
+    const float4 t = out_tc[i], r = out_ref[i];
+    max_sig = fmax(max_sig, fabs((double)t.x - r.x) / (1.0 + fabs((double)r.x)));
+    const double d = fmax(fabs((double)t.y - r.y), fmax(fabs((double)t.z - r.z), fabs((double)t.w - r.w)));
+    // fmax drops NaNs: a non-finite tensor-core result must read as a failure, not as agreement
+    const bool finite = std::isfinite(t.x) && std::isfinite(t.y) && std::isfinite(t.z) && std::isfinite(t.w);
+    max_rgb = finite ? fmax(max_rgb, d) : INFINITY;
+    if (!finite) max_sig = INFINITY;
+    mean_rgb += finite ? d : 0.0;
+    max_ref_rgb = fmax(max_ref_rgb, fmax(fabs((double)r.y), fmax(fabs((double)r.z), fabs((double)r.w))));
+  }
+  report[0] = (float)max_sig; report[1] = (float)max_rgb; report[2] = (float)(mean_rgb / n_points); report[3] = (float)max_ref_rgb;
   return NGF_OK;
 }
 

@@ -171,6 +171,8 @@ class NeuTex(nn.Module):
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
         _lib.check(lib.ngf_neutex_pack(C.byref(d), idx, C.byref(h)), "ngf_neutex_pack")
         self._handle, self._handle_sig = h, sig
+        if getattr(self, "_precision", None) is not None:             # set_precision() survives a re-pack
+            _lib.check(lib.ngf_neutex_set_precision(h, 1 if self._precision == "fp32" else 0), "ngf_neutex_set_precision")
         return h
 
     # ------------------------------------------------------------------ render
@@ -217,6 +219,24 @@ class NeuTex(nn.Module):
                                                       noise.data_ptr(), R, color_host.data_ptr(), trans_host.data_ptr()),
                    "ngf_neutex_render_host")
         return color_host, trans_host
+
+    def set_precision(self, mode: str):
+        """"tc" (default): tcgen05 fp16 / split-fp16 tensor-core arithmetic; "fp32": the CUDA-core fp32 kernel over the
+        unpacked parameters (ngf_neutex_set_precision) — slower, for checkpoints the self-check flags."""
+        if mode not in ("tc", "fp32"):
+            raise ValueError('precision is "tc" or "fp32"')
+        self._precision = mode
+        _lib.check(_lib.load().ngf_neutex_set_precision(self._ensure_handle(), 1 if mode == "fp32" else 0),
+                   "ngf_neutex_set_precision")
+
+    def self_check(self, n_points: int = 4096, seed: int = 0) -> dict:
+        """Deviation of the tensor-core path from the fp32 path on seeded random in-cube points (ngf_neutex_self_check):
+        {"sigma_rel": max |d sigma| / (1 + |sigma|), "rgb_max": max |d rgb|, "rgb_mean": ..., "rgb_range": max |rgb|}."""
+        rep = (C.c_float * 4)()
+        _lib.check(_lib.load().ngf_neutex_self_check(self._ensure_handle(), n_points, seed, rep,
+                                                     int(torch.cuda.current_stream(self.device).cuda_stream)),
+                   "ngf_neutex_self_check")
+        return {"sigma_rel": rep[0], "rgb_max": rep[1], "rgb_mean": rep[2], "rgb_range": rep[3]}
 
     def last_valid_samples(self) -> int:
         n = C.c_uint64()
