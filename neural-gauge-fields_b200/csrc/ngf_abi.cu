@@ -443,6 +443,7 @@ static int pack_params(NgfField_* h, const NgfFieldDesc* d, bool allocate) {
     CU(cudaMemcpy(h->w2p, w2p.data(), w2p.size() * sizeof(__half), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->tail, tail.data(), tail.size() * sizeof(float), cudaMemcpyHostToDevice));
     f.w1p = h->w1p; f.w2p = h->w2p; f.tail = h->tail;
+    memcpy(f.tail_c, tail.data(), sizeof(f.tail_c));
     {
       std::vector<float> raw;                       // unfolded fp32 weights, for the backward pass
       raw.insert(raw.end(), B.begin(), B.end()); raw.insert(raw.end(), W1.begin(), W1.end());

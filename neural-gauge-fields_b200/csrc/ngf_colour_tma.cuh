@@ -37,6 +37,7 @@ struct TmaSmem {                                           // shared-memory carv
   static constexpr uint32_t kW2Bytes = (kMid / 8) * kMid * 16;
   static constexpr uint32_t kLboA = kTileM * 16 + 16;
   static constexpr uint32_t kABytes = NKC * kLboA;
+  static constexpr bool kPermuteRows = false;
   static constexpr bool kAliasH = true;                    // the hidden tile reuses the (dead by then) layer-1 operand
   static constexpr uint32_t offW1 = 0;
   static constexpr uint32_t offW2 = offW1 + kW1Bytes;
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 2) ngf_colour_tma_kernel(const __gri
       asm volatile("bar.sync 1, 128;" ::: "memory");       // the mask is cleared before anyone ORs into it
       if (next < n_tiles) tma_prefetch(f, smem, src, next * kTileM, count, e0, e1, n_direct);
     };
-    mlp_layers<L, 0, true>(smem, 0u, phase, a.rgb, between);
+    mlp_layers<L, 0, true>(f, smem, 0u, phase, a.rgb, between);
   }
   mlp_teardown<0>(smem, L::offCtl);
   if (tid == 0) atomicAdd(a.stats + 3, (unsigned long long)done);

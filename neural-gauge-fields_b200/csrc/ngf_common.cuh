@@ -36,6 +36,8 @@ struct GaugeDev {
   float wm1, hm1;
 };
 
+constexpr int kTailFloats = 3 * 64 + 64 + 4;                        // 260
+
 struct FieldDev {
   int variant;
   PlaneDev plane[3];              // xy (u=x,v=y), yz (u=y,v=z), xz (u=x,v=z)
@@ -65,6 +67,8 @@ struct FieldDev {
   const __half* w1p;
   const __half* w2p;
   const float* tail;
+  // the same tail by value: kernels read it from their parameter bank with compile-time offsets (mlp_head_partial)
+  float tail_c[kTailFloats];
   // three 128-byte TMA tensor maps (device memory) over the appearance planes [H][W][48] fp16 with 48 x 5 x 5 boxes, or
   // nullptr (InfoInv; driver without cuTensorMapEncodeTiled): ngf_colour_tma.cuh
   const void* tmap;
@@ -110,7 +114,6 @@ __device__ __forceinline__ void camera_ray(const CamDev& c, long long ray, float
 }
 
 constexpr int kDmlpFloats = 32 * 72 + 32 + 32 * 32 + 32 + 32 + 1;   // 3457
-constexpr int kTailFloats = 3 * 64 + 64 + 4;                        // 260
 
 // ---------------------------------------------------------------------------------------------------------
 // Base.sample_ray prologue (FieldBase.py:121-125): first sample distance t0.

@@ -156,6 +156,8 @@ struct MlpSmem {
   static constexpr uint32_t kHBytes = (kMid / 8) * kTileM * 16;    // 16384
   // InfoInv aliases the hidden tile onto the (dead by then) A tile to stay within two CTAs per SM.
   static constexpr bool kAliasH = (V == 1);
+  // TriPlane: sample g of the tile lives in operand row tile_row(g) (see tile_row below)
+  static constexpr bool kPermuteRows = (V == 0);
   static constexpr uint32_t offW1 = 0;
   static constexpr uint32_t offW2 = offW1 + kW1Bytes;
   static constexpr uint32_t offA = offW2 + kW2Bytes;
@@ -167,6 +169,23 @@ struct MlpSmem {
   static constexpr uint32_t kCtlBytes = 64;
   static constexpr uint32_t offEnd = offCtl + kCtlBytes;
 };
+
+// Which operand row (= TMEM lane) holds sample g of a tile.  The TriPlane gather gives six consecutive lanes the six
+// 16-byte chunks of one sample, so a quarter warp stores chunks 0..5 of sample g and 0..1 of sample g+1 (then 2..5 | 0..3,
+// 4..5 | 0..5); with rows in sample order the two partial rows collide in the shared-memory banks (bank = chunk + row
+// mod 8 with the padded K-group stride): every operand store took two wavefronts per quarter warp.  Rows taken in the order
+// r0, r0+6, r0+4, r0+2 (mod 8) within each group of four samples make the eight banks of every quarter warp distinct; two
+// groups (r0 = 0 and r0 = 1) fill an aligned block of eight rows, so the map is a permutation of each 8-row core matrix.
+template <bool PERM>
+__device__ __forceinline__ int tile_row(int g) {
+  return PERM ? (g & ~7) | ((((g >> 2) & 1) + 6 * (g & 3)) & 7) : g;
+}
+template <bool PERM>
+__device__ __forceinline__ int tile_sample(int row) {
+  if (!PERM) return row;
+  const int res = row & 7, p = res & 1;
+  return (row & ~7) | (p << 2) | (((8 - (res - p)) >> 1) & 3);
+}
 
 struct MlpCtl {               // lives at offCtl
   uint64_t bar;               // mbarrier for tcgen05.commit
@@ -275,7 +294,11 @@ __device__ __forceinline__ void mlp_gather_at(const FieldDev& f, const QEntry* _
       const int m = it & (kTileM - 1), pl = it >> 7;
       const QEntry& e = q[(head + m) & (kQueueCap - 1)];
       const PlaneDev& P = f.plane[pl];
-      tapbuf[it] = to_half_taps(make_taps(e.c[2 * pl], e.c[2 * pl + 1], P.W, P.H, P.wm1, P.hm1));
+      // offsets and weights in two arrays of 16-byte slots: a 32-byte struct per lane would cost two shared-memory
+      // wavefronts per quarter warp
+      const TapsH th = to_half_taps(make_taps(e.c[2 * pl], e.c[2 * pl + 1], P.W, P.H, P.wm1, P.hm1));
+      reinterpret_cast<int4*>(tapbuf)[it] = *reinterpret_cast<const int4*>(th.off);
+      reinterpret_cast<uint4*>(tapbuf)[kTileM * 3 + it] = *reinterpret_cast<const uint4*>(th.w);
     }
     sync();
     // Phase 2: consecutive lanes take consecutive 16-byte chunks of the SAME texel (6 chunks = 96 contiguous bytes per
@@ -288,7 +311,8 @@ __device__ __forceinline__ void mlp_gather_at(const FieldDev& f, const QEntry* _
     uint4 raw[J][4];
     auto request = [&](int pl, int j) {
       const int it = tid + NT * j, chunk = it % 6;
-      t[j] = tapbuf[pl * kTileM + it / 6];
+      *reinterpret_cast<int4*>(t[j].off) = reinterpret_cast<const int4*>(tapbuf)[pl * kTileM + it / 6];
+      *reinterpret_cast<uint4*>(t[j].w) = reinterpret_cast<const uint4*>(tapbuf)[kTileM * 3 + pl * kTileM + it / 6];
       const __half* app = f.plane[pl].app;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
@@ -312,7 +336,7 @@ __device__ __forceinline__ void mlp_gather_at(const FieldDev& f, const QEntry* _
         uint4 o;
         o.x = *reinterpret_cast<uint32_t*>(&acc[0]); o.y = *reinterpret_cast<uint32_t*>(&acc[1]);
         o.z = *reinterpret_cast<uint32_t*>(&acc[2]); o.w = *reinterpret_cast<uint32_t*>(&acc[3]);
-        *reinterpret_cast<uint4*>(A + (size_t)(pl * 6 + chunk) * L::kLboA + m * 16) = o;
+        *reinterpret_cast<uint4*>(A + (size_t)(pl * 6 + chunk) * L::kLboA + tile_row<L::kPermuteRows>(m) * 16) = o;
       }
     }
   } else {
@@ -400,8 +424,9 @@ __device__ __forceinline__ void mlp_view_columns(const QEntry* __restrict__ q, u
                           pack_half2(v[6], v[7]));
     uint4 o1 = make_uint4(pack_half2(v[8], v[9]), pack_half2(v[10], v[11]), pack_half2(v[12], v[13]),
                           pack_half2(v[14], v[15]));
-    *reinterpret_cast<uint4*>(A + (size_t)(F / 8) * L::kLboA + m * 16) = o0;
-    *reinterpret_cast<uint4*>(A + (size_t)(F / 8 + 1) * L::kLboA + m * 16) = o1;
+    const int r = tile_row<L::kPermuteRows>(m);
+    *reinterpret_cast<uint4*>(A + (size_t)(F / 8) * L::kLboA + r * 16) = o0;
+    *reinterpret_cast<uint4*>(A + (size_t)(F / 8 + 1) * L::kLboA + r * 16) = o1;
   }
 }
 
@@ -422,15 +447,29 @@ struct NoBetween {
 // The layers of one MLP tile, after the layer-1 operand has been written to shared memory (layout L: MlpSmem<V> or the
 // TMA-staged colour kernel's).  `between` is called by every thread after the layer-1 MMAs have been issued and before
 // their completion is awaited (work that should hide under the tensor core, e.g. prefetching the next tile).
+// Layer 3 over 32 hidden units: h = relu(acc + b2), p += h * w3.  The constants are read from the kernel parameters
+// (FieldDev::tail_c) with compile-time offsets, so they are constant-bank operands of the FADD/FFMAs: no shared-memory
+// wavefronts (a quarter of the kernel's shared-memory traffic when they were LDS.128 broadcasts).
+template <int CH>
+__device__ __forceinline__ void mlp_head_partial(const FieldDev& f, const float (&acc)[32], float& p0, float& p1, float& p2) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    constexpr int base = CH * 128;
+    const float h = fmaxf(acc[j] + f.tail_c[base + 4 * j], 0.f);
+    p0 += h * f.tail_c[base + 4 * j + 1];
+    p1 += h * f.tail_c[base + 4 * j + 2];
+    p2 += h * f.tail_c[base + 4 * j + 3];
+  }
+}
+
 template <class L, int IMPL, bool ATOMIC, class Between>
-__device__ __forceinline__ void mlp_layers(uint8_t* smem, uint32_t head, uint32_t& phase, float* __restrict__ out,
-                                           Between between) {
+__device__ __forceinline__ void mlp_layers(const FieldDev& f, uint8_t* smem, uint32_t head, uint32_t& phase,
+                                           float* __restrict__ out, Between between) {
   constexpr int NKC = L::NKC;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = (warp & 3) * 32 + lane;        // TMEM lane == tile row handled by this thread
   const int chalf = warp >> 2;                   // which 32 of the 64 hidden columns
   MlpCtl* ctl = reinterpret_cast<MlpCtl*>(smem + L::offCtl);
-  const float* tail = reinterpret_cast<const float*>(smem + L::offTail);
   uint8_t* H = smem + L::offH;
   float acc[32];
 
@@ -540,30 +579,22 @@ __device__ __forceinline__ void mlp_layers(uint8_t* smem, uint32_t head, uint32_
 
   // ---- epilogue 2: + b2, ReLU, layer 3 (64 -> 3) partial sums over this thread's 32 hidden units
   float p0 = 0.f, p1 = 0.f, p2 = 0.f;
-  {
-    const float4* t4 = reinterpret_cast<const float4*>(tail);      // per hidden unit: (b2, w3_r, w3_g, w3_b)
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float4 c = t4[chalf * 32 + j];
-      float h = fmaxf(acc[j] + c.x, 0.f);
-      p0 += h * c.y;
-      p1 += h * c.z;
-      p2 += h * c.w;
-    }
-  }
+  if (chalf == 0) mlp_head_partial<0>(f, acc, p0, p1, p2);
+  else mlp_head_partial<1>(f, acc, p0, p1, p2);
   float4* part = reinterpret_cast<float4*>(smem + L::offPart);
   if (chalf == 1) part[row] = make_float4(p0, p1, p2, 0.f);
   if (IMPL == 0) tc_fence_before();
   __syncthreads();
   if (chalf == 0) {
     const QEntry* q = reinterpret_cast<const QEntry*>(smem + L::offQueue);
-    const QEntry& e = q[(head + row) & (kQueueCap - 1)];
+    // (w, id) of the sample in this row, one 8-byte load
+    const float2 wi = *reinterpret_cast<const float2*>(&q[(head + tile_sample<L::kPermuteRows>(row)) & (kQueueCap - 1)].w);
+    struct { float w; int id; } e = {wi.x, __float_as_int(wi.y)};
     if (e.id >= 0) {
       float4 o = part[row];
-      const float* b3 = tail + 256;
-      float r = 1.f / (1.f + expf(-(p0 + o.x + b3[0])));
-      float g = 1.f / (1.f + expf(-(p1 + o.y + b3[1])));
-      float b = 1.f / (1.f + expf(-(p2 + o.z + b3[2])));
+      float r = 1.f / (1.f + expf(-(p0 + o.x + f.tail_c[256])));
+      float g = 1.f / (1.f + expf(-(p1 + o.y + f.tail_c[257])));
+      float b = 1.f / (1.f + expf(-(p2 + o.z + f.tail_c[258])));
       float* dst = out + (size_t)e.id * 3;
       if (ATOMIC) {
         atomicAdd(dst, e.w * r);
@@ -586,7 +617,7 @@ __device__ __forceinline__ void mlp_tile(const FieldDev& f, uint8_t* smem, uint3
                                          const float* __restrict__ dir, int dir_stride, float* __restrict__ out,
                                          const CamDev* cam = nullptr) {
   mlp_gather<V>(f, smem, head, dir, dir_stride, cam);
-  mlp_layers<MlpSmem<V>, IMPL, ATOMIC>(smem, head, phase, out, NoBetween{});
+  mlp_layers<MlpSmem<V>, IMPL, ATOMIC>(f, smem, head, phase, out, NoBetween{});
 }
 
 }  // namespace ngf
