@@ -430,6 +430,19 @@ int ngf_neutex_render(NgfNeutex h, const float* campos_dev, const float* raydir_
  * are in color_host / transmittance_host. */
 int ngf_neutex_render_host(NgfNeutex h, const float* campos_host, const float* raydir_host, const float* background_host,
                            const float* noise_host, int64_t n_rays, float* color_host, float* transmittance_host);
+/* The same two calls with the jitter numbers drawn on the device instead of uploaded: sample i of frame ray r uses
+ * U = philox4x32-10(key = seed, index = r * 64 + i) >> 8 scaled to [0,1) — the role of the torch.rand call inside
+ * cube_ray_generation (renderer.py:113-118), without the 256 B per ray of host-drawn numbers.  `first_ray` is the frame
+ * index of raydir_dev[0] (a frame rendered in several calls draws the same numbers as in one).  ngf_neutex_noise writes
+ * the numbers a seeded render of rays [first_ray, first_ray + n_rays) uses into noise_dev[n_rays][sample_num], so that a
+ * checker can hand the reference the identical jitter. */
+int ngf_neutex_render_seeded(NgfNeutex h, const float* campos_dev, const float* raydir_dev, const float* background_dev,
+                             uint64_t seed, int64_t first_ray, int64_t n_rays, float* color_dev, float* transmittance_dev,
+                             void* stream);
+int ngf_neutex_render_host_seeded(NgfNeutex h, const float* campos_host, const float* raydir_host,
+                                  const float* background_host, uint64_t seed, int64_t n_rays, float* color_host,
+                                  float* transmittance_host);
+int ngf_neutex_noise(NgfNeutex h, uint64_t seed, int64_t first_ray, int64_t n_rays, float* noise_dev, void* stream);
 /* Arithmetic of the three MLP stacks: 0 (default) = tcgen05 tensor cores, fp16 operands / fp32 accumulation with the
  * gauge network and the first geometry layer in split fp16; 1 = plain fp32 on the CUDA cores from the unpacked
  * parameters (several times slower; the fall-back for checkpoints whose activations leave fp16's range or precision).

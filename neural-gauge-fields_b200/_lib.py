@@ -119,6 +119,9 @@ SIGNATURES = {
     "ngf_neutex_render_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_void_p]),
     "ngf_neutex_last_valid_samples": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
+    "ngf_neutex_render_seeded": (C.c_int, [C.c_void_p] * 4 + [C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ngf_neutex_render_host_seeded": (C.c_int, [C.c_void_p] * 4 + [C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ngf_neutex_noise": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "ngf_neutex_set_precision": (C.c_int, [C.c_void_p, C.c_int32]),
     "ngf_neutex_self_check": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(C.c_float), C.c_void_p]),
     "ngf_neutex_copy_samples": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),

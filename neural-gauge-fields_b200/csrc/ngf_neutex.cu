@@ -804,6 +804,42 @@ __device__ __forceinline__ RaySetup ray_setup(const RenderArgsN& a, long long ra
   return r;
 }
 
+// Counter-based jitter numbers (Philox 4x32, 10 rounds; Salmon et al. 2011): word (idx & 3) of block idx >> 2 under the
+// 64-bit key `seed`, top 24 bits -> U[0,1) like torch.rand's fp32 grid.  Stateless, so the ray generator and the march draw
+// the same number twice instead of storing it (256 B per ray).
+__device__ __forceinline__ float jitter_uniform(unsigned long long seed, unsigned long long idx) {
+  unsigned int c0 = (unsigned int)(idx >> 2), c1 = (unsigned int)(idx >> 34), c2 = 0u, c3 = 0u;
+  unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const unsigned int h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const unsigned int sel = (unsigned int)idx & 3u;
+  const unsigned int x = sel == 0 ? c0 : sel == 1 ? c1 : sel == 2 ? c2 : c3;
+  return (float)(x >> 8) * (1.f / 16777216.f);
+}
+__device__ __forceinline__ float jitter_at(const RenderArgsN& a, long long ray, int S, int i) {
+  if (a.noise) return __ldg(a.noise + ray * S + i);
+  return a.seeded ? jitter_uniform(a.seed, (unsigned long long)(a.ray0 + ray) * 64ull + (unsigned)i) : 0.5f;
+}
+
+__global__ void ntx_noise_kernel(unsigned long long seed, long long ray0, long long n, int S, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n * S) return;
+  const long long ray = i / S;
+  out[i] = jitter_uniform(seed, (unsigned long long)(ray0 + ray) * 64ull + (unsigned)(i - ray * S));
+}
+
+cudaError_t launch_neutex_noise(unsigned long long seed, long long ray0, long long n_rays, int S, float* noise_out, cudaStream_t st) {
+  if (n_rays <= 0) return cudaSuccess;
+  const long long n = n_rays * S;
+  ntx_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(seed, ray0, n_rays, S, noise_out);
+  return cudaGetLastError();
+}
+
 // seg_i = dt + dt*jitter*(U_i - 0.5) (renderer.py:111-118); dt = 2/S and dt*jitter are Python doubles cast to fp32
 __device__ __forceinline__ float seg_len(float dt, float dj, float u) { return __fadd_rn(dt, __fmul_rn(dj, __fsub_rn(u, 0.5f))); }
 
@@ -816,7 +852,7 @@ __device__ __forceinline__ unsigned long long walk_ray(const RenderArgsN& a, con
   int n = 0;
 #pragma unroll 4
   for (int i = 0; i < S; ++i) {
-    const float u = a.noise ? __ldg(a.noise + ray * S + i) : 0.5f;
+    const float u = jitter_at(a, ray, S, i);
     run += (double)seg_len(dt, dj, u);
     const float e = __fadd_rn(r.t, (float)run);
     const float mid = __fmul_rn(__fadd_rn(e_prev, e), 0.5f);
@@ -879,7 +915,7 @@ __global__ void __launch_bounds__(128) ntx_march_kernel(const __grid_constant__ 
   float col[3] = {0.f, 0.f, 0.f};
   for (int i = 0; i < S; ++i) {
     if (!((mask >> i) & 1ull)) continue;    // sigma * 0 -> opacity 0 -> weight 0, transmittance factor 1 + 1e-10 == 1.f
-    const float u = a.noise ? __ldg(a.noise + ray * S + i) : 0.5f;
+    const float u = jitter_at(a, ray, S, i);
     const float seg = seg_len(dt, dj, u);
     const float4 s = a.sample_out[ray * kS + i];
     const float op = __fsub_rn(1.f, expf(-__fmul_rn(s.x, seg)));

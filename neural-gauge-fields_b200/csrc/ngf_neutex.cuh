@@ -76,7 +76,12 @@ struct RenderArgsN {
   const float* campos;     // [3]
   const float* raydir;     // [R][3]
   const float* background; // [3] or nullptr
-  const float* noise;      // [R][64] or nullptr (no jitter)
+  const float* noise;      // [R][S] caller-supplied U[0,1) numbers, or nullptr
+  // noise == nullptr && seeded: the numbers are drawn in the kernels, jitter_uniform(seed, (ray0 + ray) * 64 + i);
+  // noise == nullptr && !seeded: no jitter (every U = 0.5)
+  int seeded;
+  unsigned long long seed;
+  long long ray0;          // index of this launch's first ray within the frame (batches and host chunks draw the same numbers)
   long long n_rays;
   float4* work;            // [R*64] compacted in-cube samples: (bit-cast sample id, x, y, z)
   unsigned int* counters;  // [0] work count, [1] tile counter
@@ -93,6 +98,8 @@ struct RawNet {
   const float* b[29];
   int in[29], out[29];
 };
+// Fill noise_out[n_rays][S] with the numbers a seeded render draws (tests feed them to the oracle).
+cudaError_t launch_neutex_noise(unsigned long long seed, long long ray0, long long n_rays, int S, float* noise_out, cudaStream_t st);
 cudaError_t launch_neutex_ref(const NetDev& net, const RawNet& raw, const RenderArgsN& a, cudaStream_t st);
 
 cudaError_t launch_neutex_raygen(const NetDev& net, const RenderArgsN& a, cudaStream_t st);

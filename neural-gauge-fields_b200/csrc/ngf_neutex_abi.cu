@@ -306,8 +306,16 @@ static int ntx_ensure_ws(NgfNeutex_* h, long long n_rays, cudaStream_t st) {
 // rays per internal batch: 2 x 16 B x 64 per ray of workspace -> 1 Mi rays = 2 GiB
 static const long long kNtxBatch = 1ll << 20;
 
+// where the jitter numbers of a render come from: caller's array | drawn on the device from (seed, frame ray index) | none
+struct NoiseSrc {
+  const float* ptr = nullptr;
+  bool seeded = false;
+  unsigned long long seed = 0;
+  long long ray0 = 0;
+};
+
 static int ntx_render_dev(NgfNeutex_* h, const float* campos, const float* raydir, const float* background,
-                          const float* noise, long long n_rays, float* color, float* trans, cudaStream_t st) {
+                          const NoiseSrc& nz, long long n_rays, float* color, float* trans, cudaStream_t st) {
   const long long per = n_rays < kNtxBatch ? n_rays : kNtxBatch;
   int rc = ntx_ensure_ws(h, per, st);
   if (rc) return rc;
@@ -315,7 +323,8 @@ static int ntx_render_dev(NgfNeutex_* h, const float* campos, const float* raydi
     const long long n = (n_rays - s0) < per ? (n_rays - s0) : per;
     RenderArgsN a{};
     a.campos = campos; a.raydir = raydir + s0 * 3; a.background = background;
-    a.noise = noise ? noise + s0 * h->net.S : nullptr;
+    a.noise = nz.ptr ? nz.ptr + s0 * h->net.S : nullptr;
+    a.seeded = nz.seeded ? 1 : 0; a.seed = nz.seed; a.ray0 = nz.ray0 + s0;
     a.n_rays = n;
     a.work = h->work; a.counters = h->counters; a.valid_mask = h->valid_mask; a.sample_out = h->sample_out;
     a.color = color + s0 * 3; a.transmittance = trans + s0;
@@ -336,19 +345,44 @@ static int ntx_render_dev(NgfNeutex_* h, const float* campos, const float* raydi
   return NGF_OK;
 }
 
-int ngf_neutex_render(NgfNeutex h, const float* campos_dev, const float* raydir_dev, const float* background_dev,
-                      const float* noise_dev, int64_t n_rays, float* color_dev, float* transmittance_dev, void* stream) {
+static int ntx_render_checked(NgfNeutex h, const float* campos_dev, const float* raydir_dev, const float* background_dev,
+                              const NoiseSrc& nz, int64_t n_rays, float* color_dev, float* transmittance_dev, void* stream) {
   if (!h) return ngf_set_error(NGF_EINVAL, "handle is NULL");
   if (n_rays < 0 || n_rays > (1ll << 31) / kS * 16) return ngf_set_error(NGF_EINVAL, "n_rays=%lld", (long long)n_rays);
   if (n_rays == 0) return NGF_OK;
   if (!campos_dev || !raydir_dev || !color_dev || !transmittance_dev) return ngf_set_error(NGF_EINVAL, "NULL pointer");
   Guard g(h->device);
-  return ntx_render_dev(h, campos_dev, raydir_dev, background_dev, noise_dev, n_rays, color_dev, transmittance_dev,
+  return ntx_render_dev(h, campos_dev, raydir_dev, background_dev, nz, n_rays, color_dev, transmittance_dev,
                         reinterpret_cast<cudaStream_t>(stream));
 }
 
-int ngf_neutex_render_host(NgfNeutex h, const float* campos_host, const float* raydir_host, const float* background_host,
-                           const float* noise_host, int64_t n_rays, float* color_host, float* transmittance_host) {
+int ngf_neutex_render(NgfNeutex h, const float* campos_dev, const float* raydir_dev, const float* background_dev,
+                      const float* noise_dev, int64_t n_rays, float* color_dev, float* transmittance_dev, void* stream) {
+  NoiseSrc nz;
+  nz.ptr = noise_dev;
+  return ntx_render_checked(h, campos_dev, raydir_dev, background_dev, nz, n_rays, color_dev, transmittance_dev, stream);
+}
+
+int ngf_neutex_render_seeded(NgfNeutex h, const float* campos_dev, const float* raydir_dev, const float* background_dev,
+                             uint64_t seed, int64_t first_ray, int64_t n_rays, float* color_dev, float* transmittance_dev,
+                             void* stream) {
+  if (first_ray < 0) return ngf_set_error(NGF_EINVAL, "first_ray=%lld", (long long)first_ray);
+  NoiseSrc nz;
+  nz.seeded = true; nz.seed = seed; nz.ray0 = first_ray;
+  return ntx_render_checked(h, campos_dev, raydir_dev, background_dev, nz, n_rays, color_dev, transmittance_dev, stream);
+}
+
+int ngf_neutex_noise(NgfNeutex h, uint64_t seed, int64_t first_ray, int64_t n_rays, float* noise_dev, void* stream) {
+  if (!h || !noise_dev) return ngf_set_error(NGF_EINVAL, "NULL argument");
+  if (first_ray < 0 || n_rays < 0) return ngf_set_error(NGF_EINVAL, "first_ray=%lld n_rays=%lld", (long long)first_ray, (long long)n_rays);
+  Guard g(h->device);
+  CUN(launch_neutex_noise(seed, first_ray, n_rays, h->net.S, noise_dev, reinterpret_cast<cudaStream_t>(stream)));
+  return NGF_OK;
+}
+
+static int ntx_render_host_impl(NgfNeutex h, const float* campos_host, const float* raydir_host, const float* background_host,
+                                const float* noise_host, bool seeded, uint64_t seed, int64_t n_rays, float* color_host,
+                                float* transmittance_host) {
   if (!h) return ngf_set_error(NGF_EINVAL, "handle is NULL");
   if (n_rays < 0) return ngf_set_error(NGF_EINVAL, "n_rays=%lld", (long long)n_rays);
   if (n_rays == 0) return NGF_OK;
@@ -382,8 +416,10 @@ int ngf_neutex_render_host(NgfNeutex h, const float* campos_host, const float* r
     if (noise_host) cudaMemcpyAsync(c.noise, noise_host + s * h->net.S, (size_t)n * h->net.S * sizeof(float), cudaMemcpyHostToDevice, copy);
     cudaEventRecord(up[ci], copy);
     cudaStreamWaitEvent(run, up[ci], 0);
-    rc = ntx_render_dev(h, h->cam_bg, c.raydir, background_host ? h->cam_bg + 3 : nullptr, noise_host ? c.noise : nullptr, n,
-                        c.color, c.trans, run);
+    NoiseSrc nz;
+    nz.ptr = noise_host ? c.noise : nullptr;
+    nz.seeded = seeded; nz.seed = seed; nz.ray0 = s;
+    rc = ntx_render_dev(h, h->cam_bg, c.raydir, background_host ? h->cam_bg + 3 : nullptr, nz, n, c.color, c.trans, run);
     cudaMemcpyAsync(color_host + s * 3, c.color, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, run);
     cudaMemcpyAsync(transmittance_host + s, c.trans, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, run);
     cudaEventRecord(done[ci], run);
@@ -394,6 +430,18 @@ int ngf_neutex_render_host(NgfNeutex h, const float* campos_host, const float* r
   CUN(e1);
   CUN(e2);
   return NGF_OK;
+}
+
+int ngf_neutex_render_host(NgfNeutex h, const float* campos_host, const float* raydir_host, const float* background_host,
+                           const float* noise_host, int64_t n_rays, float* color_host, float* transmittance_host) {
+  return ntx_render_host_impl(h, campos_host, raydir_host, background_host, noise_host, false, 0, n_rays, color_host,
+                              transmittance_host);
+}
+
+int ngf_neutex_render_host_seeded(NgfNeutex h, const float* campos_host, const float* raydir_host, const float* background_host,
+                                  uint64_t seed, int64_t n_rays, float* color_host, float* transmittance_host) {
+  return ntx_render_host_impl(h, campos_host, raydir_host, background_host, nullptr, true, seed, n_rays, color_host,
+                              transmittance_host);
 }
 
 int ngf_neutex_set_precision(NgfNeutex h, int32_t mode) {

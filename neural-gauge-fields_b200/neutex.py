@@ -177,47 +177,72 @@ class NeuTex(nn.Module):
 
     # ------------------------------------------------------------------ render
     @torch.no_grad()
-    def forward(self, camera_position=None, ray_direction=None, background_color=None, noise=None):
+    def forward(self, camera_position=None, ray_direction=None, background_color=None, noise=None, seed=None):
         """camera_position [N,3], ray_direction [N,R,3], background_color [N,3] or None ->
-        {'color': [N,R,3], 'transmittance': [N,R]} (model.py:27-59).  ``noise`` [N,R,64] are the U[0,1) jitter numbers
-        the reference draws with ``torch.rand`` inside ``cube_ray_generation``; drawn here the same way when omitted."""
+        {'color': [N,R,3], 'transmittance': [N,R]} (model.py:27-59).  The jitter the reference draws with ``torch.rand``
+        inside ``cube_ray_generation``: ``noise`` [N,R,sample_num] U[0,1) numbers when given; otherwise drawn inside the
+        kernels from ``seed`` (camera n uses seed + n; ``noise_for`` returns the same numbers), a fresh seed from torch's
+        generator when that is omitted too."""
         h = self._ensure_handle()
         lib, dev = _lib.load(), self.device
         cam = camera_position.to(dev).float().contiguous()
         rd = ray_direction.to(dev).float().contiguous()
         N, R = rd.shape[0], rd.shape[1]
-        S = int(getattr(self.opt, "sample_num", 64))
-        if noise is None:
-            noise = torch.rand((N, R, S), device=dev)
-        nz = noise.to(dev).float().contiguous()
+        if noise is None and seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        nz = None if noise is None else noise.to(dev).float().contiguous()
         bg = None if background_color is None else background_color.to(dev).float().contiguous()
         color = torch.empty((N, R, 3), dtype=torch.float32, device=dev)
         trans = torch.empty((N, R), dtype=torch.float32, device=dev)
         stream = int(torch.cuda.current_stream(dev).cuda_stream)
         with torch.cuda.device(dev):
             for n in range(N):
-                _lib.check(lib.ngf_neutex_render(h, cam[n].data_ptr(), rd[n].data_ptr(),
-                                                 None if bg is None else bg[n].data_ptr(), nz[n].data_ptr(), R,
-                                                 color[n].data_ptr(), trans[n].data_ptr(), stream), "ngf_neutex_render")
+                bgp = None if bg is None else bg[n].data_ptr()
+                if nz is not None:
+                    _lib.check(lib.ngf_neutex_render(h, cam[n].data_ptr(), rd[n].data_ptr(), bgp, nz[n].data_ptr(), R,
+                                                     color[n].data_ptr(), trans[n].data_ptr(), stream), "ngf_neutex_render")
+                else:
+                    _lib.check(lib.ngf_neutex_render_seeded(h, cam[n].data_ptr(), rd[n].data_ptr(), bgp, int(seed) + n, 0, R,
+                                                            color[n].data_ptr(), trans[n].data_ptr(), stream),
+                               "ngf_neutex_render_seeded")
         return {"color": color, "transmittance": trans}
 
+    def noise_for(self, seed: int, n_rays: int, first_ray: int = 0) -> torch.Tensor:
+        """[1, n_rays, sample_num] jitter numbers a render with ``seed`` draws for frame rays first_ray.. (ngf_neutex_noise)."""
+        h = self._ensure_handle()
+        S = int(getattr(self.opt, "sample_num", 64))
+        out = torch.empty((1, n_rays, S), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().ngf_neutex_noise(h, int(seed), first_ray, n_rays, out.data_ptr(),
+                                                    int(torch.cuda.current_stream(self.device).cuda_stream)), "ngf_neutex_noise")
+        return out
+
     @torch.no_grad()
-    def render_host(self, camera_position, ray_direction, background_color, noise, color_host=None, trans_host=None):
-        """One camera through HOST buffers (ngf_neutex_render_host): [1,3], [1,R,3], [1,3] or None, [1,R,64] CPU tensors
-        (pinned for full copy bandwidth) -> (color [1,R,3], transmittance [1,R]) CPU tensors."""
+    def render_host(self, camera_position, ray_direction, background_color, noise=None, color_host=None, trans_host=None,
+                    seed=None):
+        """One camera through HOST buffers (ngf_neutex_render_host[_seeded]): [1,3], [1,R,3], [1,3] or None CPU tensors
+        (pinned for full copy bandwidth), jitter as [1,R,sample_num] ``noise`` or drawn on the device from ``seed`` ->
+        (color [1,R,3], transmittance [1,R]) CPU tensors."""
         h = self._ensure_handle()
         R = ray_direction.shape[1]
-        for t in (camera_position, ray_direction, noise):
+        if (noise is None) == (seed is None):
+            raise ValueError("render_host takes either noise or seed")
+        for t in (camera_position, ray_direction) + (() if noise is None else (noise,)):
             if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
                 raise ValueError("render_host takes contiguous fp32 CPU tensors")
         if color_host is None:
             color_host = torch.empty((1, R, 3)).pin_memory()
         if trans_host is None:
             trans_host = torch.empty((1, R)).pin_memory()
-        _lib.check(_lib.load().ngf_neutex_render_host(h, camera_position.data_ptr(), ray_direction.data_ptr(),
-                                                      None if background_color is None else background_color.data_ptr(),
-                                                      noise.data_ptr(), R, color_host.data_ptr(), trans_host.data_ptr()),
-                   "ngf_neutex_render_host")
+        bgp = None if background_color is None else background_color.data_ptr()
+        if noise is not None:
+            _lib.check(_lib.load().ngf_neutex_render_host(h, camera_position.data_ptr(), ray_direction.data_ptr(), bgp,
+                                                          noise.data_ptr(), R, color_host.data_ptr(), trans_host.data_ptr()),
+                       "ngf_neutex_render_host")
+        else:
+            _lib.check(_lib.load().ngf_neutex_render_host_seeded(h, camera_position.data_ptr(), ray_direction.data_ptr(), bgp,
+                                                                 int(seed), R, color_host.data_ptr(), trans_host.data_ptr()),
+                       "ngf_neutex_render_host_seeded")
         return color_host, trans_host
 
     def set_precision(self, mode: str):

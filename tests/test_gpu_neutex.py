@@ -162,3 +162,37 @@ def test_neutex_self_check_flags_a_checkpoint_outside_fp16_range():
     mb.set_precision("fp32")
     out = mb(campos.cuda(), raydir.cuda(), bg.cuda(), noise=noise.cuda())
     assert np.abs(out["color"].cpu().numpy() - gold["color"]).max() < 2e-4
+
+
+def test_neutex_jitter_drawn_on_the_device():
+    """seed= draws the jitter inside the kernels (ngf_neutex_render_seeded: Philox 4x32-10 keyed by the seed, indexed by
+    frame ray and sample).  noise_for() exports the same numbers: fed to the oracle they give the oracle's image (<1e-3),
+    fed back through noise= they give the seeded image bit for bit; a frame rendered in pieces (host chunks of 65536 rays,
+    first_ray offsets) draws the same numbers; the numbers are uniform on [0,1)."""
+    case = K.NEUTEX_BY_NAME["neutex_white"]
+    state, tex, campos, raydir, bg, _ = K.build_neutex_inputs(case)
+    m = _build(state, tex)
+    R = raydir.shape[1]
+    args = (campos.cuda(), raydir.cuda(), bg.cuda())
+    a = m(*args, seed=1234)
+    nz = m.noise_for(1234, R)
+    b = m(*args, noise=nz)
+    assert torch.equal(a["color"], b["color"]) and torch.equal(a["transmittance"], b["transmittance"])
+    o_c, o_t = U.render(U.NeuTexSpec(state, texture=tex), campos, raydir, bg, nz.cpu())
+    assert (a["color"].cpu() - o_c).abs().max() < TOL and (a["transmittance"].cpu() - o_t).abs().max() < TOL
+    assert not torch.equal(m(*args, seed=1235)["color"], a["color"])
+    assert torch.equal(m.noise_for(1234, 100, first_ray=50), nz[:, 50:150])
+    u = m.noise_for(7, 200000).flatten()
+    assert float(u.min()) >= 0.0 and float(u.max()) < 1.0
+    assert abs(float(u.mean()) - 0.5) < 1e-3 and abs(float(u.var()) - 1 / 12) < 1e-3
+    hist = torch.histc(u, bins=16, min=0, max=1) / u.numel()
+    assert float((hist - 1 / 16).abs().max()) < 1e-3
+    # the host path (two alternating 65536-ray chunks) on a frame larger than one chunk
+    from ngf_b200 import synth
+    campos2, raydir2 = synth.neutex_camera(0)
+    rd = raydir2[:, :150000].contiguous()
+    dev = m(campos2.cuda(), rd.cuda(), bg.cuda(), seed=99)
+    c_h, t_h = m.render_host(campos2, rd.pin_memory(), bg, seed=99)
+    assert torch.equal(c_h, dev["color"].cpu()) and torch.equal(t_h, dev["transmittance"].cpu())
+    with pytest.raises(ValueError):
+        m.render_host(campos2, rd, bg)
