@@ -292,29 +292,64 @@ def main():
                           "tolerance 1e-3 rgb / 2e-3 depth (the golden tolerance; differences come from the order of the "
                           "fp32 atomic adds only)"}
 
-    # ---- device-resident timed region (value)
-    for i in range(max(args.warmup, 3)):
-        step_device(dev_rays[i % N_POSES])
-    if world > 1:
-        drain_device()
+    # ---- device-resident timed region (value).  One GPU: the frames are independent, so step i is issued on CUDA stream
+    # i % N_STREAMS (ngf_field_render keeps one workspace per caller stream) and the march of one frame runs beside the
+    # colour pass of its neighbours; the region is forked from / joined to the current stream, which carries the events.
+    N_STREAMS = int(os.environ.get("NGF_BENCH_STREAMS", "3"))
+    if world > 1 and comm_mode == "nccl":
+        N_STREAMS = 1                 # the NCCL fall-back double-buffers on its own side stream
+    side = [torch.cuda.Stream(dev) for _ in range(N_STREAMS)] if N_STREAMS > 1 else []
+
+    def run_steps(n, streams):
+        if not streams:
+            for i in range(n):
+                step_device(dev_rays[i % N_POSES])
+            if world > 1:
+                drain_device()
+            return
+        cur = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for st in streams:
+            st.wait_event(fork)
+        for i in range(n):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                step_device(dev_rays[i % N_POSES])
+        for st in streams:
+            cur.wait_stream(st)
+        if world > 1:
+            drain_device()
+
+    run_steps(max(args.warmup, 3), side)
     barrier()
     stats = field.last_stats() if world == 1 else None
-    field.kernel_timing(min(args.steps, 4096))
-    l0 = ngf_b200._lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    serial = None
+    if True:
+        # kernel durations for the roofline come from a serial pass on one stream (events around overlapping kernels would
+        # time the overlap, not the kernel); its step time is reported beside `value` as value_single_stream
+        n_serial = min(args.steps, 4096)
+        run_steps(3, [])
+        field.kernel_timing(n_serial)
+        barrier()
+        e0.record()
+        run_steps(n_serial, [])
+        e1.record()
+        barrier()
+        serial_ms = max_over_ranks(e0.elapsed_time(e1))
+        n_k, march_ms, colour_ms = field.kernel_timing_read()
+        field.kernel_timing(0)
+        serial = {"steps": n_serial, "ms_per_step": serial_ms / n_serial, "value": n_batch * n_serial / (serial_ms * 1e-3)}
+        run_steps(3, side)
+    l0 = ngf_b200._lib.launch_count()
     with ClockSampler(local) as clk:
         barrier()
         e0.record()
-        for i in range(args.steps):
-            step_device(dev_rays[i % N_POSES])
-        if world > 1:
-            drain_device()
+        run_steps(args.steps, side)
         e1.record()
         barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = ngf_b200._lib.launch_count() - l0
-    n_k, march_ms, colour_ms = field.kernel_timing_read()
-    field.kernel_timing(0)
     value = n_batch * args.steps / (ms * 1e-3)
     if stats is None:
         # the sharded path renders from the comm's own workspace; the sample statistics come from one plain render
@@ -417,7 +452,8 @@ def main():
     pk = peaks()
     n_k = max(n_k, 1)
     march_s, colour_s = march_ms / n_k * 1e-3, colour_ms / n_k * 1e-3
-    step_s = ms / args.steps * 1e-3
+    # share of the step: against the step the kernels were timed in (one GPU: the serial single-stream pass)
+    step_s = (serial["ms_per_step"] if serial else ms / args.steps) * 1e-3
     nV = stats["samples_density"] / n_local
     nA = stats["samples_colour"] / n_local
     alg_bytes = n_local * HBM_BYTES_PER_RAY
@@ -458,7 +494,8 @@ def main():
                                f"(BASELINE configs[1]" + (")" if world == 1 else f"; configs[4]: {world} frames/step ray-sharded + one all-gather of the rendered batch)"),
                    "rays_per_step": n_batch,
                    "arithmetic": "fp32 march / density / compositing; colour MLP fp16 operands with fp32 accumulation (tcgen05, TMEM)", "l2": f"inputs rotate over {N_POSES} poses ({N_POSES * n_local * 24 / 1e6:.0f} MB of rays per rank > 126 MB L2)",
-                   "parallelism": "single GPU" if world == 1 else f"ray-sharded dp{world}, {BLOCK}-ray interleaved blocks, {coll}"},
+                   "streams": N_STREAMS,
+                   "parallelism": f"single GPU, independent frames on {N_STREAMS} CUDA streams" if world == 1 else f"ray-sharded dp{world}, {BLOCK}-ray interleaved blocks, {coll}"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_local * 24, "d2h_bytes_per_step": d2h,
                 "api": e2e_api,
                 "transport_floor": {"value": e2e_floor, "unit": "rays/s", "frac_of_floor": e2e_value / e2e_floor,
@@ -468,6 +505,10 @@ def main():
         "clocks": clk.summary(),
         "roofline": roofline,
     }
+    if serial:
+        line["value_single_stream"] = {"value": serial["value"], "ms_per_step": serial["ms_per_step"], "steps": serial["steps"],
+                                       "what": "the same frames issued back to back on ONE stream (no overlap between frames); "
+                                               "roofline.kernel_ms and kernel_share_of_step are measured in this pass"}
     if e2e_cam is not None:
         line["e2e_camera"] = e2e_cam
     if parity is not None:

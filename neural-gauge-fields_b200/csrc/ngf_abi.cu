@@ -97,6 +97,7 @@ static void free_all(NgfField_* h) {
   ngf_train_free(h->train);
   h->train = nullptr;
   cudaFree(h->acc_ws); cudaFree(h->counters); cudaFree(h->queue);
+  for (auto& w : h->sws) { cudaFree(w.counters); cudaFree(w.queue); cudaFree(w.acc_ws); }
   free_chunks(h);
 }
 
@@ -621,6 +622,53 @@ int ngf_render_dev(NgfField h, const float* rays, long long n_rays, int ray_stri
 
 extern "C" {
 
+// The workspace of a device-resident render issued on stream `st` (see NgfField_::StreamWs).
+struct WsRef {
+  unsigned int* counters;
+  QEntry** queue;
+  long long* queue_cap;
+  float** acc_ws;
+  long long* acc_cap;
+};
+
+static int ws_for_stream(NgfField h, cudaStream_t st, WsRef* out) {
+  constexpr int kSlots = (int)(sizeof(h->sws) / sizeof(h->sws[0]));
+  int slot = -1, free_slot = -1, oldest = 0;
+  for (int i = 0; i < kSlots; ++i) {
+    if (h->sws[i].used && h->sws[i].stream == st) { slot = i; break; }
+    if (!h->sws[i].used && free_slot < 0) free_slot = i;
+    if (h->sws[i].last_use < h->sws[oldest].last_use) oldest = i;
+  }
+  if (slot < 0) {
+    slot = free_slot >= 0 ? free_slot : oldest;
+    NgfField_::StreamWs& w = h->sws[slot];
+    if (w.used) CU(cudaStreamSynchronize(w.stream));          // recycled: its last render must be done with the queue
+    w.stream = st; w.used = true;
+    if (slot > 0 && !w.counters) {
+      CU(cudaMalloc(reinterpret_cast<void**>(&w.counters), kCounterBytes));
+      CU(cudaMemset(w.counters, 0, kCounterBytes));
+    }
+  }
+  NgfField_::StreamWs& w = h->sws[slot];
+  w.last_use = ++h->sws_clock;
+  if (slot == 0) *out = WsRef{h->counters, &h->queue, &h->queue_cap, &h->acc_ws, &h->acc_cap};
+  else *out = WsRef{w.counters, &w.queue, &w.queue_cap, &w.acc_ws, &w.acc_cap};
+  h->stats_counters = out->counters;
+  return NGF_OK;
+}
+
+static int ws_acc(const WsRef& ws, long long n_rays, cudaStream_t st, float** acc) {
+  if (*ws.acc_cap < n_rays) {
+    CU(cudaStreamSynchronize(st));
+    cudaFree(*ws.acc_ws);
+    *ws.acc_ws = nullptr; *ws.acc_cap = 0;
+    CU(dev_alloc(ws.acc_ws, (size_t)n_rays));
+    *ws.acc_cap = n_rays;
+  }
+  *acc = *ws.acc_ws;
+  return NGF_OK;
+}
+
 static int field_render(NgfField h, const float* rays_dev, int64_t n_rays, int32_t ray_stride, int32_t n_samples,
                         int32_t white_bg, int32_t tile_w, const float* jitter_dev, float* rgb_dev, float* depth_dev,
                         float* acc_dev, int32_t mlp_impl, void* stream) {
@@ -633,19 +681,13 @@ static int field_render(NgfField h, const float* rays_dev, int64_t n_rays, int32
   DeviceGuard g(h->device);
   if (!g.ok) return fail(NGF_ECUDA, "cannot select device %d", h->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  WsRef ws;
+  int rc = ws_for_stream(h, st, &ws);
+  if (rc) return rc;
   float* acc = acc_dev;
-  if (!acc) {
-    if (h->acc_cap < n_rays) {
-      CU(cudaStreamSynchronize(st));
-      cudaFree(h->acc_ws);
-      h->acc_ws = nullptr; h->acc_cap = 0;
-      CU(dev_alloc(&h->acc_ws, (size_t)n_rays));
-      h->acc_cap = n_rays;
-    }
-    acc = h->acc_ws;
-  }
+  if (!acc && (rc = ws_acc(ws, n_rays, st, &acc))) return rc;
   return ngf_render_dev(h, rays_dev, n_rays, ray_stride, n_samples, white_bg, tile_w, rgb_dev, depth_dev, acc,
-                    h->counters, &h->queue, &h->queue_cap, mlp_impl, st, nullptr, jitter_dev);
+                        ws.counters, ws.queue, ws.queue_cap, mlp_impl, st, nullptr, jitter_dev);
 }
 
 int ngf_field_render(NgfField h, const float* rays_dev, int64_t n_rays, int32_t ray_stride, int32_t n_samples,
@@ -877,19 +919,13 @@ int ngf_field_render_camera(NgfField h, const NgfCamera* camera, int32_t n_sampl
   if (!g.ok) return fail(NGF_ECUDA, "cannot select device %d", h->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long n_rays = (long long)cam.W * cam.H;
+  WsRef ws;
+  rc = ws_for_stream(h, st, &ws);
+  if (rc) return rc;
   float* acc = acc_dev;
-  if (!acc) {
-    if (h->acc_cap < n_rays) {
-      CU(cudaStreamSynchronize(st));
-      cudaFree(h->acc_ws);
-      h->acc_ws = nullptr; h->acc_cap = 0;
-      CU(dev_alloc(&h->acc_ws, (size_t)n_rays));
-      h->acc_cap = n_rays;
-    }
-    acc = h->acc_ws;
-  }
-  return ngf_render_dev(h, nullptr, n_rays, 6, n_samples, white_bg, cam.W, rgb_dev, depth_dev, acc, h->counters, &h->queue,
-                    &h->queue_cap, mlp_impl, st, &cam);
+  if (!acc && (rc = ws_acc(ws, n_rays, st, &acc))) return rc;
+  return ngf_render_dev(h, nullptr, n_rays, 6, n_samples, white_bg, cam.W, rgb_dev, depth_dev, acc, ws.counters, ws.queue,
+                        ws.queue_cap, mlp_impl, st, &cam);
 }
 
 int ngf_field_render_camera_host_async(NgfField h, const NgfCamera* camera, int32_t n_samples, int32_t white_bg,
@@ -970,7 +1006,7 @@ int ngf_field_stats(NgfField h, NgfStats* out, void* stream) {
   DeviceGuard g(h->device);
   unsigned long long s[5];
   CU(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
-  CU(cudaMemcpy(s, h->counters + 2, sizeof(s), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(s, (h->stats_counters ? h->stats_counters : h->counters) + 2, sizeof(s), cudaMemcpyDeviceToHost));
   out->rays = 0;
   out->samples_in_box = s[0]; out->samples_density = s[1]; out->samples_colour = s[2]; out->mlp_tiles = s[3];
   out->direct_patches = s[4];

@@ -40,6 +40,7 @@ namespace {
 constexpr int kMaxWorld = 16;
 constexpr int kMaxSlots = 4;
 constexpr int kCommStreams = 2;
+constexpr int kCompStreams = 3;          // compute streams of the host pipelines: batch k renders on stream (k % n_slots) % 3
 constexpr int kMaxFrames = 64;                // frames per camera batch
 constexpr size_t kFlagBytes = 4096;           // arrived [kMaxSlots][kMaxWorld] u32 @0, freed [kMaxSlots][kMaxWorld] u32 @1024
 
@@ -108,7 +109,7 @@ struct NgfComm_ {
   uint32_t* err_host = nullptr;               // pinned, mapped
   uint32_t* err_dev = nullptr;
   long long timeout_cycles = 0;
-  cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr, s_comm[kCommStreams] = {};
+  cudaStream_t s_in = nullptr, s_comp[kCompStreams] = {}, s_out = nullptr, s_comm[kCommStreams] = {};
   struct Slot {
     cudaEvent_t ev_in = nullptr;              // rays uploaded (host path)
     cudaEvent_t ev_rendered = nullptr;        // my rows are in my frame buffer
@@ -121,14 +122,16 @@ struct NgfComm_ {
     long long u8_cap = 0;
     unsigned long long ticket = 0;            // ticket occupying the slot (0 = none)
     bool released = true;
+    // render workspace of the slot: batches in different slots may be rendered on different streams and overlap (the
+    // march of one beside the colour pass of another)
+    float *rgb = nullptr, *depth = nullptr, *acc = nullptr;
+    unsigned int* counters = nullptr;
+    QEntry* queue = nullptr;
+    long long queue_cap = 0;
   } slot[kMaxSlots];
   long long rays_cap = 0;
   int rays_stride = 0;
-  // render workspace (one set: renders are serialised on one stream at a time)
-  float *rgb = nullptr, *depth = nullptr, *acc = nullptr;
-  unsigned int* counters = nullptr;
-  QEntry* queue = nullptr;
-  long long queue_cap = 0;
+  bool ws_ready = false;
   unsigned long long next_step = 0;
 
   float4* frame(int q, int s) const { return reinterpret_cast<float4*>(peer[q] + kFlagBytes + (size_t)s * frame_bytes); }
@@ -156,12 +159,12 @@ void comm_destroy(NgfComm_* c) {
     if (s.ev_consumed) cudaEventDestroy(s.ev_consumed);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     cudaFree(s.rays); cudaFree(s.poses); cudaFree(s.u8);
+    cudaFree(s.rgb); cudaFree(s.depth); cudaFree(s.acc); cudaFree(s.counters); cudaFree(s.queue);
   }
   if (c->s_in) cudaStreamDestroy(c->s_in);
-  if (c->s_comp) cudaStreamDestroy(c->s_comp);
+  for (auto& st : c->s_comp) if (st) cudaStreamDestroy(st);
   if (c->s_out) cudaStreamDestroy(c->s_out);
   for (auto& s : c->s_comm) if (s) cudaStreamDestroy(s);
-  cudaFree(c->rgb); cudaFree(c->depth); cudaFree(c->acc); cudaFree(c->counters); cudaFree(c->queue);
   cudaFree(c->base);
   if (c->err_host) cudaFreeHost(c->err_host);
   delete c;
@@ -227,6 +230,8 @@ int render_and_push(NgfField f, NgfComm_* c, int s, unsigned long long k, const 
   // (b) the copies that pushed them to the peers have finished reading them
   CU(cudaStreamWaitEvent(st, sl.ev_consumed, 0));
   for (int j = 0; j < kCommStreams; ++j) CU(cudaStreamWaitEvent(st, sl.ev_sent[j], 0));
+  // (c) the slot's render workspace: its previous batch may have been rendered on another stream
+  CU(cudaStreamWaitEvent(st, sl.ev_rendered, 0));
   ShardOut so{};
   so.block = c->block; so.rank = c->rank; so.world = c->world;
   so.dst[so.n_dst++] = c->frame(c->rank, s);
@@ -236,8 +241,8 @@ int render_and_push(NgfField f, NgfComm_* c, int s, unsigned long long k, const 
     if (want_freed) { int rc = launch_wait(c, local_flags(c, s, false), want_freed, st); if (rc) return rc; }
     for (int d = 1; d < c->world; ++d) so.dst[so.n_dst++] = c->frame((c->rank + d) % c->world, s);
   }
-  int rc = ngf_render_dev(f, rays_dev, n_local, ray_stride, n_samples, white_bg, tile_w, c->rgb, c->depth, c->acc,
-                          c->counters, &c->queue, &c->queue_cap, mlp_impl, st, cam, nullptr, &so);
+  int rc = ngf_render_dev(f, rays_dev, n_local, ray_stride, n_samples, white_bg, tile_w, sl.rgb, sl.depth, sl.acc,
+                          sl.counters, &sl.queue, &sl.queue_cap, mlp_impl, st, cam, nullptr, &so);
   if (rc) return rc;
   if (c->mode == NGF_COMM_STORE && c->world > 1) {
     PeerList pl{};
@@ -280,13 +285,17 @@ int render_and_push(NgfField f, NgfComm_* c, int s, unsigned long long k, const 
 }
 
 int ensure_workspace(NgfComm_* c, long long n_local) {
-  if (c->rgb) return NGF_OK;
+  if (c->ws_ready) return NGF_OK;
   const size_t n = (size_t)(n_local > 0 ? n_local : 1);
-  CU(cudaMalloc(reinterpret_cast<void**>(&c->rgb), n * 3 * sizeof(float)));
-  CU(cudaMalloc(reinterpret_cast<void**>(&c->depth), n * sizeof(float)));
-  CU(cudaMalloc(reinterpret_cast<void**>(&c->acc), n * sizeof(float)));
-  CU(cudaMalloc(reinterpret_cast<void**>(&c->counters), kCounterBytes));
-  CU(cudaMemset(c->counters, 0, kCounterBytes));
+  for (int i = 0; i < c->n_slots; ++i) {
+    NgfComm_::Slot& sl = c->slot[i];
+    CU(cudaMalloc(reinterpret_cast<void**>(&sl.rgb), n * 3 * sizeof(float)));
+    CU(cudaMalloc(reinterpret_cast<void**>(&sl.depth), n * sizeof(float)));
+    CU(cudaMalloc(reinterpret_cast<void**>(&sl.acc), n * sizeof(float)));
+    CU(cudaMalloc(reinterpret_cast<void**>(&sl.counters), kCounterBytes));
+    CU(cudaMemset(sl.counters, 0, kCounterBytes));
+  }
+  c->ws_ready = true;
   return NGF_OK;
 }
 
@@ -343,7 +352,7 @@ int ngf_comm_init(int32_t rank, int32_t world, int32_t device, int64_t n_rays, i
   if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&c->err_host), 64, cudaHostAllocMapped);
   if (e == cudaSuccess) { memset(c->err_host, 0, 64); e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->err_dev), c->err_host, 0); }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking);
+  for (auto& st : c->s_comp) if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
   for (int j = 0; j < kCommStreams && e == cudaSuccess; ++j) e = cudaStreamCreateWithFlags(&c->s_comm[j], cudaStreamNonBlocking);
   for (int s = 0; s < n_slots && e == cudaSuccess; ++s) {
@@ -509,8 +518,9 @@ int ngf_field_render_sharded_host_async(NgfField f, NgfComm c, const float* rays
   if (n_local > 0)
     CU(cudaMemcpyAsync(sl.rays, rays_local_host, (size_t)n_local * ray_stride * sizeof(float), cudaMemcpyHostToDevice, c->s_in));
   CU(cudaEventRecord(sl.ev_in, c->s_in));
-  CU(cudaStreamWaitEvent(c->s_comp, sl.ev_in, 0));
-  rc = render_and_push(f, c, s, k, sl.rays, n_local, ray_stride, n_samples, white_bg, tile_w, mlp_impl, c->s_comp);
+  cudaStream_t comp = c->s_comp[s % kCompStreams];
+  CU(cudaStreamWaitEvent(comp, sl.ev_in, 0));
+  rc = render_and_push(f, c, s, k, sl.rays, n_local, ray_stride, n_samples, white_bg, tile_w, mlp_impl, comp);
   if (rc) return rc;
   // download: my rows (local event) + everybody else's (flags), then give the buffer back to the peers
   CU(cudaStreamWaitEvent(c->s_out, sl.ev_rendered, 0));
@@ -599,10 +609,11 @@ int ngf_field_render_sharded_camera_u8_host_async(NgfField f, NgfComm c, const N
   CU(cudaStreamWaitEvent(c->s_in, sl.ev_rendered, 0));
   CU(cudaMemcpyAsync(sl.poses, poses_host, (size_t)n_frames * 12 * sizeof(float), cudaMemcpyHostToDevice, c->s_in));
   CU(cudaEventRecord(sl.ev_in, c->s_in));
-  CU(cudaStreamWaitEvent(c->s_comp, sl.ev_in, 0));
+  cudaStream_t comp = c->s_comp[s % kCompStreams];
+  CU(cudaStreamWaitEvent(comp, sl.ev_in, 0));
   cam.poses = sl.poses;
   const int tile_w = (c->block % (4 * cam.W) == 0) ? cam.W : 0;
-  rc = render_and_push(f, c, s, k, nullptr, c->n_local, 6, n_samples, white_bg, tile_w, mlp_impl, c->s_comp, &cam);
+  rc = render_and_push(f, c, s, k, nullptr, c->n_local, 6, n_samples, white_bg, tile_w, mlp_impl, comp, &cam);
   if (rc) return rc;
   CU(cudaStreamWaitEvent(c->s_out, sl.ev_rendered, 0));
   if ((rc = launch_wait(c, local_flags(c, s, true), (uint32_t)(k + 1), c->s_out))) return rc;

@@ -54,6 +54,22 @@ struct NgfField_ {
   float* acc_ws = nullptr;
   long long acc_cap = 0;
   unsigned int* counters = nullptr;   // [0] tile counter, [1] queue count, [2..9] = 4 x u64 stats
+  // ngf_field_render / _jitter / _camera keep one workspace (colour queue, counters, acc scratch) per caller stream, so
+  // renders issued on different streams of one handle are independent and may overlap (the march of one frame beside the
+  // colour pass of another).  Slot 0 is the handle's own workspace above; a slot whose stream has not been seen for the
+  // longest is recycled (after synchronising that stream) when more than kStreamSlots streams are used.
+  struct StreamWs {
+    cudaStream_t stream = nullptr;
+    bool used = false;
+    unsigned long long last_use = 0;
+    unsigned int* counters = nullptr;
+    ngf::QEntry* queue = nullptr;
+    long long queue_cap = 0;
+    float* acc_ws = nullptr;
+    long long acc_cap = 0;
+  } sws[4];
+  unsigned long long sws_clock = 0;
+  const unsigned int* stats_counters = nullptr;   // counters of the most recent device render (ngf_field_stats)
   ngf::QEntry* queue = nullptr;            // colour work items of the device-resident path
   long long queue_cap = 0;
   // kernel timing (ngf_field_timing_*)

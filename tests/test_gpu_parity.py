@@ -722,3 +722,32 @@ def test_sharded_camera_batches():
             assert (frames[r].cpu() - ref).abs().max() < 1e-5, (k, r)
     for h in hs:
         lib.ngf_comm_free(h)
+
+
+def test_renders_on_different_streams_are_independent():
+    """ngf_field_render keeps one workspace (colour queue, counters) per caller stream: frames issued on several CUDA
+    streams of one field overlap on the device and each equals the same frame rendered alone (up to the order of the fp32
+    atomic adds, < 1e-5); more streams than workspace slots (4) recycle the least recently used one."""
+    from ngf_b200 import synth
+    case = K.Case("c2_hull", kind="hull", config="C2", n_samples=192)
+    state, kw, occ, rays0 = K.build_inputs(case)
+    f, rgb0, depth0 = _render_cuda(case, state, kw, occ, rays0, image_width=800)
+    frames = [rays0.cuda()] + [synth.config_rays("C2", p).cuda() for p in (1, 2, 3, 4, 5)]
+    fk = forward_kwargs(case)
+    alone = [f(r, white_bg=True, N_samples=192, image_width=800, **fk) for r in frames]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(6)]
+    for n_streams in (3, 6):
+        outs = [None] * 12
+        for st in streams:
+            st.wait_stream(torch.cuda.current_stream())
+        for i in range(12):
+            with torch.cuda.stream(streams[i % n_streams]):
+                outs[i] = f(frames[i % 6], white_bg=True, N_samples=192, image_width=800, **fk)
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
+        torch.cuda.synchronize()
+        for i in range(12):
+            assert (outs[i]["rgb_map"] - alone[i % 6]["rgb_map"]).abs().max() < 1e-5, (n_streams, i)
+            assert (outs[i]["depth_map"] - alone[i % 6]["depth_map"]).abs().max() < 1e-5, (n_streams, i)
+    assert (alone[0]["rgb_map"].cpu() - rgb0).abs().max() < 1e-5
