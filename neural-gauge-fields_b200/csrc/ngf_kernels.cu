@@ -212,14 +212,18 @@ __global__ void __launch_bounds__(kThreads, 2) ngf_colour_kernel(const __grid_co
   const float4* src = reinterpret_cast<const float4*>(a.queue);
   uint32_t phase = 0;
   uint32_t done = 0;
+  // half a work item (16 bytes) per thread; the items of the next tile are requested before this tile is processed, so
+  // their global-memory latency hides under the tile instead of standing at the head of every iteration
+  auto fetch = [&](uint32_t tile) {
+    const uint32_t first = tile * kTileM, item = first + (threadIdx.x >> 1);
+    float4 v = (threadIdx.x & 1) ? make_float4(0.f, 0.f, 0.f, __int_as_float(-1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (item < count) v = __ldg(src + (size_t)first * 2 + threadIdx.x);
+    return v;
+  };
+  float4 v = fetch(blockIdx.x);
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++done) {
-    const uint32_t first = tile * kTileM;
-    {
-      const uint32_t item = first + (threadIdx.x >> 1);
-      float4 v = (threadIdx.x & 1) ? make_float4(0.f, 0.f, 0.f, __int_as_float(-1)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (item < count) v = __ldg(src + (size_t)first * 2 + threadIdx.x);
-      q[threadIdx.x] = v;
-    }
+    q[threadIdx.x] = v;
+    if (tile + gridDim.x < n_tiles) v = fetch(tile + gridDim.x);
     __syncthreads();
     mlp_tile<V, IMPL, true>(f, smem, 0u, phase, a.rays + 3, a.ray_stride, a.rgb, a.cam_on ? &a.cam : nullptr);
   }

@@ -1,0 +1,4 @@
+# round 2 final evidence on one GPU: bench line, reference arm, ncu launch list, ncu --set full (hull + dense), sanitizer
+bash scripts/gpu_r2_final.sh
+bash scripts/gpu_r2_prof.sh
+bash scripts/gpu_sanitize_r2.sh

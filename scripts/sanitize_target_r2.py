@@ -78,3 +78,25 @@ m.load_state_dict(state)
 o = m(campos.cuda(), raydir[:, :300].cuda(), bg.cuda(), noise=noise[:, :300].cuda())
 torch.cuda.synchronize()
 print("neutex sphere", float(o["color"].mean()), m.last_valid_samples())
+# later in round 2: seeded jitter, the fp32 NeuTex path and the self-check; renders of one field on three streams
+o2 = m(campos.cuda(), raydir[:, :300].cuda(), bg.cuda(), seed=5)
+nz = m.noise_for(5, 300)
+m.set_precision("fp32")
+o3 = m(campos.cuda(), raydir[:, :300].cuda(), bg.cuda(), noise=nz)
+rep = m.self_check(512, seed=1)
+torch.cuda.synchronize()
+print("neutex seeded / fp32 / self-check", float((o2["color"] - o3["color"]).abs().max()), rep["rgb_max"])
+case = K.CASE_BY_NAME["tp_hull_c1"]
+state, kw, occ, rays = K.build_inputs(case)
+f = build_cuda_field(case, state, kw, occ)
+r = rays.cuda()
+alone = f(r, white_bg=True, N_samples=case.n_samples, **forward_kwargs(case))["rgb_map"]
+streams = [torch.cuda.Stream() for _ in range(3)]
+outs = []
+for st in streams:
+    st.wait_stream(torch.cuda.current_stream())
+for i in range(6):
+    with torch.cuda.stream(streams[i % 3]):
+        outs.append(f(r, white_bg=True, N_samples=case.n_samples, **forward_kwargs(case))["rgb_map"])
+torch.cuda.synchronize()
+print("multi-stream renders ok", max(float((o - alone).abs().max()) for o in outs))
