@@ -153,6 +153,12 @@ void ngf_field_free(NgfField f);
  *   rgb_dev    [R][3] fp32 out (rgb_map), depth_dev [R] fp32 out (depth_map); acc_dev [R] fp32 out or NULL
  *   tile_w     0, or the image width when rays are the row-major pixels of an image: lets the kernel map
  *              warps to 8x4 pixel blocks for texel locality (results do not depend on it)
+ *   stream     the cudaStream_t the kernels are enqueued on (asynchronous).  The handle keeps one workspace (colour queue,
+ *              counters) per caller stream, so frames issued on different streams are independent and overlap on the
+ *              device — on B200 three streams render independent 640 000-ray frames in 0.29 ms each against 0.38 ms back
+ *              to back on one.  Up to four streams are remembered; a fifth recycles the least recently used workspace
+ *              after synchronising its stream.  The colour queue of a workspace is sized for the worst case of a call,
+ *              min(n_rays * n_samples * 32 B, NGF_QUEUE_MIB (default 4096) MiB), allocated on first use.
  */
 int ngf_field_render(NgfField f, const float* rays_dev, int64_t n_rays, int32_t ray_stride, int32_t n_samples,
                      int32_t white_bg, int32_t tile_w, float* rgb_dev, float* depth_dev, float* acc_dev,
