@@ -340,7 +340,9 @@ __device__ __forceinline__ void mlp_gather_at(const FieldDev& f, const QEntry* _
       }
     }
   } else {
-    // items (row m, 8-channel chunk): the phase code is shared by the three planes
+    // Phase 1 (lanes = consecutive rows, one 8-channel chunk per warp iteration, so the phase code below is warp-uniform):
+    // the eight fp32 phase factors of item (row m, chunk) are parked in the operand slots that the same item fills in phase
+    // 2 for planes 0 and 1 — 16 bytes each at (plane * 9 + chunk, m) — so the table needs no shared memory of its own
     for (int it = tid; it < kTileM * 9; it += NT) {
       const int m = it & (kTileM - 1), chunk = it >> 7;
       const QEntry& e = q[(head + m) & (kQueueCap - 1)];
@@ -348,6 +350,16 @@ __device__ __forceinline__ void mlp_gather_at(const FieldDev& f, const QEntry* _
       float pe[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) pe[k] = f.infoinv ? phase_value<12>(xyz, chunk * 8 + k) : 1.f;
+      *reinterpret_cast<float4*>(A + (size_t)chunk * L::kLboA + m * 16) = make_float4(pe[0], pe[1], pe[2], pe[3]);
+      *reinterpret_cast<float4*>(A + (size_t)(9 + chunk) * L::kLboA + m * 16) = make_float4(pe[4], pe[5], pe[6], pe[7]);
+    }
+    sync();
+    // Phase 2: nine consecutive lanes take the nine 16-byte chunks of the SAME texel (144 contiguous bytes per tap), as in
+    // the TriPlane gather.  An item reads its own phase factors and then overwrites exactly those slots, and with the padded
+    // K-group stride the stores of a quarter warp fall into banks (chunk + m) mod 8 = it mod 8: conflict-free.
+    for (int it = tid; it < kTileM * 9; it += NT) {
+      const int m = it / 9, chunk = it - 9 * m;
+      const QEntry& e = q[(head + m) & (kQueueCap - 1)];
       // all twelve texel loads of the item are requested before the first blend (the gather is latency bound)
       Taps t[3];
       uint4 raw[3][4];
@@ -359,6 +371,9 @@ __device__ __forceinline__ void mlp_gather_at(const FieldDev& f, const QEntry* _
         for (int k = 0; k < 4; ++k)
           raw[pl][k] = __ldg(reinterpret_cast<const uint4*>(P.app + (size_t)t[pl].off[k] * AC + chunk * 8));
       }
+      const float4 pe_lo = *reinterpret_cast<const float4*>(A + (size_t)chunk * L::kLboA + m * 16);
+      const float4 pe_hi = *reinterpret_cast<const float4*>(A + (size_t)(9 + chunk) * L::kLboA + m * 16);
+      const float pe[8] = {pe_lo.x, pe_lo.y, pe_lo.z, pe_lo.w, pe_hi.x, pe_hi.y, pe_hi.z, pe_hi.w};
 #pragma unroll
       for (int pl = 0; pl < 3; ++pl) {
         float v[8];
