@@ -43,8 +43,7 @@ struct TmaSmem {                                           // shared-memory carv
   static constexpr uint32_t offW2 = offW1 + kW1Bytes;
   static constexpr uint32_t offA = offW2 + kW2Bytes;
   static constexpr uint32_t offH = offA;
-  static constexpr uint32_t offTail = offA + kABytes;
-  static constexpr uint32_t offQueue = offTail + ((kTailFloats * 4 + 15) / 16) * 16;
+  static constexpr uint32_t offQueue = offA + kABytes;
   static constexpr uint32_t offPart = offQueue + kQueueCap * sizeof(QEntry);
   static constexpr uint32_t offTap = offPart + kTileM * 16;                       // TapC [3][128]
   static constexpr uint32_t offBox = ((offTap + 3 * kTileM * 16 + 127) / 128) * 128;   // 12 patch slots
@@ -202,8 +201,6 @@ __global__ void __launch_bounds__(kThreads, 2) ngf_colour_tma_kernel(const __gri
     const uint4* s2 = reinterpret_cast<const uint4*>(f.w2p);
     uint4* d2 = reinterpret_cast<uint4*>(smem + L::offW2);
     for (int i = tid; i < (int)(L::kW2Bytes / 16); i += kThreads) d2[i] = __ldg(s2 + i);
-    float* dt = reinterpret_cast<float*>(smem + L::offTail);
-    for (int i = tid; i < kTailFloats; i += kThreads) dt[i] = __ldg(f.tail + i);
     if (tid == 0) {
       ctl->tmem_base = 0;
       ctl->staged = 0;

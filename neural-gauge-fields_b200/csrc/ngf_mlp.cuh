@@ -162,8 +162,8 @@ struct MlpSmem {
   static constexpr uint32_t offW2 = offW1 + kW1Bytes;
   static constexpr uint32_t offA = offW2 + kW2Bytes;
   static constexpr uint32_t offH = kAliasH ? offA : offA + kABytes;
-  static constexpr uint32_t offTail = (kAliasH ? offA + kABytes : offH + kHBytes);
-  static constexpr uint32_t offQueue = offTail + ((kTailFloats * 4 + 15) / 16) * 16;
+  // (the layer-3 constants are read from the kernel parameters, FieldDev::tail_c: no shared-memory copy)
+  static constexpr uint32_t offQueue = (kAliasH ? offA + kABytes : offH + kHBytes);
   static constexpr uint32_t offPart = offQueue + kQueueCap * sizeof(QEntry);   // layer-3 partial sums [128][4]
   static constexpr uint32_t offCtl = offPart + kTileM * 16;
   static constexpr uint32_t kCtlBytes = 64;
@@ -204,8 +204,6 @@ __device__ __forceinline__ void mlp_setup(const FieldDev& f, uint8_t* smem) {
   const uint4* s2 = reinterpret_cast<const uint4*>(f.w2p);
   uint4* d2 = reinterpret_cast<uint4*>(smem + L::offW2);
   for (int i = tid; i < (int)(L::kW2Bytes / 16); i += kThreads) d2[i] = __ldg(s2 + i);
-  float* dt = reinterpret_cast<float*>(smem + L::offTail);
-  for (int i = tid; i < kTailFloats; i += kThreads) dt[i] = __ldg(f.tail + i);
   // zero the A tile once: K padding chunks are never written again
   uint4* da = reinterpret_cast<uint4*>(smem + L::offA);
   for (int i = tid; i < (int)(L::kABytes / 16); i += kThreads) da[i] = make_uint4(0, 0, 0, 0);

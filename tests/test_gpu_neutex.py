@@ -182,6 +182,9 @@ def test_neutex_jitter_drawn_on_the_device():
     assert (a["color"].cpu() - o_c).abs().max() < TOL and (a["transmittance"].cpu() - o_t).abs().max() < TOL
     assert not torch.equal(m(*args, seed=1235)["color"], a["color"])
     assert torch.equal(m.noise_for(1234, 100, first_ray=50), nz[:, 50:150])
+    from oracle import philox                                          # numpy Philox 4x32-10, pinned to the Random123 vectors
+    assert np.array_equal(nz[0].cpu().numpy(), philox.neutex_noise(1234, 0, R, 64))
+    assert np.array_equal(m.noise_for((7 << 32) | 5, 9, first_ray=1 << 30)[0].cpu().numpy(), philox.neutex_noise((7 << 32) | 5, 1 << 30, 9, 64))
     u = m.noise_for(7, 200000).flatten()
     assert float(u.min()) >= 0.0 and float(u.max()) < 1.0
     assert abs(float(u.mean()) - 0.5) < 1e-3 and abs(float(u.var()) - 1 / 12) < 1e-3
