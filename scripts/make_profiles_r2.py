@@ -62,7 +62,9 @@ def run(*a):
 
 
 traffic = json.load(open(os.path.join(P, "traffic.json")))
-for regime, target in (("hull", "hull 20"), ("dense", "dense 3")):
+for regime, target in (("hull", "hull 20"), ("dense", "dense 3"), ("infoinv", "infoinv 6")):
+    if not os.path.exists(os.path.join(G, f"r2_prof_{regime}.ncu-rep")):
+        continue
     rep = os.path.join(G, f"r2_prof_{regime}.ncu-rep")
     summ = run("scripts/ncu_summary.py", rep)
     txt = [f"# ncu --set full --clock-control none --import-source on, march + colour kernels of the {regime} regime, one frame of",
