@@ -642,7 +642,12 @@ static int ws_for_stream(NgfField h, cudaStream_t st, WsRef* out) {
   if (slot < 0) {
     slot = free_slot >= 0 ? free_slot : oldest;
     NgfField_::StreamWs& w = h->sws[slot];
-    if (w.used) CU(cudaStreamSynchronize(w.stream));          // recycled: its last render must be done with the queue
+    if (w.used && cudaStreamSynchronize(w.stream) != cudaSuccess) {
+      // recycled: its last render must be done with the queue.  The caller may have destroyed that stream since (CUDA then
+      // finishes its work on its own): fall back to a device-wide wait
+      cudaGetLastError();
+      CU(cudaDeviceSynchronize());
+    }
     w.stream = st; w.used = true;
     if (slot > 0 && !w.counters) {
       CU(cudaMalloc(reinterpret_cast<void**>(&w.counters), kCounterBytes));
